@@ -1,0 +1,144 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the NumPy oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): stamped Jacobians 1e-12 relative, per-NR-solve voltages 1e-9
+relative, waveforms 1e-6 RMS relative with the same accepted-step sequence.  Vector parity metric:
+max_i |a_i - b_i| / max(|b_i|, floor).
+"""
+import numpy as np
+import pytest
+
+from vajax_b200.benchmarks import circuits
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b, floor):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def engines(circ, bundles, limiting=False, graph=False):
+    from oracle.engine import OracleEngine
+    from vajax_b200.analysis.engine import B200Engine
+
+    o = OracleEngine(circ, bundles, use_device_limiting=limiting)
+    o.setup()
+    g = B200Engine(circ, bundles, use_device_limiting=limiting, use_device_graph=graph).prepare()
+    return o, g
+
+
+CIRCUITS = {
+    "rc": lambda: circuits.rc_circuit(stop=2e-4),
+    "clipper": lambda: circuits.diode_clipper_circuit(stop=4e-4),
+    "ring": lambda: circuits.ring_circuit(stop=3e-9),
+    "mul3": lambda: circuits.multiplier_circuit(3, stop=3e-10),
+}
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+@pytest.mark.parametrize("limiting", [False, True])
+def test_setup_and_build_system_parity(name, limiting, bundles):
+    circ = CIRCUITS[name]()
+    o, g = engines(circ, bundles, limiting)
+    assert g.n_total == o.n_total and g.nse == o.nse and g.n_aug == o.n_aug
+    assert np.array_equal(g.csr_indptr, o.csr_indptr) and np.array_equal(g.csr_indices, o.csr_indices)
+    assert g.total_limit_states == o.total_limit_states
+    rng = np.random.default_rng(7)
+    X = np.zeros(o.n_total + o.n_vs)
+    X[1:] = rng.uniform(-0.3, 1.2, X.size - 1)
+    Qp, dq, q2 = (rng.normal(0, 1e-13, o.n_unknowns) for _ in range(3))
+    vs, isv = o.eval_sources(2.5e-10)
+    ls = rng.uniform(0, 0.7, o.total_limit_states)
+    for (c0, c1, d1, c2, it) in [(0.0, 0.0, 0.0, 0.0, 0), (2e12, -2e12, -1.0, 0.0, 1), (1.5e9, -2e9, 0.0, 0.5e9, 3)]:
+        ro = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, ls, it)
+        rg = g.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, ls, it)
+        names = ["csr", "f", "Q", "Ivs", "limit", "maxres"]
+        floors = [1e-12, 1e-12, 1e-24, 1e-12, 1e-6, 1e-12]
+        for nm, a, b, fl in zip(names, rg, ro, floors):
+            scale = max(np.max(np.abs(b)) if b.size else 0.0, fl)
+            err = relerr(a, b, max(fl, 1e-13 * scale))
+            assert err < 1e-12 if nm in ("csr",) else err < 1e-10, (name, nm, err)
+    g.close()
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+def test_lu_solve_against_superlu(name, bundles):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    circ = CIRCUITS[name]()
+    o, g = engines(circ, bundles)
+    rng = np.random.default_rng(3)
+    X = np.zeros(o.n_total + o.n_vs)
+    X[1:o.n_total] = rng.uniform(0, 1.2, o.n_total - 1)
+    if len(o.noi_indices):
+        X[o.noi_indices] = 0
+    vs, isv = o.eval_sources(1e-10)
+    csr, f, *_ = o.build_system(X, vs, isv, np.zeros(o.n_unknowns), 1e12)
+    if len(o.noi_res_idx):
+        csr[o.noi_row_mask] = 0
+        csr[o.noi_col_mask] = 0
+        csr[o.noi_diag] = 1
+    A = sp.csr_matrix((csr, o.csr_indices, o.csr_indptr), shape=(o.n_aug, o.n_aug))
+    for k in range(3):
+        b = rng.normal(size=o.n_aug)
+        x = g.lu_solve(csr * (1.0 + 0.1 * k), b)
+        xr = spla.splu((A * (1.0 + 0.1 * k)).tocsc()).solve(b)
+        assert relerr(x, xr, 1e-9 * np.max(np.abs(xr))) < 1e-9
+        r = A @ x * (1.0 + 0.1 * k) - b
+        assert np.max(np.abs(r)) < 1e-9 * max(1.0, np.max(np.abs(b)))
+    st = g.lu_stats()
+    assert st["n"] == o.n_aug and st["nnz_lu"] >= o.nse
+    g.close()
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+@pytest.mark.parametrize("limiting", [False, True])
+def test_nr_solve_parity(name, limiting, bundles):
+    circ = CIRCUITS[name]()
+    o, g = engines(circ, bundles, limiting)
+    nu = o.n_unknowns
+    X0 = np.zeros(o.n_total + o.n_vs)
+    X0[:o.n_total] = o.init_mid_rail()
+    vs, isv = o.eval_sources(0.0)
+    ro = o.nr_solve(X0, vs, isv, np.zeros(nu), 0.0, 1e-12)
+    rg = g.nr_solve(X0, vs, isv, np.zeros(nu), 0.0, 1e-12)
+    assert rg[1] == ro[1] and rg[2] == ro[2], (rg[1], ro[1], rg[2], ro[2])
+    assert relerr(rg[0], ro[0], 1e-6) < 1e-9
+    assert relerr(rg[4], ro[4], max(1e-24, 1e-9 * np.max(np.abs(ro[4])))) < 1e-8
+    # a transient-style solve from the DC point
+    c0 = 2.0 / 1e-11
+    r2o = o.nr_solve(ro[0], vs, isv, ro[4], c0, 1e-12, 0.0, -c0, -1.0, np.zeros(nu), 0.0, None, ro[7], None)
+    r2g = g.nr_solve(ro[0], vs, isv, ro[4], c0, 1e-12, 0.0, -c0, -1.0, np.zeros(nu), 0.0, None, ro[7], None)
+    assert r2g[1] == r2o[1] and r2g[2] == r2o[2]
+    assert relerr(r2g[0], r2o[0], 1e-6) < 1e-9
+    g.close()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("name", ["rc", "clipper", "ring", "mul3"])
+def test_transient_parity(name, graph, bundles):
+    circ = CIRCUITS[name]()
+    o, g = engines(circ, bundles, False, graph)
+    rec = []
+    to, Vo, so = o.run_transient(record=rec)
+    tg, Vg, sg = g.run_transient()
+    assert sg["error_flags"] == 0
+    assert sg["n_steps"] == so["n_steps"], (sg["n_steps"], so["n_steps"])
+    assert sg["rejected_steps"] == so["rejected_steps"]
+    assert sg["total_nr_iterations"] == so["total_nr_iterations"]
+    n = so["n_steps"]
+    # accepted-step sequence: same (step, t, dt, nr_iters, accept) records
+    gr = g.step_records()
+    assert len(gr) == len(rec)
+    for a, b in zip(gr, rec):
+        assert int(a[0]) == b["step"] and int(a[3]) == b["nr_iters"] and bool(a[4]) == b["accept"]
+        assert abs(a[1] - b["t_next"]) <= 1e-12 * abs(b["t_next"]) and abs(a[2] - b["dt"]) <= 1e-12 * b["dt"]
+    assert np.max(np.abs(tg[:n] - to[:n])) <= 1e-12 * to[n - 1]
+    span = max(np.max(Vo[:n]) - np.min(Vo[:n]), 1e-12)
+    rms = np.sqrt(np.mean((Vg[:n] - Vo[:n]) ** 2)) / span
+    assert rms < 1e-6, rms
+    assert relerr(Vg[:n], Vo[:n], 1e-6) < 1e-7
+    g.close()

@@ -1,0 +1,850 @@
+"""Host-side mirror of the reference's engine / strategy interface for the transient hot path.
+
+Same names and argument meaning as the reference so the parity tests read like its tests:
+
+* ``B200Engine.prepare()``            ~ ``CircuitEngine.prepare`` (vajax/analysis/engine.py:824)
+* ``B200Engine.build_system(...)``    ~ ``build_system`` (vajax/analysis/mna_builder.py:528-550)
+* ``B200Engine.nr_solve(...)``        ~ ``nr_solve`` (vajax/analysis/solver_factories.py:604-725)
+* ``B200Engine.run_transient()``      ~ ``FullMNAStrategy.run`` (vajax/analysis/transient/full_mna.py:780)
+  returning ``(times, V_out, stats)`` with the reference's stats keys (:1168-1186).
+
+Setup (node collapse, parameter split, stamp maps, CSR pattern) is NumPy on the host exactly as in
+the reference (it is Python there too); everything per NR iteration / per timestep runs in
+``libvajax_b200.so``.  The init function of every model runs as an emitted CUDA kernel, so there is
+no CPU evaluation path: without a CUDA device ``prepare()`` raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import re
+import time
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .. import lib as vlib
+from ..codegen import cuda_emitter as emitter
+
+U32_MAX = 4294967295
+KIND_CODES = {"dc": 0, "pulse": 1, "sine": 2, "pwl": 3, "exp": 4, "am": 5, "fm": 6}
+METHOD_CODES = {"be": 0, "euler": 0, "backward_euler": 0, "trap": 1, "trapezoidal": 1, "gear2": 2, "bdf2": 2, "gear": 2}
+
+
+@dataclass
+class AdaptiveConfig:
+    """reference: vajax/analysis/transient/adaptive.py:37-91"""
+    lte_ratio: float = 3.5
+    redo_factor: float = 2.5
+    reltol: float = 1e-3
+    abstol: float = 1e-12
+    min_dt: float = 1e-15
+    max_dt: float = float("inf")
+    tran_minpts: int = 50
+    warmup_steps: int = 2
+    max_order: int = 2
+    grow_factor: float = 2.0
+    nr_convtol: float = 1.0
+    gshunt_init: float = 0.0
+    gshunt_steps: int = 5
+    gshunt_target: float = 0.0
+    tran_fs: float = 0.25
+    tran_ft: float = 0.25
+    integration_method: str = "trap"
+    max_consecutive_rejects: int = 5
+
+
+@dataclass
+class SimulationOptions:
+    """reference: vajax/analysis/options.py:34-190 (hot-path subset)"""
+    nr_damping: float = 1.0
+    tran_itl: int = 20
+    reltol: float = 1e-3
+    abstol: float = 1e-12
+    vntol: float = 1e-6
+    gmin: float = 1e-12
+    temp: float = 27.0
+    icmode: str = "op"
+
+
+_INTERNAL_NAME_MAP = {  # reference: vajax/analysis/engine.py:634-660
+    "NOI": "node4", "GP": "node5", "SI": "node6", "DI": "node7", "BP": "node8", "BI": "node9",
+    "BS": "node10", "BD": "node11", "G": "node1", "D": "node0", "S": "node2", "B": "node3",
+    "A": "node0", "C": "node1", "CI": "node2", "a": "node0", "c": "node1", "a_int": "node2",
+}
+_SIMPLE_2TERM = {"A": "node0", "B": "node1"}
+
+
+def _source_desc(params: dict, pwl_t: List[float], pwl_v: List[float]) -> vlib.SourceDesc:
+    """Pack a source's parameters (defaults: vajax/analysis/sources.py:190-296)."""
+    g = params.get
+    st = str(g("type", "dc")).lower()
+    s = vlib.SourceDesc()
+    f = lambda k, d: float(d if g(k, d) is None else g(k, d))  # noqa: E731
+    if st in ("dc", "0", "0.0", ""):
+        s.kind = 0
+        s.p[0] = float(g("dc", 0))
+    elif st == "pulse":
+        s.kind = 1
+        for i, (k, d) in enumerate([("val0", 0), ("val1", 1), ("rise", 1e-9), ("fall", 1e-9), ("width", 1e-6),
+                                    ("period", 2e-6), ("delay", 0)]):
+            s.p[i] = f(k, d)
+    elif st == "sine":
+        s.kind = 2
+        for i, (k, d) in enumerate([("sinedc", 0), ("ampl", 1), ("freq", 1e3), ("phase", 0)]):
+            s.p[i] = f(k, d)
+    elif st == "pwl":
+        s.kind = 3
+        wave = g("wave", [0, 0])
+        if isinstance(wave, str):
+            import ast
+            wave = ast.literal_eval(wave)
+        wa = np.asarray(wave, dtype=np.float64)
+        times = wa[0::2] * f("stretch", 1)
+        vals = wa[1::2] * f("scale", 1) + f("offset", 0)
+        s.p[0] = f("pwlperiod", 0)
+        s.pwl_offset = len(pwl_t)
+        s.pwl_count = len(times)
+        pwl_t.extend(times.tolist())
+        pwl_v.extend(vals.tolist())
+    elif st == "exp":
+        s.kind = 4
+        for i, (k, d) in enumerate([("val0", 0), ("val1", 1), ("delay", 0), ("td2", 1e-9), ("tau1", 1e-10), ("tau2", 1e-10)]):
+            s.p[i] = f(k, d)
+    elif st in ("am", "fm"):
+        s.kind = 5 if st == "am" else 6
+        ph = g("phase", g("sinephase", 0))
+        vals = [f("sinedc", 0), f("ampl", 1), f("freq", 1e3), float(ph), f("delay", 0), f("modfreq", 1e3),
+                f("modphase", 0), f("modindex", 0.5)]
+        for i, v in enumerate(vals):
+            s.p[i] = v
+    else:
+        raise ValueError(f"Unknown source type '{st}'")
+    return s
+
+
+class _Plugin:
+    """A loaded init plugin (eval plugins are loaded by the C library itself)."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.dll = C.CDLL(path)
+
+
+class B200Engine:
+    def __init__(self, circuit: dict, bundles: Dict[str, dict], use_device_limiting: bool = False,
+                 device: int = 0, use_device_graph: bool = False, pivot_tol: float = 1e-3):
+        self.circuit = circuit
+        self.devices = circuit["devices"]
+        self.num_nodes = int(circuit["num_nodes"])
+        self.node_names = dict(circuit.get("node_names", {}))
+        self.bundles = bundles
+        self.use_device_limiting = use_device_limiting
+        self.device = device
+        self.use_device_graph = use_device_graph
+        self.pivot_tol = pivot_tol
+        self.analysis_params = dict(circuit.get("analysis", {}))
+        self.options = SimulationOptions()
+        for k in ("nr_damping", "tran_itl", "reltol", "abstol", "vntol", "gmin", "temp", "icmode"):
+            if k in self.analysis_params:
+                setattr(self.options, k, type(getattr(self.options, k))(self.analysis_params[k]))
+        self.temperature_k = float(circuit.get("temperature_k", self.options.temp + 273.15))
+        self.handle = C.c_void_p(None)
+        self._prepared = False
+        self._keep: List[Any] = []
+        self.timings: Dict[str, float] = {}
+
+    # ------------------------------------------------------------------------------------
+    def _torch(self):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise vlib.VjxError("no CUDA device: vajax_b200 has no CPU fallback")
+        return torch
+
+    def adaptive_config(self) -> AdaptiveConfig:
+        """reference: vajax/analysis/engine.py:884-907"""
+        ap = self.analysis_params
+        kw = {}
+        for src, dst, cast in [("tran_lteratio", "lte_ratio", float), ("tran_redofactor", "redo_factor", float),
+                               ("nr_convtol", "nr_convtol", float), ("tran_gshunt", "gshunt_init", float),
+                               ("reltol", "reltol", float), ("abstol", "abstol", float), ("tran_fs", "tran_fs", float),
+                               ("tran_minpts", "tran_minpts", int), ("maxstep", "max_dt", float),
+                               ("tran_method", "integration_method", str)]:
+            if src in ap:
+                kw[dst] = cast(ap[src])
+        return AdaptiveConfig(**kw)
+
+    # ---- init kernel on the GPU --------------------------------------------------------
+    def _run_init(self, mt: str, cols: List[Any], n: int):
+        """Run the emitted init kernel. ``cols[i]`` is a scalar (shared) or an (n,) array."""
+        torch = self._torch()
+        b = self.bundles[mt]
+        if mt not in self._init_plugins:
+            src, meta = emitter.emit_init_source(b)
+            self._init_plugins[mt] = (_Plugin(emitter.compile_plugin(src, f"{mt}_init")), meta)
+        plug, meta = self._init_plugins[mt]
+        vals: List[np.ndarray] = []
+        off, stride = [], []
+        pos = 0
+        for c in cols:
+            if np.ndim(c) == 0:
+                vals.append(np.array([float(c)]))
+                off.append(pos)
+                stride.append(0)
+                pos += 1
+            else:
+                a = np.ascontiguousarray(c, dtype=np.float64)
+                vals.append(a)
+                off.append(pos)
+                stride.append(1)
+                pos += n
+        dev = torch.device("cuda", self.device)
+        packed = torch.from_numpy(np.concatenate(vals) if vals else np.zeros(1)).to(dev)
+        d_off = torch.tensor(off or [0], dtype=torch.int32, device=dev)
+        d_str = torch.tensor(stride or [0], dtype=torch.int32, device=dev)
+        cs, nc = meta["cache_size"], meta["n_collapse_outputs"]
+        cache = torch.zeros((max(cs, 1), n), dtype=torch.float64, device=dev)
+        col = torch.zeros((max(nc, 1), n), dtype=torch.float32, device=dev)
+        args = vlib.VjxInitArgs(n, packed.data_ptr(), d_off.data_ptr(), d_str.data_ptr(), cache.data_ptr(), col.data_ptr())
+        torch.cuda.synchronize(dev)
+        rc = plug.dll.vjx_model_init(C.byref(args), C.c_void_p(0))
+        torch.cuda.synchronize(dev)
+        if rc != 0:
+            raise vlib.VjxError(f"init kernel launch failed for {mt}: cuda error {rc}")
+        return cache[:cs].t().contiguous(), col[:nc].t().contiguous()
+
+    # ---- early collapse decisions (reference: openvaf_models.py:556-670) ---------------
+    def _collapse_decisions(self) -> Dict[str, Dict[tuple, List[Tuple[int, int]]]]:
+        out: Dict[str, Any] = {}
+        for mt, devs in self.by_type.items():
+            b = self.bundles[mt]
+            pairs = [tuple(p) for p in b["collapsible_pairs"]]
+            names = [p.lower() for p in b["init_param_names"]]
+            defaults = {k.lower(): v for k, v in b["param_defaults"].items()}
+            if len(names) == 0 or len(pairs) == 0:
+                out[mt] = (None, {None: list(pairs)})
+                continue
+            keys = [tuple(float(d["params"][n]) if n in d["params"] else float(defaults.get(n, 0.0)) for n in names)
+                    for d in devs]
+            uniq = list(dict.fromkeys(keys))
+            cols = [np.array([u[i] for u in uniq]) for i in range(len(names))]
+            _, col = self._run_init(mt, cols, len(uniq))
+            col = col.cpu().numpy()
+            table = {}
+            for k, u in enumerate(uniq):
+                table[u] = [pairs[i] for i in range(len(pairs)) if i < col.shape[1] and col[k, i] > 0.5]
+            out[mt] = (keys, table)
+        return out
+
+    @staticmethod
+    def _collapse_roots(pairs, n_nodes):
+        """reference: vajax/analysis/node_setup.py:15-57"""
+        parent = list(range(n_nodes))
+
+        def find(x):
+            while parent[x] != x:
+                parent[x] = parent[parent[x]]
+                x = parent[x]
+            return x
+
+        for a, b in pairs:
+            if b != U32_MAX and a < n_nodes and b < n_nodes:
+                px, py = find(a), find(b)
+                if px != py:
+                    if py < 4:
+                        parent[px] = py
+                    elif px < 4:
+                        parent[py] = px
+                    else:
+                        parent[py] = px
+        return [find(i) for i in range(n_nodes)]
+
+    # ---- node setup (reference: vajax/analysis/node_setup.py:60-156) --------------------
+    def _setup_nodes(self, collapse):
+        next_internal = self.num_nodes
+        idx_in_type = {mt: 0 for mt in self.by_type}
+        node_of = {mt: np.zeros((len(devs), len(self.bundles[mt]["nodes"])), dtype=np.int64)
+                   for mt, devs in self.by_type.items()}
+        roots_cache: Dict[Tuple[str, tuple], list] = {}
+        noi, internal = [], []
+        for dev in self.devices:
+            if not dev.get("is_openvaf"):
+                continue
+            mt = dev["model"]
+            k = idx_in_type[mt]
+            idx_in_type[mt] += 1
+            keys, table = collapse[mt]
+            pairs = table[None] if keys is None else table[keys[k]]
+            model_nodes = self.bundles[mt]["nodes"]
+            nm = len(model_nodes)
+            ck = (mt, tuple(sorted(pairs)))
+            if ck not in roots_cache:
+                roots_cache[ck] = self._collapse_roots(pairs, nm)
+            roots = roots_cache[ck]
+            ext = dev["nodes"]
+            n_ext = len(ext)
+            row = node_of[mt][k]
+            row[:n_ext] = ext
+            r2c: Dict[int, int] = {}
+            for i in range(n_ext, nm):
+                root = roots[i]
+                if root < n_ext:
+                    row[i] = ext[root]
+                else:
+                    if root not in r2c:
+                        r2c[root] = next_internal
+                        next_internal += 1
+                    row[i] = r2c[root]
+                internal.append(int(row[i]))
+                if model_nodes[i] == "node4":
+                    noi.append(int(row[i]))
+        return next_internal, node_of, noi, internal
+
+    # ---- prepare_static_inputs (reference: openvaf_models.py:668-1056) ------------------
+    def _prepare_model(self, mt: str, devs: List[dict], node_of: np.ndarray) -> dict:
+        b = self.bundles[mt]
+        names, kinds = b["param_names"], b["param_kinds"]
+        model_nodes = b["nodes"]
+        dae = b["dae_data"]
+        n_dev, n_params = len(devs), len(names)
+        n_ext = len(devs[0]["nodes"])
+        if any(len(d["nodes"]) != n_ext for d in devs):
+            raise ValueError(f"{mt}: instances with different terminal counts are not supported")
+        voltage_indices = [i for i, k in enumerate(kinds) if k == "voltage"]
+        col_values: Dict[int, Any] = {}
+        varying = set(voltage_indices)
+        p2c: Dict[str, List[int]] = {}
+        g2c: Dict[str, List[int]] = {}
+        limit_param_map: Dict[int, Tuple[str, str]] = {}
+        for idx, (nm, kd) in enumerate(zip(names, kinds)):
+            nl = nm.lower()
+            if kd == "param":
+                p2c.setdefault(nl, []).append(idx)
+            elif kd == "param_given":
+                g2c.setdefault(nl, []).append(idx)
+            elif kd == "temperature":
+                col_values[idx] = self.temperature_k
+            elif kd == "sysfun" and nl == "mfactor":
+                col_values[idx] = 1.0
+            elif kd in ("prev_state", "enable_lim", "new_state", "enable_integration"):
+                limit_param_map[idx] = (kd, nm)
+        all_unique = set()
+        for d in devs:
+            all_unique.update(k.lower() for k in d["params"].keys())
+        for pn in all_unique:
+            if pn in p2c:
+                vals = np.array([float(d["params"].get(pn, d["params"].get(pn.upper(), 0.0))) for d in devs])
+                if np.all(vals == vals[0]):
+                    for c in p2c[pn]:
+                        col_values[c] = float(vals[0])
+                else:
+                    for c in p2c[pn]:
+                        col_values[c] = vals
+                        varying.add(c)
+            if pn in g2c:
+                for c in g2c[pn]:
+                    col_values[c] = 1.0
+        defaults = b["param_defaults"]
+        for pn, cols in p2c.items():
+            if pn not in all_unique:
+                if pn in ("tnom", "tref", "tr"):
+                    dflt = 27.0
+                elif pn in ("nf", "mult", "ns", "nd"):
+                    dflt = 1.0
+                else:
+                    dflt = defaults.get(pn, 0.0)
+                for c in cols:
+                    col_values[c] = dflt
+        shared_idx = [c for c in range(n_params) if c not in limit_param_map and c not in varying]
+        varying_idx = [c for c in range(n_params) if c not in limit_param_map and c in varying]
+        shared_vals = []
+        for c in shared_idx:
+            v = col_values.get(c, 0.0)
+            shared_vals.append(float(v[0]) if isinstance(v, np.ndarray) else float(v))
+        dev_cols = {}
+        for c in varying_idx:
+            v = col_values.get(c)
+            if v is None:
+                dev_cols[c] = np.zeros(n_dev)
+            elif isinstance(v, np.ndarray):
+                dev_cols[c] = v.astype(np.float64)
+            else:
+                dev_cols[c] = np.full(n_dev, float(v))
+        # ---- init -> cache on the GPU (openvaf_models.py:886-921)
+        e2i = {n.lower(): i for i, n in enumerate(names)}
+        init_to_eval = [e2i.get(n.lower(), -1) for n in b["init_param_names"]]
+        s_pos = {c: k for k, c in enumerate(shared_idx)}
+        cols = []
+        for ei in init_to_eval:
+            if ei in s_pos:
+                cols.append(shared_vals[s_pos[ei]])
+            elif ei in dev_cols:
+                cols.append(dev_cols[ei])
+            else:
+                cols.append(0.0)
+        cache_t, _collapse = self._run_init(mt, cols, n_dev)
+        ncc = cache_t.shape[1]
+        torch = self._torch()
+        if ncc > 0 and n_dev > 1:
+            const_mask = torch.all(cache_t == cache_t[0:1, :], dim=0).cpu().numpy()
+            shared_cache_idx = [int(i) for i in np.where(const_mask)[0]]
+            varying_cache_idx = [int(i) for i in np.where(~const_mask)[0]]
+        else:
+            shared_cache_idx, varying_cache_idx = [], list(range(ncc))
+        cache = cache_t.cpu().numpy()
+        # ---- emit + compile the eval kernel for this layout
+        layout = emitter.compute_eval_layout(b, shared_idx, varying_idx, shared_cache_idx, varying_cache_idx,
+                                             limit_param_map)
+        src, meta = emitter.emit_eval_source(b, layout, self.use_device_limiting)
+        use_lim = self.use_device_limiting and not meta.get("limiting_disabled", False)
+        plugin = emitter.compile_plugin(src, f"{mt}_eval")
+        # ---- node name -> model node index (device independent), then vectorised over instances
+        keys_present: Dict[str, int] = {}
+        for i in range(len(model_nodes)):
+            keys_present[model_nodes[i]] = i
+        va_terms, va_int = dae["terminals"], dae["internal_nodes"]
+        for i, vn in enumerate(va_terms):
+            if i < n_ext:
+                keys_present[vn] = i
+        nt = len(va_terms)
+        internal_keys = set(model_nodes[n_ext:])
+        for i, vn in enumerate(va_int):
+            key = f"node{nt + i}"
+            if key in internal_keys:
+                keys_present[vn] = model_nodes.index(key)
+
+        def resolve(nm: Optional[str]) -> Optional[int]:
+            if nm is None:
+                return None
+            if nm in _INTERNAL_NAME_MAP:
+                mp = _INTERNAL_NAME_MAP[nm]
+                if mp in keys_present:
+                    return keys_present[mp]
+                if nm in _SIMPLE_2TERM and _SIMPLE_2TERM[nm] in keys_present:
+                    return keys_present[_SIMPLE_2TERM[nm]]
+            elif nm in _SIMPLE_2TERM:
+                if _SIMPLE_2TERM[nm] in keys_present:
+                    return keys_present[_SIMPLE_2TERM[nm]]
+            if nm in keys_present:
+                return keys_present[nm]
+            return keys_present.get(nm.lower())
+
+        def circ(idx: Optional[int]) -> np.ndarray:
+            return np.zeros(n_dev, dtype=np.int64) if idx is None else node_of[:, idx]
+
+        nv = len(layout["volt_param_indices"])
+        vn1 = np.zeros((n_dev, nv), dtype=np.int32)
+        vn2 = np.zeros((n_dev, nv), dtype=np.int32)
+        for k, pi in enumerate(layout["volt_param_indices"]):
+            m = re.match(r"V\(([^,)]+)(?:,([^)]+))?\)", names[pi])
+            if m:
+                vn1[:, k] = circ(resolve(m.group(1).strip()))
+                vn2[:, k] = circ(resolve(m.group(2).strip())) if m.group(2) else 0
+        node_names = [r["node_name"] for r in dae["residuals"]]
+        jkeys = [(e["row_node_name"], e["col_node_name"]) for e in dae["jacobian"]]
+        R, J = len(node_names), len(jkeys)
+
+        def stamp_node(name: str) -> np.ndarray:
+            idx = keys_present.get(name)
+            return np.full(n_dev, -1, dtype=np.int64) if idx is None else node_of[:, idx]
+
+        res_idx = np.full((n_dev, R), -1, dtype=np.int32)
+        for r, nm in enumerate(node_names):
+            ni = stamp_node(nm)
+            res_idx[:, r] = np.where(ni > 0, ni - 1, -1)
+        jr = np.full((n_dev, J), -1, dtype=np.int32)
+        jc = np.full((n_dev, J), -1, dtype=np.int32)
+        for j, (rn, cn) in enumerate(jkeys):
+            ri, ci = stamp_node(rn), stamp_node(cn)
+            ok = (ri > 0) & (ci > 0)
+            jr[:, j] = np.where(ok, ri - 1, -1)
+            jc[:, j] = np.where(ok, ci - 1, -1)
+        dpi = layout["dev_param_indices"]
+        dev_params = np.ascontiguousarray(np.column_stack([dev_cols[c] for c in dpi]) if dpi else np.zeros((n_dev, 0)))
+        return dict(
+            bundle=b, n_dev=n_dev, layout=layout, meta=meta, plugin=plugin, use_device_limiting=use_lim,
+            num_limit_states=meta["n_limit_states"] if use_lim else 0,
+            shared_indices=shared_idx, varying_indices=varying_idx, shared_params=np.array(shared_vals, dtype=np.float64),
+            dev_params=dev_params, dev_param_indices=dpi,
+            cache=cache, shared_cache_indices=shared_cache_idx, varying_cache_indices=varying_cache_idx,
+            shared_cache=np.ascontiguousarray(cache[0, shared_cache_idx] if n_dev else np.zeros(0)),
+            dev_cache=np.ascontiguousarray(cache[:, varying_cache_idx]),
+            limit_param_map=limit_param_map, vnode1=np.ascontiguousarray(vn1), vnode2=np.ascontiguousarray(vn2),
+            res_indices=np.ascontiguousarray(res_idx), jac_row_indices=np.ascontiguousarray(jr),
+            jac_col_indices=np.ascontiguousarray(jc), R=R, J=J,
+            simparam_defaults=np.array(meta["simparam_defaults"], dtype=np.float64),
+        )
+
+    # ---- prepare (engine.py:824-1054 + full_mna.py:344-560) ----------------------------
+    def prepare(self):
+        if self._prepared:
+            return self
+        t0 = time.perf_counter()
+        lib = vlib.load()
+        self._torch()
+        self._init_plugins: Dict[str, Any] = {}
+        self.by_type: Dict[str, List[dict]] = {}
+        self.vsources, self.isources = [], []
+        for dev in self.devices:
+            if dev.get("is_openvaf"):
+                self.by_type.setdefault(dev["model"], []).append(dev)
+            elif dev["model"] == "vsource":
+                self.vsources.append(dev)
+            elif dev["model"] == "isource":
+                self.isources.append(dev)
+        collapse = self._collapse_decisions()
+        self.n_total, node_of, noi, internal = self._setup_nodes(collapse)
+        self.n_unknowns = self.n_total - 1
+        self.n_external = self.num_nodes
+        self.n_vs, self.n_is = len(self.vsources), len(self.isources)
+        self.n_aug = self.n_unknowns + self.n_vs
+        self.models = {mt: self._prepare_model(mt, devs, node_of[mt]) for mt, devs in self.by_type.items()}
+        self.timings["models"] = time.perf_counter() - t0
+        self.noi_indices = np.array(noi, dtype=np.int32)
+        self.internal_indices = np.array(sorted(set(internal)), dtype=np.int32)
+        self.vs_p = np.array([d["nodes"][0] for d in self.vsources], dtype=np.int32)
+        self.vs_n = np.array([d["nodes"][1] for d in self.vsources], dtype=np.int32)
+        self.is_p = np.array([d["nodes"][0] for d in self.isources], dtype=np.int32)
+        self.is_n = np.array([d["nodes"][1] for d in self.isources], dtype=np.int32)
+        self.total_limit_states = sum(m["n_dev"] * m["num_limit_states"] for m in self.models.values())
+        # ---- CSR pattern discovery (full_mna.py:423-513)
+        n_aug, nu = self.n_aug, self.n_unknowns
+        lin = []
+        for m in self.models.values():
+            r, c = m["jac_row_indices"].ravel().astype(np.int64), m["jac_col_indices"].ravel().astype(np.int64)
+            valid = (r >= 0) & (c >= 0)
+            lin.append(np.where(valid, r, 0) * n_aug + np.where(valid, c, 0))
+        if self.n_vs > 0:
+            br = np.arange(self.n_vs, dtype=np.int64)
+            vp, vn_ = self.vs_p > 0, self.vs_n > 0
+            p1, n1 = self.vs_p.astype(np.int64) - 1, self.vs_n.astype(np.int64) - 1
+            lin += [np.where(vp, p1 * n_aug + nu + br, 0), np.where(vn_, n1 * n_aug + nu + br, 0),
+                    np.where(vp, (nu + br) * n_aug + p1, 0), np.where(vn_, (nu + br) * n_aug + n1, 0)]
+        di = np.arange(nu, dtype=np.int64)
+        lin.append(di * n_aug + di)
+        self.unique_linear = np.unique(np.concatenate(lin))
+        self.nse = len(self.unique_linear)
+        urows = (self.unique_linear // n_aug).astype(np.int32)
+        self.csr_indices = np.ascontiguousarray((self.unique_linear % n_aug).astype(np.int32))
+        self.csr_indptr = np.zeros(n_aug + 1, dtype=np.int32)
+        self.csr_indptr[1:] = np.cumsum(np.bincount(urows, minlength=n_aug))
+        # ---- create the handle
+        cfg = self.adaptive_config()
+        o = vlib.Options()
+        so = self.options
+        o.nr_damping, o.reltol, o.abstol, o.vntol, o.gmin, o.max_step = so.nr_damping, so.reltol, so.abstol, so.vntol, so.gmin, 1e30
+        o.tran_itl = so.tran_itl
+        o.lte_ratio, o.redo_factor, o.lte_reltol, o.lte_abstol = cfg.lte_ratio, cfg.redo_factor, cfg.reltol, cfg.abstol
+        o.min_dt, o.grow_factor, o.tran_ft = cfg.min_dt, cfg.grow_factor, cfg.tran_ft
+        o.gshunt_init, o.gshunt_target, o.gshunt_steps = cfg.gshunt_init, cfg.gshunt_target, cfg.gshunt_steps
+        o.warmup_steps, o.max_order, o.max_consecutive_rejects = cfg.warmup_steps, cfg.max_order, cfg.max_consecutive_rejects
+        o.integration_method = METHOD_CODES[str(cfg.integration_method).strip("\"'").lower()]
+        o.pivot_tol = self.pivot_tol
+        o.use_device_graph = 1 if self.use_device_graph else 0
+        md = (vlib.ModelDesc * max(len(self.models), 1))()
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        for k, (mt, m) in enumerate(self.models.items()):
+            d = md[k]
+            d.plugin_path = m["plugin"].encode()
+            d.n_dev, d.n_volt = m["n_dev"], m["vnode1"].shape[1]
+            d.n_dev_params, d.n_dev_cache = m["dev_params"].shape[1], m["dev_cache"].shape[1]
+            d.n_res, d.n_jac, d.n_lim = m["R"], m["J"], m["num_limit_states"]
+            d.vnode1, d.vnode2 = ptr(m["vnode1"]), ptr(m["vnode2"])
+            d.dev_params, d.dev_cache = ptr(m["dev_params"]), ptr(m["dev_cache"])
+            d.shared_params, d.n_shared = ptr(m["shared_params"]), len(m["shared_params"])
+            d.shared_cache, d.n_shared_cache = ptr(m["shared_cache"]), len(m["shared_cache"])
+            d.simparam_defaults, d.n_simparams = ptr(m["simparam_defaults"]), len(m["simparam_defaults"])
+            d.res_idx, d.jac_row, d.jac_col = ptr(m["res_indices"]), ptr(m["jac_row_indices"]), ptr(m["jac_col_indices"])
+        pwl_t: List[float] = []
+        pwl_v: List[float] = []
+        vsd = (vlib.SourceDesc * max(self.n_vs, 1))(*[_source_desc(d["params"], pwl_t, pwl_v) for d in self.vsources])
+        isd = (vlib.SourceDesc * max(self.n_is, 1))(*[_source_desc(d["params"], pwl_t, pwl_v) for d in self.isources])
+        self._pwl_t = np.array(pwl_t or [0.0])
+        self._pwl_v = np.array(pwl_v or [0.0])
+        cd = vlib.CircuitDesc()
+        cd.n_total, cd.n_external, cd.n_vsources, cd.n_isources = self.n_total, self.n_external, self.n_vs, self.n_is
+        cd.nse, cd.csr_indptr, cd.csr_indices = self.nse, ptr(self.csr_indptr), ptr(self.csr_indices)
+        cd.n_models, cd.models = len(self.models), md
+        cd.vs_node_p, cd.vs_node_n, cd.is_node_p, cd.is_node_n = ptr(self.vs_p), ptr(self.vs_n), ptr(self.is_p), ptr(self.is_n)
+        cd.vsrc, cd.isrc = vsd, isd
+        cd.pwl_times, cd.pwl_values, cd.n_pwl = ptr(self._pwl_t), ptr(self._pwl_v), len(pwl_t)
+        cd.noi_nodes, cd.n_noi = ptr(self.noi_indices), len(self.noi_indices)
+        cd.internal_nodes, cd.n_internal = ptr(self.internal_indices), len(self.internal_indices)
+        cd.opts = o
+        self._keep += [md, vsd, isd, cd]
+        t1 = time.perf_counter()
+        vlib.check(lib.vjx_create(C.byref(cd), self.device, C.byref(self.handle)))
+        self.timings["create"] = time.perf_counter() - t1
+        self.timings["prepare"] = time.perf_counter() - t0
+        self.cfg = cfg
+        self._prepared = True
+        return self
+
+    def close(self):
+        if self.handle:
+            vlib.load().vjx_destroy(self.handle)
+            self.handle = C.c_void_p(None)
+        self._prepared = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device helpers ---------------------------------------------------------------
+    def _dev(self, a, n=None):
+        torch = self._torch()
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            return a.to(device=f"cuda:{self.device}", dtype=torch.float64).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=f"cuda:{self.device}")
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+    def eval_sources(self, t: float):
+        """Host evaluation of sources at time t for the DC/UIC initialisation only (the per-step
+        evaluation happens in k_pre_step on the device). reference: sources.py:26-187."""
+        def one(p):
+            st = str(p.get("type", "dc")).lower()
+            if st in ("dc", "0", "0.0", ""):
+                return float(p.get("dc", 0))
+            if st == "pulse":
+                v0, v1 = float(p.get("val0", 0)), float(p.get("val1", 1))
+                r, f = float(p.get("rise", 1e-9)), float(p.get("fall", 1e-9))
+                w, per, d = float(p.get("width", 1e-6)), float(p.get("period", 2e-6)), float(p.get("delay", 0))
+                tp = np.mod(t - d, per)
+                if t < d:
+                    return v0
+                if tp < r:
+                    return float(v0 + (v1 - v0) * tp / r)
+                if tp < r + w:
+                    return v1
+                if tp < r + w + f:
+                    return float(v1 - (v1 - v0) * (tp - r - w) / f)
+                return v0
+            if st == "sine":
+                return float(float(p.get("sinedc", 0)) + float(p.get("ampl", 1)) * np.sin(
+                    2 * np.pi * float(p.get("freq", 1e3)) * t + float(p.get("phase", 0))))
+            if st == "pwl":
+                wave = p.get("wave", [0, 0])
+                wa = np.asarray(wave, dtype=np.float64)
+                tt = t
+                per = float(p.get("pwlperiod", 0))
+                if per > 0:
+                    tt = np.mod(t, per)
+                return float(np.interp(tt, wa[0::2] * float(p.get("stretch", 1)),
+                                       wa[1::2] * float(p.get("scale", 1)) + float(p.get("offset", 0))))
+            if st == "exp":
+                v0, v1, d = float(p.get("val0", 0)), float(p.get("val1", 1)), float(p.get("delay", 0))
+                td, t1, t2 = float(p.get("td2", 1e-9)), float(p.get("tau1", 1e-10)), float(p.get("tau2", 1e-10))
+                if t < d:
+                    return v0
+                rising = v0 + (v1 - v0) * (1 - np.exp(-(t - d) / t1))
+                if t < d + td:
+                    return float(rising)
+                raf = v0 + (v1 - v0) * (1 - np.exp(-td / t1))
+                return float(raf + (v0 - raf) * (1 - np.exp(-(t - d - td) / t2)))
+            raise ValueError(f"source type {st} not supported for t=0 evaluation")
+        return (np.array([one(d["params"]) for d in self.vsources], dtype=np.float64),
+                np.array([one(d["params"]) for d in self.isources], dtype=np.float64))
+
+    # ---- Seam S2 -----------------------------------------------------------------------
+    def build_system(self, X, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0, integ_c1=0.0,
+                     integ_d1=0.0, dQdt_prev=None, integ_c2=0.0, Q_prev2=None, limit_state_in=None, nr_iteration=1):
+        self.prepare()
+        torch = self._torch()
+        dev = f"cuda:{self.device}"
+        z = lambda n: torch.zeros(max(n, 1), dtype=torch.float64, device=dev)  # noqa: E731
+        csr, f, Q = z(self.nse), z(self.n_aug), z(self.n_unknowns)
+        Ivs, lim, mrc = z(self.n_vs), z(self.total_limit_states), z(self.n_unknowns)
+        args = [self._dev(X), self._dev(vsource_vals), self._dev(isource_vals), self._dev(Q_prev)]
+        dq, q2, li = self._dev(dQdt_prev), self._dev(Q_prev2), self._dev(limit_state_in)
+        self._keep_call = args + [dq, q2, li]
+        vlib.check(vlib.load().vjx_build_system(
+            self.handle, self._p(args[0]), self._p(args[1]) if self.n_vs else None, self._p(args[2]) if self.n_is else None,
+            self._p(args[3]), float(integ_c0), float(gmin), float(gshunt), float(integ_c1), float(integ_d1),
+            self._p(dq), float(integ_c2), self._p(q2), self._p(li), int(nr_iteration),
+            self._p(csr), self._p(f), self._p(Q), self._p(Ivs), self._p(lim), self._p(mrc), None))
+        torch.cuda.synchronize()
+        return (csr[:self.nse].cpu().numpy(), f[:self.n_aug].cpu().numpy(), Q[:self.n_unknowns].cpu().numpy(),
+                Ivs[:self.n_vs].cpu().numpy(), lim[:self.total_limit_states].cpu().numpy(), mrc[:self.n_unknowns].cpu().numpy())
+
+    # ---- Seam S1 -----------------------------------------------------------------------
+    def lu_solve(self, csr_data, b):
+        self.prepare()
+        torch = self._torch()
+        c, bb = self._dev(csr_data), self._dev(b)
+        x = torch.zeros(self.n_aug, dtype=torch.float64, device=c.device)
+        vlib.check(vlib.load().vjx_lu_solve(self.handle, self._p(c), self._p(bb), self._p(x), None))
+        torch.cuda.synchronize()
+        return x.cpu().numpy()
+
+    def lu_stats(self) -> dict:
+        out = np.zeros(6)
+        vlib.check(vlib.load().vjx_lu_stats(self.handle, out.ctypes.data_as(C.c_void_p)))
+        return dict(nnz_lu=int(out[0]), flops=float(out[1]), levels_l=int(out[2]), levels_u=int(out[3]),
+                    max_row_len=int(out[4]), n=int(out[5]))
+
+    # ---- Seam S3 -----------------------------------------------------------------------
+    def nr_solve(self, X_init, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0, integ_c1=0.0,
+                 integ_d1=0.0, dQdt_prev=None, integ_c2=0.0, Q_prev2=None, limit_state_in=None, res_tol_floor=None,
+                 max_iterations=None, return_device=False):
+        self.prepare()
+        torch = self._torch()
+        dev = f"cuda:{self.device}"
+        z = lambda n: torch.zeros(max(n, 1), dtype=torch.float64, device=dev)  # noqa: E731
+        nx = self.n_total + self.n_vs
+        X_out, Q, dQdt, Ivs = z(nx), z(self.n_unknowns), z(self.n_unknowns), z(self.n_vs)
+        lim, mrc = z(self.total_limit_states), z(self.n_unknowns)
+        a = [self._dev(X_init), self._dev(vsource_vals), self._dev(isource_vals), self._dev(Q_prev),
+             self._dev(dQdt_prev), self._dev(Q_prev2), self._dev(limit_state_in), self._dev(res_tol_floor)]
+        it, cv, mf = C.c_int(0), C.c_int(0), C.c_double(0.0)
+        vlib.check(vlib.load().vjx_nr_solve(
+            self.handle, self._p(a[0]), self._p(a[1]) if self.n_vs else None, self._p(a[2]) if self.n_is else None,
+            self._p(a[3]), float(integ_c0), float(gmin), float(gshunt), float(integ_c1), float(integ_d1), self._p(a[4]),
+            float(integ_c2), self._p(a[5]), self._p(a[6]), self._p(a[7]),
+            -1 if max_iterations is None else int(max_iterations),
+            self._p(X_out), C.byref(it), C.byref(cv), C.byref(mf), self._p(Q), self._p(dQdt), self._p(Ivs),
+            self._p(lim), self._p(mrc), None))
+        torch.cuda.synchronize()
+        outs = (X_out[:nx], it.value, bool(cv.value), mf.value, Q[:self.n_unknowns], dQdt[:self.n_unknowns],
+                Ivs[:self.n_vs], lim[:self.total_limit_states], mrc[:self.n_unknowns])
+        if return_device:
+            return outs
+        return tuple(o.cpu().numpy() if hasattr(o, "cpu") else o for o in outs)
+
+    def init_mid_rail(self) -> np.ndarray:
+        """reference: vajax/analysis/transient/full_mna.py:694-746"""
+        vdd = 0.0
+        for d in self.devices:
+            if d["model"] == "vsource":
+                dc = d["params"].get("dc", 0.0)
+                if dc > vdd:
+                    vdd = dc
+        V = np.full(self.n_total, vdd / 2.0)
+        V[0] = 0.0
+        for name, idx in self.node_names.items():
+            nl = name.lower()
+            if "vdd" in nl or "vcc" in nl:
+                V[idx] = vdd
+            elif nl in ("gnd", "vss", "0"):
+                V[idx] = 0.0
+        for d in self.devices:
+            if d["model"] == "vsource" and len(d["nodes"]) >= 2:
+                p, n = d["nodes"][0], d["nodes"][1]
+                if n == 0 and p > 0:
+                    V[p] = float(d["params"].get("dc", 0.0))
+        if len(self.noi_indices):
+            V[self.noi_indices] = 0.0
+        return V
+
+    # ---- FullMNAStrategy.run (full_mna.py:780-1196) --------------------------------------
+    def run_transient(self, t_stop: Optional[float] = None, dt: Optional[float] = None, max_steps: Optional[int] = None,
+                      chunk_attempts: int = 0, read_outputs: bool = True):
+        self.prepare()
+        torch = self._torch()
+        lib = vlib.load()
+        ap = self.analysis_params
+        t_stop = float(ap["stop"]) if t_stop is None else float(t_stop)
+        dt = float(ap["step"]) if dt is None else float(dt)
+        if max_steps is None:
+            max_steps = int(t_stop / dt * 1.1) + 10  # engine.py:875
+        cfg = self.cfg
+        max_dt = cfg.max_dt
+        if cfg.tran_minpts > 0:
+            max_dt = min(max_dt, t_stop / cfg.tran_minpts)
+        if cfg.tran_fs != 1.0:
+            dt = dt * cfg.tran_fs
+        nu, nt, nvs = self.n_unknowns, self.n_total, self.n_vs
+        X0 = np.zeros(nt + nvs)
+        X0[:nt] = self.init_mid_rail()
+        vs0, is0 = self.eval_sources(0.0)
+        t_setup = time.perf_counter()
+        if self.options.icmode == "uic":
+            X0[:nt] = 0.0
+            _, _, Q_init, I_dc, _, _ = self.build_system(X0, vs0, is0, np.zeros(nu), 0.0, self.options.gmin, 0.0, 0.0, 0.0,
+                                                         None, 0.0, None, None, 1)
+            dc_mrc = np.zeros(nu)
+        else:
+            X_dc, _, dc_conv, _, Q_dc, _, I_dc, _, dc_mrc = self.nr_solve(
+                X0, vs0, is0, np.zeros(nu), 0.0, self.options.gmin, 0.0, 0.0, 0.0, None, 0.0, None, None, None)
+            X0, Q_init = X_dc, Q_dc
+        dX0, dQ, dI, dM = self._dev(X0), self._dev(Q_init), self._dev(I_dc if nvs else np.zeros(1)), self._dev(dc_mrc)
+        vlib.check(lib.vjx_tran_begin(self.handle, self._p(dX0), self._p(dQ), self._p(dI), self._p(dM), t_stop, dt,
+                                      float(max_dt), int(max_steps), None))
+        torch.cuda.synchronize()
+        self.timings["tran_setup"] = time.perf_counter() - t_setup
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start = time.perf_counter()
+        ev0.record()
+        att = C.c_int(0)
+        total_att = 0
+        while True:
+            vlib.check(lib.vjx_tran_run(self.handle, int(chunk_attempts), C.byref(att), None))
+            total_att += att.value
+            if att.value == 0 or chunk_attempts <= 0:
+                break
+            sc = np.zeros(12)
+            vlib.check(lib.vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), None))
+            if not (sc[0] < t_stop) or sc[2] >= max_steps:
+                break
+        ev1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t_start
+        sc = np.zeros(12)
+        vlib.check(lib.vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), None))
+        n_steps = int(sc[2])
+        times = np.zeros(max_steps)
+        V_out = np.zeros((max_steps, self.n_external))
+        I_out = np.zeros((max_steps, max(nvs, 1)))
+        if read_outputs:
+            vlib.check(lib.vjx_tran_read(self.handle, 0, max_steps, times.ctypes.data_as(C.c_void_p),
+                                         V_out.ctypes.data_as(C.c_void_p), I_out.ctypes.data_as(C.c_void_p), None))
+        node_indices = {name: idx for name, idx in self.node_names.items() if 0 < idx < self.n_external}
+        rejected = int(sc[4])
+        stats = {
+            "n_steps": n_steps, "total_timesteps": n_steps, "accepted_steps": n_steps, "rejected_steps": rejected,
+            "total_nr_iterations": int(sc[3]), "avg_nr_iterations": float(sc[3]) / max(n_steps, 1),
+            "wall_time": wall, "time_per_step_ms": wall / n_steps * 1000 if n_steps > 0 else 0,
+            "device_time_ms": ev0.elapsed_time(ev1),
+            "min_dt_used": float(sc[5]), "max_dt_used": float(sc[6]),
+            "convergence_rate": n_steps / max(n_steps + rejected, 1),
+            "strategy": "adaptive_full_mna_b200", "solver": "b200_sparse_lu",
+            "V_out": V_out, "I_out": I_out, "node_indices": node_indices,
+            "current_indices": {d["name"]: i for i, d in enumerate(self.vsources)},
+            "attempts": int(sc[10]), "error_flags": int(sc[11]),
+        }
+        return times, V_out, stats
+
+    def step_records(self, count: Optional[int] = None) -> np.ndarray:
+        """Per-attempt records (step, t_next, dt, nr_iters, accept, lte_reject, nr_failed, lte_norm)."""
+        sc = np.zeros(12)
+        lib = vlib.load()
+        vlib.check(lib.vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), None))
+        n = int(sc[10]) if count is None else count
+        out = np.zeros((max(n, 1), 8))
+        if n > 0:
+            vlib.check(lib.vjx_tran_records(self.handle, 0, n, out.ctypes.data_as(C.c_void_p), None))
+        return out[:n]
+
+    def tran_state(self):
+        X = np.zeros(self.n_total + self.n_vs)
+        Q = np.zeros(max(self.n_unknowns, 1))
+        dQ = np.zeros(max(self.n_unknowns, 1))
+        vlib.check(vlib.load().vjx_tran_state(self.handle, X.ctypes.data_as(C.c_void_p), Q.ctypes.data_as(C.c_void_p),
+                                              dQ.ctypes.data_as(C.c_void_p), None))
+        return X, Q[:self.n_unknowns], dQ[:self.n_unknowns]
+
+    def time_phase(self, phase: int, reps: int = 20) -> Tuple[float, int]:
+        ms, nl = C.c_double(0.0), C.c_int(0)
+        vlib.check(vlib.load().vjx_time_phase(self.handle, phase, reps, C.byref(ms), C.byref(nl), None))
+        return ms.value, nl.value
+
+    def launch_count(self) -> int:
+        return int(vlib.load().vjx_launch_count(self.handle))

@@ -1,0 +1,1930 @@
+// libvajax_b200: B200 (sm_100a) implementation of VAJAX's transient Newton-Raphson hot path.
+// See include/vajax_b200.h for the boundary and DESIGN.md for the data layout.
+//
+// Kernel inventory (all fp64, all deterministic - no floating-point atomics):
+//   model eval (emitted plugin)  K1+K2  one thread per instance, scatters into slot-sorted arrays
+//   k_isrc                       K4     current-source contributions
+//   k_stamp_jacobian             K3,K5,K8  segmented sum over slot-sorted contributions -> CSR values
+//   k_residual                   K4,K6,K7  row-sorted vector sums, residual assembly, convergence
+//   k_lu_factor                  K9     dependency-driven (sync-free) row-wise refactorisation
+//   k_lu_lsolve / k_lu_usolve    K9     dependency-driven triangular solves
+//   k_delta_reduce / k_nr_update K7,K10 delta convergence, step limiting, X update, NOI clamp
+//   k_pre_step .. k_step_commit  K11,K12 integration coefficients, sources, predictor, LTE,
+//                                       accept/reject, history, outputs - all on the device
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vajax_b200.h"
+#include "vjx_model_abi.h"
+#include "vjx_symbolic.h"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(VJX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+typedef unsigned long long ull;
+
+// ------------------------------------------------------------------------------------------
+// Device-side state
+// ------------------------------------------------------------------------------------------
+struct NRStat {
+  int iter;          // NR iteration counter
+  int converged;
+  int bad_res;       // any |f_check| !< res_tol
+  int bad_delta;     // any |conv_delta| !< tol
+  int max_iter;
+  int cont;          // loop-continue flag (host-polled mode mirror of the WHILE handle)
+  int error;         // watchdog / pivot flags
+  int pad;
+  ull max_f_bits;    // max |f_check|   (bit pattern of a non-negative double: order-preserving)
+  ull max_dv_bits;   // max |delta V|
+  ull lim_delta_bits;
+  ull lim_ref_bits;
+  unsigned epoch;    // LU flag epoch
+  unsigned ticket_f, ticket_l, ticket_u;
+};
+
+struct TranScalars {
+  double t, dt, t_stop, max_dt, min_dt_used, max_dt_used;
+  double dt_hist[4];
+  int hist_count, step_idx, warmup, total_nr, rejected, consec, attempts, hist_head, max_steps, cont;
+  int attempts_limit, pad0;
+  // per-attempt
+  double t_next, dt_cur, eci, a[3], pred_err, gshunt, new_dt;
+  int can_predict, accept, use_new, nr_fail_min, lte_reject, nr_failed, reject, pad;
+  ull lte_bits;
+};
+
+struct LUDev {
+  int n;
+  const int* ptr;
+  const int* col;
+  const int* diag;
+  const int* src;
+  const int* order_l;
+  const int* order_u;
+  const int* perm_r;
+  const int* perm_c;
+  const long long* pair_ptr;   // [nnz+1] contributor pairs of each L+U entry
+  const int* pair_l;           // absolute index of L(i,k)
+  const int* pair_u;           // absolute index of U(k,j)
+  const int* ent_order;        // [nnz] entries per row sorted by wave
+  const int* row_wave_ptr;     // [n+1]
+  const int* wave_end;         // end offset into ent_order per wave
+  double* val;
+  double* inv_diag;
+  double* y;
+  double* xp;
+  unsigned* flag_f;
+  unsigned* flag_l;
+  unsigned* flag_u;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double nan0(double v) { return (v != v) ? 0.0 : v; }
+__device__ __forceinline__ void atomic_max_pos(ull* addr, double v) {
+  atomicMax(addr, (ull)__double_as_longlong(v));
+}
+
+// ------------------------------------------------------------------------------------------
+// Sources (reference: vajax/analysis/sources.py:26-187)
+// ------------------------------------------------------------------------------------------
+__device__ double py_mod(double a, double b) {
+  double r = fmod(a, b);
+  if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+  return r;
+}
+__device__ double eval_source(const vjx_source_desc& s, double t, const double* pt, const double* pv) {
+  const double* p = s.p;
+  const double PI = 3.141592653589793;
+  switch (s.kind) {
+    case VJX_SRC_DC: return p[0];
+    case VJX_SRC_PULSE: {
+      double v0 = p[0], v1 = p[1], r = p[2], f = p[3], w = p[4], per = p[5], d = p[6];
+      double tp = py_mod(t - d, per);
+      double rising = v0 + (v1 - v0) * tp / r;
+      double falling = v1 - (v1 - v0) * (tp - r - w) / f;
+      if (t < d) return v0;
+      if (tp < r) return rising;
+      if (tp < r + w) return v1;
+      if (tp < r + w + f) return falling;
+      return v0;
+    }
+    case VJX_SRC_SINE: return p[0] + p[1] * sin(2 * PI * p[2] * t + p[3]);
+    case VJX_SRC_PWL: {
+      double per = p[0];
+      if (per > 0) t = py_mod(t, per);
+      const double* xp = pt + s.pwl_offset;
+      const double* fp = pv + s.pwl_offset;
+      int n = s.pwl_count;
+      if (n <= 0) return 0.0;
+      if (t <= xp[0]) return fp[0];
+      if (t >= xp[n - 1]) return fp[n - 1];
+      int lo = 0, hi = n - 1;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (xp[mid] <= t) lo = mid; else hi = mid;
+      }
+      double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+      return slope * (t - xp[lo]) + fp[lo];
+    }
+    case VJX_SRC_EXP: {
+      double v0 = p[0], v1 = p[1], d = p[2], td = p[3], t1 = p[4], t2 = p[5];
+      double tf = d + td;
+      double rising = v0 + (v1 - v0) * (1 - exp(-(t - d) / t1));
+      double raf = v0 + (v1 - v0) * (1 - exp(-td / t1));
+      double falling = raf + (v0 - raf) * (1 - exp(-(t - tf) / t2));
+      return t < d ? v0 : (t < tf ? rising : falling);
+    }
+    case VJX_SRC_AM: {
+      double dc = p[0], a = p[1], f = p[2], ph = p[3], d = p[4], mf = p[5], mph = p[6], mi = p[7];
+      double initial = dc + a * sin(ph * PI / 180) * (1 + mi * sin(mph * PI / 180));
+      double carrier = sin(2 * PI * f * (t - d) + ph * PI / 180);
+      double mod = 1 + mi * sin(2 * PI * mf * (t - d) + mph * PI / 180);
+      return t < d ? initial : dc + a * carrier * mod;
+    }
+    case VJX_SRC_FM: {
+      double dc = p[0], a = p[1], f = p[2], ph = p[3], d = p[4], mf = p[5], mph = p[6], mi = p[7];
+      double initial = dc + a * sin(ph * PI / 180 + mi * sin(mph * PI / 180));
+      double cph = 2 * PI * f * (t - d) + ph * PI / 180;
+      double mc = mi * sin(2 * PI * mf * (t - d) + mph * PI / 180);
+      return t < d ? initial : dc + a * sin(cph + mc);
+    }
+  }
+  return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stamping kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_isrc(int n2, const int* __restrict__ dest, const double* __restrict__ isrc, double* vsorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  int rec = dest[i];
+  if (rec < 0) return;
+  double v = isrc[i >> 1] * ((i & 1) ? -1.0 : 1.0);
+  double* q = vsorted + (size_t)rec * 4;
+  q[0] = nan0(v);
+  q[1] = 0.0;
+  q[2] = 0.0;
+  q[3] = 0.0;
+}
+
+enum { SLOT_DIAG = 1, SLOT_NOI_ZERO = 2, SLOT_NOI_ONE = 4 };
+
+// csr[s] = sum of the slot's contributions in the reference's scatter order
+// (model order, instance, entry; vajax/analysis/mna_builder.py:953-958), then the diagonal
+// regularisation (:969) and the vsource incidence constants (:972-989).  With enforce_noi the
+// NOI rows/columns are rewritten as in solver_factories.py:1268-1276.
+__global__ void k_stamp_jacobian(int nse, const int* __restrict__ seg, const double* __restrict__ jsorted,
+                                 const unsigned char* __restrict__ flags, const float* __restrict__ cst,
+                                 const double* __restrict__ ctl, int enforce_noi, double* __restrict__ csr) {
+  const double reg = ctl[VJX_CTL_DIAGREG] + ctl[VJX_CTL_GSHUNT];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nse; s += gridDim.x * blockDim.x) {
+    int b = seg[s], e = seg[s + 1];
+    double acc = 0.0;
+    for (int p = b; p < e; ++p) acc += jsorted[p];
+    unsigned char f = flags[s];
+    if (f & SLOT_DIAG) acc += reg;
+    float c = cst[s];
+    if (c != 0.0f) acc += (double)c;
+    if (enforce_noi) {
+      if (f & SLOT_NOI_ZERO) acc = 0.0;
+      if (f & SLOT_NOI_ONE) acc = 1.0;
+    }
+    csr[s] = acc;
+  }
+}
+
+struct ResidualArgs {
+  int n_unknowns, n_vs, n_total;
+  const int* vseg;            // [n_unknowns+1] row segments of vsorted records
+  const double* vsorted;
+  const int* att_ptr;         // [n_unknowns+1] vsources attached to each node row
+  const int* att_idx;         // vsource index
+  const signed char* att_sign;  // +1 p terminal, -1 n terminal
+  const int* vs_p;
+  const int* vs_n;
+  const double* X;
+  const double* vsrc;
+  const double* Q_prev;
+  const double* dQdt_prev;
+  const double* Q_prev2;
+  const double* res_tol_floor;  // null -> abstol
+  const unsigned char* conv_mask;
+  const double* ctl;
+  double reltol, abstol, vntol;
+  double* f;
+  double* Q;
+  double* Ivs;
+  double* maxres;
+  NRStat* st;
+  int check;                  // accumulate convergence statistics
+};
+
+// reference: _build_residual vajax/analysis/mna_builder.py:1012-1076, combine_transient_residual
+// vajax/analysis/mna.py:673-719, residual test solver_factories.py:271-281
+__global__ void k_residual(ResidualArgs a) {
+  const int n_aug = a.n_unknowns + a.n_vs;
+  const double c0 = a.ctl[VJX_CTL_C0], c1 = a.ctl[VJX_CTL_C1], d1 = a.ctl[VJX_CTL_D1], c2 = a.ctl[VJX_CTL_C2];
+  const double eff = a.ctl[VJX_CTL_DIAGREG] + a.ctl[VJX_CTL_GSHUNT];
+  int bad = 0;
+  double mf = 0.0;
+  bool mfnan = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_aug; i += gridDim.x * blockDim.x) {
+    double f, tol;
+    if (i < a.n_unknowns) {
+      double fr = 0.0, q = 0.0, lr = 0.0, lq = 0.0, mx = 0.0;
+      for (int p = a.vseg[i]; p < a.vseg[i + 1]; ++p) {
+        const double2* r = reinterpret_cast<const double2*>(a.vsorted + (size_t)p * 4);
+        double2 r0 = r[0], r1 = r[1];
+        fr += r0.x;
+        mx = fmax(mx, fabs(r0.x));
+        q += r0.y;
+        lr += r1.x;
+        lq += r1.y;
+      }
+      fr = fr - lr;
+      double fb = 0.0;
+      for (int p = a.att_ptr[i]; p < a.att_ptr[i + 1]; ++p) {
+        int v = a.att_idx[p];
+        if (a.att_sign[p] > 0) {
+          if (a.Ivs) a.Ivs[v] = -fr;
+          fb += a.X[a.n_total + v];
+        } else {
+          fb += -a.X[a.n_total + v];
+        }
+      }
+      if (a.n_vs > 0) fr = fr + fb;
+      double qp = a.Q_prev ? a.Q_prev[i] : 0.0;
+      double dq = a.dQdt_prev ? a.dQdt_prev[i] : 0.0;
+      double q2 = a.Q_prev2 ? a.Q_prev2[i] : 0.0;
+      f = fr - 0.0 + c0 * (q - lq) + c1 * qp + d1 * dq + c2 * q2;
+      f = f + eff * a.X[i + 1];
+      if (a.Q) a.Q[i] = q;
+      if (a.maxres) a.maxres[i] = mx;
+      double fl = a.res_tol_floor ? a.res_tol_floor[i] : a.abstol;
+      tol = fmax(mx * a.reltol, fl);
+      if (mx != mx || fl != fl) tol = mx * 0.0 + fl * 0.0 + tol;  // jnp.maximum propagates NaN
+    } else {
+      int v = i - a.n_unknowns;
+      f = a.X[a.vs_p[v]] - a.X[a.vs_n[v]] - a.vsrc[v];
+      tol = a.vntol;
+      if (a.Ivs && a.vs_p[v] <= 0) a.Ivs[v] = 0.0;
+    }
+    if (a.f) a.f[i] = f;
+    if (a.check) {
+      double fc = a.conv_mask[i] ? f : 0.0;
+      double af = fabs(fc);
+      if (af != af) mfnan = true; else mf = fmax(mf, af);
+      if (!(af < tol)) bad = 1;
+    }
+  }
+  if (a.check) {
+    // warp-level pre-reduction, then integer atomics (deterministic)
+    for (int o = 16; o > 0; o >>= 1) {
+      mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+      bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+      mfnan |= (bool)__shfl_xor_sync(0xffffffffu, (int)mfnan, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (mfnan) atomicMax(&a.st->max_f_bits, 0x7ff8000000000000ULL);
+      else if (mf > 0.0) atomic_max_pos(&a.st->max_f_bits, mf);
+      if (bad) atomicOr(&a.st->bad_res, 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Sparse LU: numeric refactorisation on the fixed pattern / pivot order, dependency driven.
+// One warp per row; rows are handed out through a ticket counter in dependency-level order, so
+// with every warp resident the smallest unfinished row can always make progress (no deadlock).
+// Cross-SM visibility: producers __threadfence() + st.release a per-row epoch flag; consumers
+// ld.acquire the flag and read finished rows with ld.cg (L2), never through L1.
+// ------------------------------------------------------------------------------------------
+#define VJX_SPIN_LIMIT (1u << 24)
+
+// Wait until every row in cols[b..e) carries the current epoch flag. Lanes poll different
+// dependencies in parallel. Returns false if the watchdog fired.
+__device__ __forceinline__ bool wait_deps(const unsigned* flags, const int* cols, int b, int e, unsigned epoch,
+                                          int lane, NRStat* st, int errbit) {
+  bool ok = true;
+  for (int p = b + lane; p < e; p += 32) {
+    const unsigned* f = flags + cols[p];
+    unsigned spins = 0;
+    while (ld_acquire_u32(f) != epoch) {
+      if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); ok = false; break; }
+      __nanosleep(32);
+    }
+  }
+  __syncwarp();
+  return ok;
+}
+
+// Numeric refactorisation.  One warp per row, rows handed out in dependency-level order.  Inside
+// a row the entries are evaluated wave by wave: each entry gathers its contributor products
+// L(i,k)*U(k,j) in ascending k (bit-identical to the classic k-sequential row update), and the
+// entries of one wave are independent, so the 4,800-entry supply-rail rows take ~150 parallel
+// waves instead of 4,800 serial updates.
+__global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __restrict__ csr, NRStat* st) {
+  const unsigned epoch = st->epoch;
+  const int lane = threadIdx.x & 31;
+  const int n = lu.n;
+  while (true) {
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(&st->ticket_f, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= (unsigned)n) break;
+    const int i = lu.order_l[tk];
+    const int rb = lu.ptr[i], dg = lu.diag[i];
+    wait_deps(lu.flag_f, lu.col, rb, dg, epoch, lane, st, 1);
+    const int w0 = lu.row_wave_ptr[i], w1 = lu.row_wave_ptr[i + 1];
+    int eb = rb;
+    for (int w = w0; w < w1; ++w) {
+      const int ee = lu.wave_end[w];
+      for (int q = eb + lane; q < ee; q += 32) {
+        const int pos = lu.ent_order[q];
+        const int s = lu.src[pos];
+        double acc = s >= 0 ? csr[s] : 0.0;
+        const long long pb = lu.pair_ptr[pos], pe = lu.pair_ptr[pos + 1];
+        for (long long pr = pb; pr < pe; ++pr) acc -= lu.val[lu.pair_l[pr]] * __ldcg(lu.val + lu.pair_u[pr]);
+        if (pos < dg) acc *= __ldcg(lu.inv_diag + lu.col[pos]);
+        lu.val[pos] = acc;
+      }
+      eb = ee;
+      __syncwarp();
+    }
+    if (lane == 0) {
+      double d = lu.val[dg];
+      if (d == 0.0 || d != d) atomicOr(&st->error, 2);
+      lu.inv_diag[i] = 1.0 / d;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_u32(lu.flag_f + i, epoch);
+  }
+}
+
+// Deterministic warp sum: fixed butterfly order.
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Forward solve y = L^-1 P b: one warp per row, lanes stride over the row's L entries.
+__global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __restrict__ b, double scale,
+                                                   const unsigned char* __restrict__ zero_mask, NRStat* st) {
+  const unsigned epoch = st->epoch;
+  const int lane = threadIdx.x & 31;
+  const int n = lu.n;
+  while (true) {
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(&st->ticket_l, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= (unsigned)n) break;
+    const int i = lu.order_l[tk];
+    const int rb = lu.ptr[i], dg = lu.diag[i];
+    wait_deps(lu.flag_l, lu.col, rb, dg, epoch, lane, st, 4);
+    double part = 0.0;
+    for (int p = rb + lane; p < dg; p += 32) part += lu.val[p] * __ldcg(lu.y + lu.col[p]);
+    part = warp_sum(part);
+    if (lane == 0) {
+      const int r = lu.perm_r[i];
+      const double bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
+      lu.y[i] = bi - part;
+      __threadfence();
+      st_release_u32(lu.flag_l + i, epoch);
+    }
+  }
+}
+
+// Back solve x = U^-1 y, scattered through the column permutation.
+__global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict__ x_out, NRStat* st) {
+  const unsigned epoch = st->epoch;
+  const int lane = threadIdx.x & 31;
+  const int n = lu.n;
+  while (true) {
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(&st->ticket_u, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= (unsigned)n) break;
+    const int i = lu.order_u[tk];
+    const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
+    wait_deps(lu.flag_u, lu.col, ub, re, epoch, lane, st, 8);
+    double part = 0.0;
+    for (int p = ub + lane; p < re; p += 32) part += lu.val[p] * __ldcg(lu.xp + lu.col[p]);
+    part = warp_sum(part);
+    if (lane == 0) {
+      const double xi = (lu.y[i] - part) * lu.inv_diag[i];
+      lu.xp[i] = xi;
+      x_out[lu.perm_c[i]] = xi;
+      __threadfence();
+      st_release_u32(lu.flag_u + i, epoch);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NR control (reference: _nr_body_common vajax/analysis/solver_factories.py:230-325)
+// ------------------------------------------------------------------------------------------
+__global__ void k_nr_begin(NRStat* st, double* ctl, int max_iter, int reset_iter) {
+  if (reset_iter) {
+    st->iter = 0;
+    st->converged = 0;
+    ctl[VJX_CTL_ITER] = 0.0;
+  }
+  st->max_iter = max_iter;
+  st->cont = 1;
+}
+
+// Runs at the head of every NR iteration: clears the per-iteration reductions and opens a new
+// LU epoch (flags from earlier factorizations become stale without being cleared).
+__global__ void k_iter_begin(NRStat* st) {
+  st->bad_res = 0;
+  st->bad_delta = 0;
+  st->max_f_bits = 0ULL;
+  st->max_dv_bits = 0ULL;
+  st->lim_delta_bits = 0ULL;
+  st->lim_ref_bits = 0ULL;
+  st->epoch += 1u;
+  st->ticket_f = 0u;
+  st->ticket_l = 0u;
+  st->ticket_u = 0u;
+}
+
+struct UpdateArgs {
+  int n_unknowns, n_vs, n_total, n_lim;
+  const double* delta;
+  double* X;
+  const unsigned char* delta_mask;  // residual_mask (NOI excluded)
+  const unsigned char* is_noi;      // per node (index in V)
+  const double* limit_in;
+  const double* limit_out;
+  double damping, reltol, vntol, abstol, max_step;
+  NRStat* st;
+};
+
+__global__ void k_delta_reduce(UpdateArgs a) {
+  const int n_aug = a.n_unknowns + a.n_vs;
+  int bad = 0;
+  double mv = 0.0, ld = 0.0, lr = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_aug; i += gridDim.x * blockDim.x) {
+    double d = a.delta[i];
+    double cd = (i < a.n_unknowns) ? d * a.damping : d;
+    double xr = a.X[i + 1];
+    double tol = fmax(fabs(xr) * a.reltol, (i < a.n_unknowns) ? a.vntol : a.abstol);
+    if (!a.delta_mask[i]) cd = 0.0;
+    if (!(fabs(cd) < tol)) bad = 1;
+    if (i < a.n_unknowns) {
+      double ad = fabs(d);
+      mv = (ad != ad) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(mv, ad);
+    }
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_lim; i += gridDim.x * blockDim.x) {
+    ld = fmax(ld, fabs(a.limit_out[i] - a.limit_in[i]));
+    lr = fmax(lr, fabs(a.limit_in[i]));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    double t = __shfl_xor_sync(0xffffffffu, mv, o);
+    mv = (mv != mv || t != t) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(mv, t);
+    ld = fmax(ld, __shfl_xor_sync(0xffffffffu, ld, o));
+    lr = fmax(lr, __shfl_xor_sync(0xffffffffu, lr, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicOr(&a.st->bad_delta, 1);
+    if (mv != mv) atomicMax(&a.st->max_dv_bits, 0x7ff8000000000000ULL);
+    else if (mv > 0.0) atomic_max_pos(&a.st->max_dv_bits, mv);
+    if (ld > 0.0) atomic_max_pos(&a.st->lim_delta_bits, ld);
+    if (lr > 0.0) atomic_max_pos(&a.st->lim_ref_bits, lr);
+  }
+}
+
+__global__ void k_nr_update(UpdateArgs a, double* ctl, double* limit_state, cudaGraphConditionalHandle handle,
+                            int use_handle) {
+  const int n_aug = a.n_unknowns + a.n_vs;
+  const double maxv = __longlong_as_double((long long)a.st->max_dv_bits);
+  const double scale = fmin(1.0, a.max_step / fmax(maxv, 1e-30));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_aug; i += gridDim.x * blockDim.x) {
+    double d = a.delta[i];
+    double x = a.X[i + 1];
+    if (i < a.n_unknowns) {
+      x = x + d * scale * a.damping;
+      if (a.is_noi[i + 1]) x = 0.0;
+    } else {
+      x = x + d;
+    }
+    a.X[i + 1] = x;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_lim; i += gridDim.x * blockDim.x)
+    limit_state[i] = a.limit_out[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    NRStat* st = a.st;
+    int it = st->iter;
+    bool conv = (st->bad_res == 0) && (it == 0 || st->bad_delta == 0);
+    if (a.n_lim > 0) {
+      double ld = __longlong_as_double((long long)st->lim_delta_bits);
+      double lref = fmax(__longlong_as_double((long long)st->lim_ref_bits) * a.reltol, a.vntol);
+      conv = conv && (ld < lref) && (it >= 1);
+    }
+    st->converged = conv ? 1 : 0;
+    st->iter = it + 1;
+    ctl[VJX_CTL_ITER] = (double)(it + 1);
+    int cont = (!conv && (it + 1) < st->max_iter) ? 1 : 0;
+    st->cont = cont;
+    if (use_handle) cudaGraphSetConditional(handle, cont);
+  }
+}
+
+__global__ void k_dqdt(int n, const double* ctl, const double* Q, const double* Qp, const double* dq,
+                       const double* q2, double* out) {
+  const double c0 = ctl[VJX_CTL_C0], c1 = ctl[VJX_CTL_C1], d1 = ctl[VJX_CTL_D1], c2 = ctl[VJX_CTL_C2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double a = Qp ? Qp[i] : 0.0, b = dq ? dq[i] : 0.0, c = q2 ? q2[i] : 0.0;
+    out[i] = c0 * Q[i] + c1 * a + d1 * b + c2 * c;
+  }
+}
+
+__global__ void k_set_ctl(double* ctl, double c0, double c1, double d1, double c2, double gmin, double gshunt,
+                          double iter, double diagreg) {
+  ctl[VJX_CTL_C0] = c0;
+  ctl[VJX_CTL_C1] = c1;
+  ctl[VJX_CTL_D1] = d1;
+  ctl[VJX_CTL_C2] = c2;
+  ctl[VJX_CTL_GMIN] = gmin;
+  ctl[VJX_CTL_GSHUNT] = gshunt;
+  ctl[VJX_CTL_ITER] = iter;
+  ctl[VJX_CTL_DIAGREG] = diagreg;
+}
+
+__global__ void k_copy(int n, const double* src, double* dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src ? src[i] : 0.0;
+}
+__global__ void k_fill(int n, double v, double* dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Transient step control (reference: body_fn vajax/analysis/transient/full_mna.py:1840-2194,
+// predict_voltage_jax / compute_lte_timestep_jax vajax/analysis/transient/adaptive.py:94-339)
+// ------------------------------------------------------------------------------------------
+struct StepArgs {
+  TranScalars* ts;
+  NRStat* st;
+  double* ctl;
+  vjx_options o;
+  int n_total, n_unknowns, n_vs, n_is, n_ext, n_lim, H;
+  const vjx_source_desc* vsrc_desc;
+  const vjx_source_desc* isrc_desc;
+  const double* pwl_t;
+  const double* pwl_v;
+  double* vsrc;       // [n_vs] source values at t_next
+  double* isrc;       // [n_is]
+  double* X;          // accepted solution [n_total + n_vs]
+  double* Xw;         // NR working vector
+  double* Vpred;      // [n_total]
+  double* Vhist;      // [H][n_total] ring
+  double* Vmax;       // [n_total]
+  double* Q_prev;     // [n_unknowns]
+  double* dQdt_prev;
+  double* Q_prev2;
+  double* Qw;         // Q from the final build
+  double* dQdtw;
+  double* Ivs;        // [n_vs]
+  double* maxres_w;   // [n_unknowns]
+  double* hist_mrc;   // [n_unknowns]
+  double* res_tol_floor;
+  double* limit_state;  // accepted
+  double* limit_w;      // working (NR in/out)
+  double* times_out;
+  double* V_out;
+  double* I_out;
+  double* records;    // 8 doubles per attempt
+  int max_records;
+};
+
+__global__ void k_pre_step(StepArgs a, cudaGraphConditionalHandle nr_handle, int use_handle) {
+  TranScalars* s = a.ts;
+  __shared__ double sh_tnext;
+  if (threadIdx.x == 0) {
+    const double dt_cur = s->dt;
+    const double inv_dt = 1.0 / dt_cur;
+    double c0, c1, d1, c2, eci;
+    if (a.o.integration_method == 0) {
+      c0 = inv_dt; c1 = -inv_dt; d1 = 0.0; c2 = 0.0; eci = -0.5;
+    } else if (a.o.integration_method == 1) {
+      c0 = 2.0 * inv_dt; c1 = -2.0 * inv_dt; d1 = -1.0; c2 = 0.0; eci = 1.0 / 24.0;
+    } else {
+      double dt_prev = s->dt_hist[0];
+      double omega = dt_prev > 0 ? dt_cur / dt_prev : 1.0;
+      double op1 = 1.0 + omega;
+      c0 = (1.0 + 2.0 * omega) / (op1 * dt_cur);
+      c1 = -op1 / dt_cur;
+      d1 = 0.0;
+      c2 = (omega * omega) / (op1 * dt_cur);
+      eci = -2.0 / 9.0;
+    }
+    const double t_next = s->t + dt_cur;
+    s->t_next = t_next;
+    s->dt_cur = dt_cur;
+    s->eci = eci;
+    sh_tnext = t_next;
+    s->can_predict = (s->warmup >= a.o.warmup_steps) && (s->hist_count >= 2);
+    // predictor coefficients (adaptive.py:114-168)
+    int order = min(s->hist_count - 1, a.o.max_order);
+    order = max(order, 0);
+    const double new_dt = dt_cur;
+    double cum0 = s->dt_hist[0];
+    double cum1 = cum0 + s->dt_hist[1];
+    double tau1 = -(new_dt + cum0) / new_dt;
+    double tau2 = -(new_dt + cum1) / new_dt;
+    double ratio1 = new_dt / fmax(s->dt_hist[0], 1e-30);
+    double tau0 = -1.0;
+    double den0 = (tau0 - tau1) * (tau0 - tau2);
+    double den1 = (tau1 - tau0) * (tau1 - tau2);
+    double den2 = (tau2 - tau0) * (tau2 - tau1);
+    den0 = fabs(den0) < 1e-30 ? 1e-30 : den0;
+    den1 = fabs(den1) < 1e-30 ? 1e-30 : den1;
+    den2 = fabs(den2) < 1e-30 ? 1e-30 : den2;
+    double l0 = (0 - tau1) * (0 - tau2) / den0;
+    double l1 = (0 - tau0) * (0 - tau2) / den1;
+    double l2 = (0 - tau0) * (0 - tau1) / den2;
+    double aa[3], err;
+    if (order == 0) { aa[0] = 1.0; aa[1] = 0.0; aa[2] = 0.0; err = 1.0; }
+    else if (order == 1) { aa[0] = 1.0 + ratio1; aa[1] = -ratio1; aa[2] = 0.0; err = -ratio1 * (1 + ratio1) / 2; }
+    else { aa[0] = l0; aa[1] = l1; aa[2] = l2; err = -tau0 * tau1 * tau2 / 6; }
+    for (int k = 0; k < 3; ++k) s->a[k] = (k <= order) ? aa[k] : 0.0;
+    s->pred_err = err;
+    // gshunt ramp (full_mna.py:1914-1920)
+    double ramp = 1.0;
+    if (a.o.gshunt_steps > 0) ramp = fmin(fmax((double)s->step_idx / (double)a.o.gshunt_steps, 0.0), 1.0);
+    double gsh = a.o.gshunt_init + ramp * (a.o.gshunt_target - a.o.gshunt_init);
+    s->gshunt = gsh;
+    a.ctl[VJX_CTL_C0] = c0;
+    a.ctl[VJX_CTL_C1] = c1;
+    a.ctl[VJX_CTL_D1] = d1;
+    a.ctl[VJX_CTL_C2] = c2;
+    a.ctl[VJX_CTL_GMIN] = 1e-12;  // body_fn passes the literal 1e-12 (full_mna.py:1948)
+    a.ctl[VJX_CTL_GSHUNT] = gsh;
+    a.ctl[VJX_CTL_ITER] = 0.0;
+    a.ctl[VJX_CTL_DIAGREG] = a.o.gmin;
+    s->lte_bits = 0ULL;
+    a.st->iter = 0;
+    a.st->converged = 0;
+    a.st->max_iter = a.o.tran_itl;
+    a.st->cont = 1;
+    s->attempts += 1;
+    if (use_handle) cudaGraphSetConditional(nr_handle, 1);
+  }
+  __syncthreads();
+  const double t_next = sh_tnext;
+  for (int v = threadIdx.x; v < a.n_vs; v += blockDim.x) a.vsrc[v] = eval_source(a.vsrc_desc[v], t_next, a.pwl_t, a.pwl_v);
+  for (int v = threadIdx.x; v < a.n_is; v += blockDim.x) a.isrc[v] = eval_source(a.isrc_desc[v], t_next, a.pwl_t, a.pwl_v);
+}
+
+__global__ void k_predict(StepArgs a) {
+  const TranScalars* s = a.ts;
+  const int H = a.H, head = s->hist_head;
+  const double a0 = s->a[0], a1 = s->a[1], a2 = s->a[2];
+  const double* h0 = a.Vhist + (size_t)((head + 0) % H) * a.n_total;
+  const double* h1 = a.Vhist + (size_t)((head + 1) % H) * a.n_total;
+  const double* h2 = a.Vhist + (size_t)((head + 2) % H) * a.n_total;
+  const int can = s->can_predict;
+  const int nx = a.n_total + a.n_vs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    if (i < a.n_total) {
+      double vp = a0 * h0[i] + a1 * h1[i] + a2 * h2[i];
+      a.Vpred[i] = vp;
+      a.Xw[i] = can ? vp : a.X[i];
+    } else {
+      a.Xw[i] = a.X[i];
+    }
+    if (i < a.n_unknowns) a.res_tol_floor[i] = fmax(a.hist_mrc[i] * a.o.lte_reltol, a.o.lte_abstol);
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_lim; i += gridDim.x * blockDim.x)
+    a.limit_w[i] = a.limit_state[i];
+}
+
+__global__ void k_lte(StepArgs a) {
+  const TranScalars* s = a.ts;
+  const double scale = s->eci / (s->eci - s->pred_err);
+  double m = 0.0;
+  bool isnan_ = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_total; i += gridDim.x * blockDim.x) {
+    double vn = a.Xw[i], vp = a.Vpred[i];
+    double lte = (vn - vp) * scale;
+    double vc = fmax(fabs(vn), fabs(vp));
+    double vs = fmax(a.Vmax[i], vc);
+    double tol = a.o.lte_reltol * vs + a.o.lte_abstol;
+    double r = fabs(lte) / tol;
+    if (r != r) isnan_ = true; else m = fmax(m, r);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    isnan_ |= (bool)__shfl_xor_sync(0xffffffffu, (int)isnan_, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (isnan_) atomicMax(&a.ts->lte_bits, 0x7ff8000000000000ULL);
+    else if (m > 0.0) atomic_max_pos(&a.ts->lte_bits, m);
+  }
+}
+
+__global__ void k_step_decide(StepArgs a, cudaGraphConditionalHandle handle, int use_handle, int max_attempts_total) {
+  TranScalars* s = a.ts;
+  const NRStat* st = a.st;
+  const vjx_options& o = a.o;
+  const double dt_cur = s->dt_cur, t_next = s->t_next;
+  const bool converged = st->converged != 0;
+  const int iterations = st->iter;
+  const bool can_predict = s->can_predict != 0;
+  const double lte_norm = __longlong_as_double((long long)s->lte_bits);
+  // compute_lte_timestep_jax (adaptive.py:333-339)
+  int order = min(s->hist_count - 1, o.max_order);
+  double factor = pow(o.lte_ratio / fmax(lte_norm, 1e-10), 1.0 / (double)(order + 1));
+  if (lte_norm != lte_norm) factor = lte_norm;
+  factor = fmin(fmax(factor, 0.1), o.grow_factor);
+  if (lte_norm != lte_norm) factor = lte_norm;
+  const double dt_lte = dt_cur * factor;
+  const bool nr_failed = !converged;
+  const bool at_min_dt = dt_cur <= o.min_dt;
+  const bool nr_fail_min = nr_failed && at_min_dt;
+  const bool lte_reject = (dt_cur / dt_lte > o.redo_factor) && can_predict && converged;
+  const bool nr_reject = nr_failed && !at_min_dt;
+  const bool force_accept = s->consec >= o.max_consecutive_rejects;
+  const bool reject = (lte_reject || nr_reject) && !force_accept;
+  const bool accept = !reject;
+  const int consec = accept ? 0 : (lte_reject ? s->consec + 1 : s->consec);
+  const double dt_from_lte = can_predict ? dt_lte : dt_cur;
+  const double dt_nr = fmax(dt_cur * o.tran_ft, o.min_dt);
+  const double last_good = s->hist_count > 0 ? s->dt_hist[0] : o.min_dt * 16.0;
+  const double dt_rec = fmax(last_good / 8.0, o.min_dt * 2.0);
+  double new_dt = nr_failed ? (at_min_dt ? dt_rec : dt_nr) : dt_from_lte;
+  new_dt = fmin(fmax(new_dt, o.min_dt), s->max_dt);
+  if (dt_from_lte != dt_from_lte && !nr_failed) new_dt = dt_from_lte;
+  new_dt = fmin(new_dt, s->t_stop - t_next);
+  const bool use_new = accept && !nr_fail_min;
+  s->accept = accept;
+  s->use_new = use_new;
+  s->nr_fail_min = nr_fail_min;
+  s->lte_reject = lte_reject;
+  s->nr_failed = nr_failed;
+  s->reject = reject;
+  s->new_dt = new_dt;
+  if (s->attempts <= a.max_records) {
+    double* r = a.records + (size_t)(s->attempts - 1) * 8;
+    r[0] = (double)s->step_idx;
+    r[1] = t_next;
+    r[2] = dt_cur;
+    r[3] = (double)iterations;
+    r[4] = accept ? 1.0 : 0.0;
+    r[5] = lte_reject ? 1.0 : 0.0;
+    r[6] = nr_failed ? 1.0 : 0.0;
+    r[7] = lte_norm;
+  }
+  // scalar state update (vector state is committed by k_step_commit using the flags above)
+  if (accept) {
+    a.times_out[s->step_idx] = t_next;
+    s->t = t_next;
+    s->min_dt_used = fmin(s->min_dt_used, dt_cur);
+    s->max_dt_used = fmax(s->max_dt_used, dt_cur);
+  }
+  s->total_nr += iterations;
+  s->rejected += reject ? 1 : 0;
+  s->consec = consec;
+  s->dt = new_dt;
+  // hist/step counters are bumped in k_step_commit's thread 0 after the vector commit is issued
+  (void)handle; (void)use_handle; (void)max_attempts_total;
+}
+
+__global__ void k_step_commit(StepArgs a, cudaGraphConditionalHandle handle, int use_handle, int attempts_limit) {
+  TranScalars* s = a.ts;
+  const int accept = s->accept, use_new = s->use_new, nr_fail_min = s->nr_fail_min;
+  const int H = a.H;
+  const int new_head = (s->hist_head + H - 1) % H;
+  const int row = s->step_idx;
+  const int nx = a.n_total + a.n_vs;
+  const int nvs1 = a.n_vs > 0 ? a.n_vs : 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    double xn = a.Xw[i];
+    if (use_new) {
+      a.X[i] = xn;
+      if (i < a.n_total) {
+        a.Vhist[(size_t)new_head * a.n_total + i] = xn;
+        a.Vmax[i] = fmax(a.Vmax[i], fabs(xn));
+      }
+      if (i < a.n_unknowns) {
+        double qp = a.Q_prev[i];
+        a.Q_prev2[i] = qp;
+        a.Q_prev[i] = a.Qw[i];
+        a.dQdt_prev[i] = a.dQdtw[i];
+        a.hist_mrc[i] = fmax(a.hist_mrc[i], a.maxres_w[i]);
+      }
+    }
+    if (accept) {
+      if (i < a.n_ext) a.V_out[(size_t)row * a.n_ext + i] = use_new ? xn : a.X[i];
+      if (i < nvs1) a.I_out[(size_t)row * nvs1 + i] = (a.n_vs > 0 && !nr_fail_min) ? a.Ivs[i] : 0.0;
+    }
+  }
+  if (use_new)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_lim; i += gridDim.x * blockDim.x)
+      a.limit_state[i] = a.limit_w[i];
+}
+
+// Runs after k_step_commit (separate launch => ordered after all vector writes).
+__global__ void k_step_finish(StepArgs a, cudaGraphConditionalHandle handle, int use_handle, int attempts_limit) {
+  TranScalars* s = a.ts;
+  if (s->use_new) {
+    s->hist_head = (s->hist_head + a.H - 1) % a.H;
+    s->dt_hist[3] = s->dt_hist[2];
+    s->dt_hist[2] = s->dt_hist[1];
+    s->dt_hist[1] = s->dt_hist[0];
+    s->dt_hist[0] = s->dt_cur;
+    s->hist_count = min(s->hist_count + 1, a.H);
+    s->warmup += 1;
+  }
+  if (s->accept) s->step_idx += 1;
+  int cont = (s->t < s->t_stop) && (s->step_idx < s->max_steps) && (s->attempts < s->attempts_limit) &&
+             (a.st->error == 0);
+  s->cont = cont;
+  if (use_handle) cudaGraphSetConditional(handle, cont);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t count) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = count;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+};
+
+struct ModelState {
+  void* dl = nullptr;
+  vjx_model_eval_fn eval = nullptr;
+  vjx_model_set_const_fn set_const = nullptr;
+  int n_dev = 0, n_volt = 0, n_dev_params = 0, n_dev_cache = 0, R = 0, J = 0, n_lim = 0;
+  int n_shared = 0, n_shared_cache = 0, n_simparams = 0;
+  int limit_offset = 0;
+  std::vector<double> simparam_defaults;
+  DevBuf<int> vnode1, vnode2, jdest, vdest;
+  DevBuf<double> dev_params, dev_cache;
+};
+
+struct vjx_handle {
+  int device = 0;
+  int n_total = 0, n_unknowns = 0, n_ext = 0, n_vs = 0, n_is = 0, n_aug = 0, nse = 0, total_lim = 0;
+  vjx_options o{};
+  std::vector<int> h_indptr, h_indices;
+  std::vector<ModelState*> models;
+  // stamping tables
+  DevBuf<int> jseg, vseg, isrc_dest, att_ptr, att_idx, vs_p, vs_n;
+  DevBuf<signed char> att_sign;
+  DevBuf<unsigned char> slot_flags, conv_mask, delta_mask, is_noi, noi_row_mask;
+  DevBuf<float> slot_const;
+  DevBuf<double> jsorted, vsorted;
+  size_t n_jcontrib = 0, n_vcontrib = 0;
+  // work vectors
+  DevBuf<double> ctl, csr, f, delta, Xw, Qw, dQdtw, Ivs, maxres_w, limit_w, limit_out, zeros, abstol_floor;
+  DevBuf<NRStat> st;
+  // sources
+  DevBuf<vjx_source_desc> vsrc_desc, isrc_desc;
+  DevBuf<double> pwl_t, pwl_v, vsrc_val, isrc_val;
+  // LU
+  bool lu_ready = false;
+  VjxSymbolic sym;
+  DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_order_l, lu_order_u, lu_perm_r, lu_perm_c;
+  DevBuf<long long> lu_pair_ptr;
+  DevBuf<int> lu_pair_l, lu_pair_u, lu_ent_order, lu_row_wave_ptr, lu_wave_end;
+  DevBuf<unsigned> lu_flags;
+  DevBuf<double> lu_val, lu_inv, lu_y, lu_xp;
+  LUDev lud{};
+  int lu_grid_f = 0, lu_grid_s = 0;
+  // transient
+  DevBuf<TranScalars> ts;
+  DevBuf<double> X, Vpred, Vhist, Vmax, Q_prev, dQdt_prev, Q_prev2, hist_mrc, res_tol_floor, limit_state;
+  DevBuf<double> times_out, V_out, I_out, records;
+  int max_steps = 0, max_records = 0, H = 4;
+  // graphs
+  cudaGraphExec_t g_iter = nullptr;    // one NR iteration
+  cudaGraphExec_t g_final = nullptr;   // final build + dQdt
+  cudaGraphExec_t g_step_pre = nullptr, g_step_post = nullptr;
+  cudaGraphExec_t g_tran = nullptr;    // whole device-resident loop (WHILE nodes)
+  int g_tran_limit = 0;
+  cudaStream_t own_stream = nullptr;
+  void* pinned = nullptr;
+  long long launches = 0;
+  int sm_count = 148;
+  ~vjx_handle();
+};
+
+vjx_handle::~vjx_handle() {
+  for (auto* m : models) {
+    if (m) {
+      if (m->dl) dlclose(m->dl);
+      delete m;
+    }
+  }
+  if (g_iter) cudaGraphExecDestroy(g_iter);
+  if (g_final) cudaGraphExecDestroy(g_final);
+  if (g_step_pre) cudaGraphExecDestroy(g_step_pre);
+  if (g_step_post) cudaGraphExecDestroy(g_step_post);
+  if (g_tran) cudaGraphExecDestroy(g_tran);
+  if (own_stream) cudaStreamDestroy(own_stream);
+  if (pinned) cudaFreeHost(pinned);
+}
+
+static inline int grid_for(const vjx_handle* h, long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  long long cap = (long long)h->sm_count * 8;
+  if (g < 1) g = 1;
+  return (int)std::min(g, cap);
+}
+
+static int csr_find(const std::vector<int>& indptr, const std::vector<int>& indices, int r, int c) {
+  auto b = indices.begin() + indptr[r], e = indices.begin() + indptr[r + 1];
+  auto it = std::lower_bound(b, e, c);
+  if (it == e || *it != c) return -1;
+  return (int)(it - indices.begin());
+}
+
+extern "C" const char* vjx_last_error(void) { return g_err.c_str(); }
+extern "C" int vjx_version(void) { return 100; }
+extern "C" int vjx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+extern "C" void vjx_clear_cache(void) {}
+
+extern "C" void vjx_destroy(vjx_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  delete h;
+}
+
+extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** out) {
+  if (!d || !out) return fail(VJX_ERR_INVALID, "null descriptor");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(VJX_ERR_NODEVICE, "no CUDA device visible: libvajax_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(VJX_ERR_INVALID, "bad device index");
+  CK(cudaSetDevice(device));
+  std::unique_ptr<vjx_handle> h(new vjx_handle());
+  h->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  h->n_total = d->n_total;
+  h->n_unknowns = d->n_total - 1;
+  h->n_ext = d->n_external;
+  h->n_vs = d->n_vsources;
+  h->n_is = d->n_isources;
+  h->n_aug = h->n_unknowns + h->n_vs;
+  h->nse = d->nse;
+  h->o = d->opts;
+  const int nu = h->n_unknowns, n_aug = h->n_aug, nse = h->nse;
+  if (nu < 0 || nse <= 0 || !d->csr_indptr || !d->csr_indices) return fail(VJX_ERR_INVALID, "bad sizes");
+  // ---- CSR validation, once (umfpack_ffi.cpp:60-93; full_mna.py:483-513)
+  h->h_indptr.assign(d->csr_indptr, d->csr_indptr + n_aug + 1);
+  h->h_indices.assign(d->csr_indices, d->csr_indices + nse);
+  if (h->h_indptr[0] != 0 || h->h_indptr[n_aug] != nse) return fail(VJX_ERR_INVALID, "CSR indptr ends mismatch");
+  for (int r = 0; r < n_aug; ++r) {
+    if (h->h_indptr[r + 1] < h->h_indptr[r]) return fail(VJX_ERR_INVALID, "CSR indptr not monotonic");
+    for (int p = h->h_indptr[r]; p < h->h_indptr[r + 1]; ++p) {
+      int c = h->h_indices[p];
+      if (c < 0 || c >= n_aug) return fail(VJX_ERR_INVALID, "CSR column index out of range");
+      if (p > h->h_indptr[r] && c <= h->h_indices[p - 1]) return fail(VJX_ERR_INVALID, "CSR columns not strictly sorted");
+    }
+  }
+  // ---- Jacobian contributions: count per slot in the reference's scatter order
+  std::vector<int> jcount(nse, 0);
+  std::vector<std::vector<int>> slots(d->n_models);
+  h->total_lim = 0;
+  for (int m = 0; m < d->n_models; ++m) {
+    const vjx_model_desc& md = d->models[m];
+    auto* ms = new ModelState();
+    h->models.push_back(ms);
+    ms->n_dev = md.n_dev; ms->n_volt = md.n_volt; ms->n_dev_params = md.n_dev_params;
+    ms->n_dev_cache = md.n_dev_cache; ms->R = md.n_res; ms->J = md.n_jac; ms->n_lim = md.n_lim;
+    ms->n_shared = md.n_shared; ms->n_shared_cache = md.n_shared_cache; ms->n_simparams = md.n_simparams;
+    ms->limit_offset = h->total_lim;
+    h->total_lim += md.n_lim * md.n_dev;
+    auto& sl = slots[m];
+    sl.assign((size_t)md.n_dev * md.n_jac, -1);
+    for (int dv = 0; dv < md.n_dev; ++dv)
+      for (int e = 0; e < md.n_jac; ++e) {
+        int r = md.jac_row[(size_t)dv * md.n_jac + e], c = md.jac_col[(size_t)dv * md.n_jac + e];
+        if (r < 0 || c < 0) continue;
+        if (r >= n_aug || c >= n_aug) return fail(VJX_ERR_INVALID, "stamp index out of range");
+        int s = csr_find(h->h_indptr, h->h_indices, r, c);
+        if (s < 0) return fail(VJX_ERR_INVALID, "device Jacobian entry outside the CSR pattern");
+        sl[(size_t)dv * md.n_jac + e] = s;
+        jcount[s]++;
+      }
+  }
+  std::vector<int> jseg(nse + 1, 0);
+  for (int s = 0; s < nse; ++s) jseg[s + 1] = jseg[s] + jcount[s];
+  h->n_jcontrib = (size_t)jseg[nse];
+  {
+    std::vector<int> nxt(jseg.begin(), jseg.end() - 1);
+    for (int m = 0; m < d->n_models; ++m) {
+      const vjx_model_desc& md = d->models[m];
+      std::vector<int> dest((size_t)md.n_dev * md.n_jac, -1);  // SoA (J, n_dev)
+      for (int dv = 0; dv < md.n_dev; ++dv)
+        for (int e = 0; e < md.n_jac; ++e) {
+          int s = slots[m][(size_t)dv * md.n_jac + e];
+          if (s >= 0) dest[(size_t)e * md.n_dev + dv] = nxt[s]++;
+        }
+      CK(h->models[m]->jdest.upload(dest));
+    }
+  }
+  CK(h->jseg.upload(jseg));
+  CK(h->jsorted.alloc(std::max<size_t>(h->n_jcontrib, 1)));
+  // ---- slot flags: diagonal regularisation, vsource incidence, NOI rows/cols
+  std::vector<unsigned char> flags(nse, 0);
+  std::vector<float> cst(nse, 0.0f);
+  for (int i = 0; i < nu; ++i) {
+    int s = csr_find(h->h_indptr, h->h_indices, i, i);
+    if (s < 0) return fail(VJX_ERR_INVALID, "diagonal entry missing from the CSR pattern");
+    flags[s] |= SLOT_DIAG;
+  }
+  for (int v = 0; v < h->n_vs; ++v) {
+    int p = d->vs_node_p[v], n = d->vs_node_n[v];
+    if (p < 0 || p >= h->n_total || n < 0 || n >= h->n_total) return fail(VJX_ERR_INVALID, "vsource node out of range");
+    int br = nu + v;
+    struct { int r, c; float val; } ent[4] = {{p - 1, br, 1.f}, {n - 1, br, -1.f}, {br, p - 1, 1.f}, {br, n - 1, -1.f}};
+    for (int k = 0; k < 4; ++k) {
+      if (ent[k].r < 0 || ent[k].c < 0) continue;
+      int s = csr_find(h->h_indptr, h->h_indices, ent[k].r, ent[k].c);
+      if (s < 0) return fail(VJX_ERR_INVALID, "vsource incidence entry missing from the CSR pattern");
+      cst[s] += ent[k].val;
+    }
+  }
+  std::vector<unsigned char> is_noi(h->n_total, 0), noi_row(n_aug, 0);
+  for (int k = 0; k < d->n_noi; ++k) {
+    int nd = d->noi_nodes[k];
+    if (nd <= 0 || nd >= h->n_total) return fail(VJX_ERR_INVALID, "NOI node index out of range");
+    is_noi[nd] = 1;
+    noi_row[nd - 1] = 1;
+  }
+  if (d->n_noi > 0)
+    for (int r = 0; r < n_aug; ++r)
+      for (int p = h->h_indptr[r]; p < h->h_indptr[r + 1]; ++p) {
+        int c = h->h_indices[p];
+        if (noi_row[r]) flags[p] |= SLOT_NOI_ZERO;
+        if (r < nu && noi_row[c]) flags[p] |= SLOT_NOI_ZERO;
+        if (noi_row[r] && c == r) flags[p] |= SLOT_NOI_ONE;
+      }
+  CK(h->slot_flags.upload(flags));
+  CK(h->slot_const.upload(cst));
+  CK(h->is_noi.upload(is_noi));
+  CK(h->noi_row_mask.upload(noi_row));
+  // ---- convergence masks (solver_factories.py:86-101, 1018-1036); negative indices wrap on the
+  // n_unknowns-long node mask exactly like jnp's .at[]
+  std::vector<unsigned char> conv(n_aug, 1), dmask(n_aug, 1);
+  for (int k = 0; k < d->n_noi; ++k) dmask[d->noi_nodes[k] - 1] = 0;
+  if (d->n_internal > 0) {
+    for (int k = 0; k < d->n_internal; ++k) {
+      int idx = d->internal_nodes[k] - 1;
+      if (idx < 0) idx += nu;
+      if (idx >= 0 && idx < nu) conv[idx] = 0;
+    }
+  } else {
+    conv = dmask;
+  }
+  CK(h->conv_mask.upload(conv));
+  CK(h->delta_mask.upload(dmask));
+  // ---- vector contributions sorted by row: isources first, then models in order
+  std::vector<int> vcount(std::max(nu, 1), 0);
+  auto is_idx = [&](int node) { return node != 0 ? node - 1 : -1; };
+  for (int i = 0; i < h->n_is; ++i) {
+    int a = is_idx(d->is_node_p[i]), b = is_idx(d->is_node_n[i]);
+    if (a >= nu || b >= nu) return fail(VJX_ERR_INVALID, "isource node out of range");
+    if (a >= 0) vcount[a]++;
+    if (b >= 0) vcount[b]++;
+  }
+  for (int m = 0; m < d->n_models; ++m) {
+    const vjx_model_desc& md = d->models[m];
+    for (size_t k = 0; k < (size_t)md.n_dev * md.n_res; ++k) {
+      int r = md.res_idx[k];
+      if (r >= nu) return fail(VJX_ERR_INVALID, "residual index out of range");
+      if (r >= 0) vcount[r]++;
+    }
+  }
+  std::vector<int> vseg(nu + 1, 0);
+  for (int i = 0; i < nu; ++i) vseg[i + 1] = vseg[i] + vcount[i];
+  h->n_vcontrib = (size_t)vseg[nu];
+  {
+    std::vector<int> nxt(vseg.begin(), vseg.end() - 1);
+    std::vector<int> idest((size_t)std::max(2 * h->n_is, 1), -1);
+    for (int i = 0; i < h->n_is; ++i) {
+      int a = is_idx(d->is_node_p[i]), b = is_idx(d->is_node_n[i]);
+      if (a >= 0) idest[2 * i] = nxt[a]++;
+      if (b >= 0) idest[2 * i + 1] = nxt[b]++;
+    }
+    CK(h->isrc_dest.upload(idest));
+    for (int m = 0; m < d->n_models; ++m) {
+      const vjx_model_desc& md = d->models[m];
+      std::vector<int> dest((size_t)md.n_dev * md.n_res, -1);  // SoA (R, n_dev)
+      for (int dv = 0; dv < md.n_dev; ++dv)
+        for (int r = 0; r < md.n_res; ++r) {
+          int row = md.res_idx[(size_t)dv * md.n_res + r];
+          if (row >= 0) dest[(size_t)r * md.n_dev + dv] = nxt[row]++;
+        }
+      CK(h->models[m]->vdest.upload(dest));
+    }
+  }
+  CK(h->vseg.upload(vseg));
+  CK(h->vsorted.alloc(std::max<size_t>(h->n_vcontrib * 4, 4)));
+  // ---- vsources attached to each node row, in the order of the concatenated [p..., n...] scatter
+  {
+    std::vector<int> cnt(std::max(nu, 1), 0);
+    for (int v = 0; v < h->n_vs; ++v) {
+      if (d->vs_node_p[v] > 0) cnt[d->vs_node_p[v] - 1]++;
+      if (d->vs_node_n[v] > 0) cnt[d->vs_node_n[v] - 1]++;
+    }
+    std::vector<int> ap(nu + 1, 0);
+    for (int i = 0; i < nu; ++i) ap[i + 1] = ap[i] + cnt[i];
+    std::vector<int> ai(std::max(ap[nu], 1), 0), nxt(ap.begin(), ap.end() - 1);
+    std::vector<signed char> as(std::max(ap[nu], 1), 0);
+    for (int v = 0; v < h->n_vs; ++v)
+      if (d->vs_node_p[v] > 0) { int q = nxt[d->vs_node_p[v] - 1]++; ai[q] = v; as[q] = 1; }
+    for (int v = 0; v < h->n_vs; ++v)
+      if (d->vs_node_n[v] > 0) { int q = nxt[d->vs_node_n[v] - 1]++; ai[q] = v; as[q] = -1; }
+    CK(h->att_ptr.upload(ap));
+    CK(h->att_idx.upload(ai));
+    CK(h->att_sign.upload(as));
+    std::vector<int> vp(d->vs_node_p, d->vs_node_p + h->n_vs), vn(d->vs_node_n, d->vs_node_n + h->n_vs);
+    if (vp.empty()) { vp.push_back(0); vn.push_back(0); }
+    CK(h->vs_p.upload(vp));
+    CK(h->vs_n.upload(vn));
+  }
+  // ---- models: plugin + instance tables (SoA on the device)
+  for (int m = 0; m < d->n_models; ++m) {
+    const vjx_model_desc& md = d->models[m];
+    ModelState* ms = h->models[m];
+    ms->dl = dlopen(md.plugin_path, RTLD_NOW | RTLD_LOCAL);
+    if (!ms->dl) return fail(VJX_ERR_PLUGIN, std::string("cannot load model plugin: ") + dlerror());
+    ms->eval = (vjx_model_eval_fn)dlsym(ms->dl, "vjx_model_eval");
+    ms->set_const = (vjx_model_set_const_fn)dlsym(ms->dl, "vjx_model_set_const");
+    if (!ms->eval || !ms->set_const) return fail(VJX_ERR_PLUGIN, "model plugin lacks vjx_model_eval/vjx_model_set_const");
+    auto to_soa_i = [&](const int* src, int rows, int cols) {
+      std::vector<int> o((size_t)rows * cols);
+      for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) o[(size_t)c * rows + r] = src[(size_t)r * cols + c];
+      return o;
+    };
+    auto to_soa_d = [&](const double* src, int rows, int cols) {
+      std::vector<double> o((size_t)rows * cols);
+      for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) o[(size_t)c * rows + r] = src[(size_t)r * cols + c];
+      return o;
+    };
+    for (size_t k = 0; k < (size_t)md.n_dev * md.n_volt; ++k)
+      if (md.vnode1[k] < 0 || md.vnode1[k] >= h->n_total || md.vnode2[k] < 0 || md.vnode2[k] >= h->n_total)
+        return fail(VJX_ERR_INVALID, "voltage node index out of range");
+    CK(ms->vnode1.upload(to_soa_i(md.vnode1, md.n_dev, md.n_volt)));
+    CK(ms->vnode2.upload(to_soa_i(md.vnode2, md.n_dev, md.n_volt)));
+    CK(ms->dev_params.upload(to_soa_d(md.dev_params, md.n_dev, md.n_dev_params)));
+    CK(ms->dev_cache.upload(to_soa_d(md.dev_cache, md.n_dev, md.n_dev_cache)));
+    ms->simparam_defaults.assign(md.simparam_defaults, md.simparam_defaults + md.n_simparams);
+    int rc = ms->set_const(md.shared_params, md.n_shared, md.shared_cache, md.n_shared_cache,
+                           md.simparam_defaults, md.n_simparams, 0);
+    if (rc != 0) return fail(VJX_ERR_PLUGIN, "vjx_model_set_const failed (layout mismatch?) rc=" + std::to_string(rc));
+  }
+  // ---- sources
+  {
+    std::vector<vjx_source_desc> vd(d->vsrc, d->vsrc + h->n_vs), id(d->isrc, d->isrc + h->n_is);
+    if (vd.empty()) vd.push_back(vjx_source_desc{});
+    if (id.empty()) id.push_back(vjx_source_desc{});
+    CK(h->vsrc_desc.upload(vd));
+    CK(h->isrc_desc.upload(id));
+    std::vector<double> pt(d->pwl_times, d->pwl_times + d->n_pwl), pv(d->pwl_values, d->pwl_values + d->n_pwl);
+    if (pt.empty()) { pt.push_back(0); pv.push_back(0); }
+    CK(h->pwl_t.upload(pt));
+    CK(h->pwl_v.upload(pv));
+    CK(h->vsrc_val.alloc(std::max(h->n_vs, 1)));
+    CK(h->isrc_val.alloc(std::max(h->n_is, 1)));
+  }
+  // ---- work vectors
+  const int nl = std::max(h->total_lim, 1);
+  CK(h->ctl.alloc(VJX_CTL_COUNT));
+  CK(h->csr.alloc(nse));
+  CK(h->f.alloc(n_aug));
+  CK(h->delta.alloc(n_aug));
+  CK(h->Xw.alloc(h->n_total + h->n_vs));
+  CK(h->Qw.alloc(std::max(nu, 1)));
+  CK(h->dQdtw.alloc(std::max(nu, 1)));
+  CK(h->Ivs.alloc(std::max(h->n_vs, 1)));
+  CK(h->maxres_w.alloc(std::max(nu, 1)));
+  CK(h->limit_w.alloc(nl));
+  CK(h->limit_out.alloc(nl));
+  CK(h->zeros.alloc(std::max(std::max(n_aug, nl), h->n_total + h->n_vs)));
+  CK(h->st.alloc(1));
+  CK(h->ts.alloc(1));
+  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CK(cudaHostAlloc(&h->pinned, 4096, cudaHostAllocDefault));
+  CK(cudaDeviceSynchronize());
+  *out = h.release();
+  return VJX_OK;
+}
+
+extern "C" int vjx_update_model_data(vjx_handle* h, int model, const double* dev_params, const double* dev_cache,
+                                     const double* shared_params, const double* shared_cache) {
+  if (!h || model < 0 || model >= (int)h->models.size()) return fail(VJX_ERR_INVALID, "bad model index");
+  CK(cudaSetDevice(h->device));
+  ModelState* ms = h->models[model];
+  auto soa = [&](const double* src, int rows, int cols) {
+    std::vector<double> o((size_t)rows * cols);
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) o[(size_t)c * rows + r] = src[(size_t)r * cols + c];
+    return o;
+  };
+  if (dev_params && ms->n_dev_params > 0) {
+    auto v = soa(dev_params, ms->n_dev, ms->n_dev_params);
+    CK(cudaMemcpy(ms->dev_params.p, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (dev_cache && ms->n_dev_cache > 0) {
+    auto v = soa(dev_cache, ms->n_dev, ms->n_dev_cache);
+    CK(cudaMemcpy(ms->dev_cache.p, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (shared_params || shared_cache) {
+    int rc = ms->set_const(shared_params, shared_params ? ms->n_shared : 0, shared_cache,
+                           shared_cache ? ms->n_shared_cache : 0, nullptr, 0, 0);
+    if (rc != 0) return fail(VJX_ERR_PLUGIN, "vjx_model_set_const failed");
+  }
+  return VJX_OK;
+}
+
+extern "C" int vjx_update_sources(vjx_handle* h, const vjx_source_desc* vsrc, const vjx_source_desc* isrc) {
+  if (!h) return fail(VJX_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(h->device));
+  if (vsrc && h->n_vs > 0) CK(cudaMemcpy(h->vsrc_desc.p, vsrc, sizeof(vjx_source_desc) * h->n_vs, cudaMemcpyHostToDevice));
+  if (isrc && h->n_is > 0) CK(cudaMemcpy(h->isrc_desc.p, isrc, sizeof(vjx_source_desc) * h->n_is, cudaMemcpyHostToDevice));
+  return VJX_OK;
+}
+
+// ---- launch helpers -----------------------------------------------------------------------
+struct BuildPtrs {
+  const double* X; const double* vsrc; const double* isrc; const double* Q_prev; const double* dQdt_prev;
+  const double* Q_prev2; const double* limit_in; double* limit_out; const double* res_tol_floor;
+  double* csr; double* f; double* Q; double* Ivs; double* maxres;
+};
+
+static int launch_eval(vjx_handle* h, const BuildPtrs& b, cudaStream_t s) {
+  if (h->n_is > 0) {
+    k_isrc<<<(2 * h->n_is + 127) / 128, 128, 0, s>>>(2 * h->n_is, h->isrc_dest.p, b.isrc, h->vsorted.p);
+    h->launches++;
+  }
+  for (ModelState* ms : h->models) {
+    VjxEvalArgs a;
+    a.n_dev = ms->n_dev;
+    a.V = b.X;
+    a.vnode1 = ms->vnode1.p;
+    a.vnode2 = ms->vnode2.p;
+    a.dev_params = ms->dev_params.p;
+    a.dev_cache = ms->dev_cache.p;
+    a.ctl = h->ctl.p;
+    a.limit_in = (ms->n_lim > 0 && b.limit_in) ? b.limit_in + ms->limit_offset : nullptr;
+    a.limit_out = (ms->n_lim > 0 && b.limit_out) ? b.limit_out + ms->limit_offset : nullptr;
+    a.jdest = ms->jdest.p;
+    a.jsorted = h->jsorted.p;
+    a.vdest = ms->vdest.p;
+    a.vsorted = h->vsorted.p;
+    int rc = ms->eval(&a, s);
+    if (rc != 0) return fail(VJX_ERR_CUDA, "model eval launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+    h->launches++;
+  }
+  return VJX_OK;
+}
+
+static void launch_stamp(vjx_handle* h, double* csr, int enforce_noi, cudaStream_t s) {
+  k_stamp_jacobian<<<grid_for(h, h->nse), 256, 0, s>>>(h->nse, h->jseg.p, h->jsorted.p, h->slot_flags.p,
+                                                       h->slot_const.p, h->ctl.p, enforce_noi, csr);
+  h->launches++;
+}
+
+static void launch_residual(vjx_handle* h, const BuildPtrs& b, int check, cudaStream_t s) {
+  ResidualArgs a;
+  a.n_unknowns = h->n_unknowns; a.n_vs = h->n_vs; a.n_total = h->n_total;
+  a.vseg = h->vseg.p; a.vsorted = h->vsorted.p;
+  a.att_ptr = h->att_ptr.p; a.att_idx = h->att_idx.p; a.att_sign = h->att_sign.p;
+  a.vs_p = h->vs_p.p; a.vs_n = h->vs_n.p;
+  a.X = b.X; a.vsrc = b.vsrc; a.Q_prev = b.Q_prev; a.dQdt_prev = b.dQdt_prev; a.Q_prev2 = b.Q_prev2;
+  a.res_tol_floor = b.res_tol_floor; a.conv_mask = h->conv_mask.p; a.ctl = h->ctl.p;
+  a.reltol = h->o.reltol; a.abstol = h->o.abstol; a.vntol = h->o.vntol;
+  a.f = b.f; a.Q = b.Q; a.Ivs = b.Ivs; a.maxres = b.maxres; a.st = h->st.p; a.check = check;
+  k_residual<<<grid_for(h, h->n_aug), 256, 0, s>>>(a);
+  h->launches++;
+}
+
+static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s);
+
+static void launch_lu(vjx_handle* h, const double* csr, const double* b, double scale, const unsigned char* zero_mask,
+                      double* x, cudaStream_t s) {
+  k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, csr, h->st.p);
+  k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, b, scale, zero_mask, h->st.p);
+  k_lu_usolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, x, h->st.p);
+  h->launches += 3;
+}
+
+static UpdateArgs make_update_args(vjx_handle* h, double* X, const double* limit_in, const double* limit_out) {
+  UpdateArgs a;
+  a.n_unknowns = h->n_unknowns; a.n_vs = h->n_vs; a.n_total = h->n_total; a.n_lim = h->total_lim;
+  a.delta = h->delta.p; a.X = X; a.delta_mask = h->delta_mask.p; a.is_noi = h->is_noi.p;
+  a.limit_in = limit_in; a.limit_out = limit_out;
+  a.damping = h->o.nr_damping; a.reltol = h->o.reltol; a.vntol = h->o.vntol; a.abstol = h->o.abstol;
+  a.max_step = h->o.max_step; a.st = h->st.p;
+  return a;
+}
+
+// One NR iteration on (X, limit_w): reference _nr_body_common.
+static int launch_nr_iteration(vjx_handle* h, const BuildPtrs& b, double* X, cudaGraphConditionalHandle handle,
+                               int use_handle, cudaStream_t s) {
+  k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
+  h->launches++;
+  int rc = launch_eval(h, b, s);
+  if (rc) return rc;
+  launch_stamp(h, h->csr.p, 1, s);
+  launch_residual(h, b, 1, s);
+  launch_lu(h, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
+  UpdateArgs ua = make_update_args(h, X, b.limit_in, b.limit_out);
+  k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua);
+  k_nr_update<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua, h->ctl.p, h->limit_w.p, handle, use_handle);
+  h->launches += 2;
+  return VJX_OK;
+}
+
+static int upload_symbolic(vjx_handle* h) {
+  VjxSymbolic& S = h->sym;
+  CK(h->lu_ptr.upload(S.lu_ptr));
+  CK(h->lu_col.upload(S.lu_col));
+  CK(h->lu_diag.upload(S.lu_diag));
+  CK(h->lu_src.upload(S.lu_src));
+  CK(h->lu_order_l.upload(S.order_l));
+  CK(h->lu_order_u.upload(S.order_u));
+  CK(h->lu_perm_r.upload(S.perm_r));
+  CK(h->lu_perm_c.upload(S.perm_c));
+  std::vector<long long> pp(S.pair_ptr.begin(), S.pair_ptr.end());
+  CK(h->lu_pair_ptr.upload(pp));
+  std::vector<int> pl(S.pair_l), pu(S.pair_u);
+  if (pl.empty()) { pl.push_back(0); pu.push_back(0); }
+  CK(h->lu_pair_l.upload(pl));
+  CK(h->lu_pair_u.upload(pu));
+  CK(h->lu_ent_order.upload(S.ent_order));
+  CK(h->lu_row_wave_ptr.upload(S.row_wave_ptr));
+  CK(h->lu_wave_end.upload(S.wave_end));
+  CK(h->lu_val.alloc((size_t)S.nnz_lu));
+  CK(h->lu_inv.alloc(S.n));
+  CK(h->lu_y.alloc(S.n));
+  CK(h->lu_xp.alloc(S.n));
+  CK(h->lu_flags.alloc((size_t)3 * S.n));
+  LUDev& L = h->lud;
+  L.n = S.n;
+  L.ptr = h->lu_ptr.p; L.col = h->lu_col.p; L.diag = h->lu_diag.p; L.src = h->lu_src.p;
+  L.order_l = h->lu_order_l.p; L.order_u = h->lu_order_u.p; L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
+  L.pair_ptr = h->lu_pair_ptr.p; L.pair_l = h->lu_pair_l.p; L.pair_u = h->lu_pair_u.p;
+  L.ent_order = h->lu_ent_order.p; L.row_wave_ptr = h->lu_row_wave_ptr.p; L.wave_end = h->lu_wave_end.p;
+  L.val = h->lu_val.p; L.inv_diag = h->lu_inv.p; L.y = h->lu_y.p; L.xp = h->lu_xp.p;
+  L.flag_f = h->lu_flags.p; L.flag_l = h->lu_flags.p + S.n; L.flag_u = h->lu_flags.p + 2 * (size_t)S.n;
+  // persistent grids: every CTA must be resident (dependency waits), so size from occupancy
+  int occ_f = 1, occ_s = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_lu_factor, 256, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_lu_lsolve, 256, 0));
+  int occ_u = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_lu_usolve, 256, 0));
+  occ_s = std::min(occ_s, occ_u);
+  long long warps_needed = S.n;
+  h->lu_grid_f = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * std::min(occ_f, 4), (warps_needed + 7) / 8));
+  h->lu_grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * std::min(occ_s, 4), (warps_needed + 7) / 8));
+  h->lu_ready = true;
+  return VJX_OK;
+}
+
+static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s) {
+  if (h->lu_ready) return VJX_OK;
+  std::vector<double> vals(h->nse);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpy(vals.data(), csr_dev, sizeof(double) * h->nse, cudaMemcpyDeviceToHost));
+  std::string err;
+  double tol = h->o.pivot_tol > 0 ? h->o.pivot_tol : 1e-3;
+  int rc = vjx_symbolic_analyze(h->n_aug, h->h_indptr.data(), h->h_indices.data(), vals.data(), tol, true, h->sym, err);
+  if (rc != 0) return fail(VJX_ERR_SINGULAR, "LU analysis failed: " + err);
+  return upload_symbolic(h);
+}
+
+extern "C" int vjx_lu_analyze(vjx_handle* h, const double* csr_data_dev, vjx_stream stream) {
+  if (!h) return fail(VJX_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(h->device));
+  h->lu_ready = false;
+  if (h->g_iter) { cudaGraphExecDestroy(h->g_iter); h->g_iter = nullptr; }
+  if (h->g_tran) { cudaGraphExecDestroy(h->g_tran); h->g_tran = nullptr; }
+  return ensure_lu(h, csr_data_dev, (cudaStream_t)stream);
+}
+
+extern "C" int vjx_lu_stats(vjx_handle* h, double* out6) {
+  if (!h || !h->lu_ready) return fail(VJX_ERR_INVALID, "LU not analysed yet");
+  out6[0] = (double)h->sym.nnz_lu;
+  out6[1] = h->sym.flops;
+  out6[2] = h->sym.n_levels_l;
+  out6[3] = h->sym.n_levels_u;
+  out6[4] = h->sym.max_row_len;
+  out6[5] = h->sym.n;
+  return VJX_OK;
+}
+
+static int check_device_error(vjx_handle* h, cudaStream_t s) {
+  NRStat* hs = (NRStat*)h->pinned;
+  CK(cudaMemcpyAsync(hs, h->st.p, sizeof(NRStat), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (hs->error & (1 | 4 | 8)) return fail(VJX_ERR_HANG, "dependency wait watchdog fired in the LU kernels");
+  return VJX_OK;
+}
+
+extern "C" int vjx_lu_solve(vjx_handle* h, const double* csr_data_dev, const double* b_dev, double* x_dev, vjx_stream stream) {
+  if (!h || !csr_data_dev || !b_dev || !x_dev) return fail(VJX_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = ensure_lu(h, csr_data_dev, s);
+  if (rc) return rc;
+  k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
+  h->launches++;
+  launch_lu(h, csr_data_dev, b_dev, 1.0, nullptr, x_dev, s);
+  CK(cudaGetLastError());
+  return VJX_OK;
+}
+
+extern "C" int vjx_build_system(vjx_handle* h, const double* X, const double* vsrc, const double* isrc,
+                                const double* Q_prev, double c0, double gmin, double gshunt, double c1, double d1,
+                                const double* dQdt_prev, double c2, const double* Q_prev2, const double* limit_in,
+                                int nr_iteration, double* csr_out, double* f_out, double* Q_out, double* Ivs_out,
+                                double* limit_out, double* maxres_out, vjx_stream stream) {
+  if (!h || !X) return fail(VJX_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  k_set_ctl<<<1, 1, 0, s>>>(h->ctl.p, c0, c1, d1, c2, gmin, gshunt, (double)nr_iteration, h->o.gmin);
+  h->launches++;
+  BuildPtrs b{};
+  b.X = X; b.vsrc = vsrc ? vsrc : h->zeros.p; b.isrc = isrc ? isrc : h->zeros.p;
+  b.Q_prev = Q_prev; b.dQdt_prev = dQdt_prev; b.Q_prev2 = Q_prev2;
+  b.limit_in = limit_in ? limit_in : h->zeros.p;
+  b.limit_out = limit_out ? limit_out : h->limit_out.p;
+  b.res_tol_floor = nullptr;
+  b.csr = csr_out; b.f = f_out ? f_out : h->f.p; b.Q = Q_out; b.Ivs = Ivs_out; b.maxres = maxres_out;
+  int rc = launch_eval(h, b, s);
+  if (rc) return rc;
+  if (csr_out) launch_stamp(h, csr_out, 0, s);
+  launch_residual(h, b, 0, s);
+  CK(cudaGetLastError());
+  return VJX_OK;
+}
+
+static void fill_build_ptrs_nr(vjx_handle* h, BuildPtrs& b, const double* X, const double* vsrc, const double* isrc,
+                               const double* Q_prev, const double* dQdt_prev, const double* Q_prev2,
+                               const double* rtf) {
+  b.X = X; b.vsrc = vsrc ? vsrc : h->zeros.p; b.isrc = isrc ? isrc : h->zeros.p;
+  b.Q_prev = Q_prev; b.dQdt_prev = dQdt_prev; b.Q_prev2 = Q_prev2;
+  b.limit_in = h->limit_w.p; b.limit_out = h->limit_out.p; b.res_tol_floor = rtf;
+  b.csr = h->csr.p; b.f = h->f.p; b.Q = nullptr; b.Ivs = nullptr; b.maxres = h->maxres_w.p;
+}
+
+// Host-polled NR loop: one graph-free chain per iteration + a 64-byte status read.
+static int run_nr_host(vjx_handle* h, BuildPtrs& b, double* X, int max_iter, bool reset, cudaStream_t s) {
+  k_nr_begin<<<1, 1, 0, s>>>(h->st.p, h->ctl.p, max_iter, reset ? 1 : 0);
+  h->launches++;
+  NRStat* hs = (NRStat*)h->pinned;
+  if (!h->lu_ready) {
+    // first factorisation of this handle: build the system once to analyse its values
+    k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
+    int rc = launch_eval(h, b, s);
+    if (rc) return rc;
+    launch_stamp(h, h->csr.p, 1, s);
+    rc = ensure_lu(h, h->csr.p, s);
+    if (rc) return rc;
+  }
+  if (max_iter <= 0) return VJX_OK;
+  while (true) {
+    int rc = launch_nr_iteration(h, b, X, 0, 0, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(hs, h->st.p, sizeof(NRStat), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (hs->error & (1 | 4 | 8)) return fail(VJX_ERR_HANG, "dependency wait watchdog fired in the LU kernels");
+    if (!hs->cont) break;
+  }
+  return VJX_OK;
+}
+
+extern "C" int vjx_nr_solve(vjx_handle* h, const double* X_init, const double* vsrc, const double* isrc,
+                            const double* Q_prev, double c0, double gmin, double gshunt, double c1, double d1,
+                            const double* dQdt_prev, double c2, const double* Q_prev2, const double* limit_in,
+                            const double* res_tol_floor, int max_iterations, double* X_out, int* iterations,
+                            int* converged, double* max_f, double* Q_out, double* dQdt_out, double* Ivs_out,
+                            double* limit_out, double* maxres_out, vjx_stream stream) {
+  if (!h || !X_init || !X_out) return fail(VJX_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nx = h->n_total + h->n_vs;
+  if (max_iterations < 0) max_iterations = h->o.tran_itl;
+  k_set_ctl<<<1, 1, 0, s>>>(h->ctl.p, c0, c1, d1, c2, gmin, gshunt, 0.0, h->o.gmin);
+  if (X_out != X_init) k_copy<<<grid_for(h, nx), 256, 0, s>>>(nx, X_init, X_out);
+  if (h->total_lim > 0) k_copy<<<grid_for(h, h->total_lim), 256, 0, s>>>(h->total_lim, limit_in, h->limit_w.p);
+  h->launches += 3;
+  BuildPtrs b{};
+  fill_build_ptrs_nr(h, b, X_out, vsrc, isrc, Q_prev, dQdt_prev, Q_prev2, res_tol_floor);
+  int rc = run_nr_host(h, b, X_out, max_iterations, true, s);
+  if (rc) return rc;
+  // final build at X_final for Q, I_vsource, max_res_contrib (solver_factories.py:689-713)
+  BuildPtrs bf = b;
+  bf.csr = nullptr; bf.f = h->f.p; bf.Q = Q_out ? Q_out : h->Qw.p; bf.Ivs = Ivs_out ? Ivs_out : h->Ivs.p;
+  bf.maxres = maxres_out ? maxres_out : h->maxres_w.p;
+  bf.limit_out = h->limit_out.p;
+  rc = launch_eval(h, bf, s);
+  if (rc) return rc;
+  launch_residual(h, bf, 0, s);
+  if (dQdt_out) {
+    k_dqdt<<<grid_for(h, h->n_unknowns), 256, 0, s>>>(h->n_unknowns, h->ctl.p, bf.Q, Q_prev, dQdt_prev, Q_prev2, dQdt_out);
+    h->launches++;
+  }
+  if (limit_out && h->total_lim > 0) {
+    k_copy<<<grid_for(h, h->total_lim), 256, 0, s>>>(h->total_lim, h->limit_w.p, limit_out);
+    h->launches++;
+  }
+  NRStat* hs = (NRStat*)h->pinned;
+  CK(cudaMemcpyAsync(hs, h->st.p, sizeof(NRStat), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (iterations) *iterations = hs->iter;
+  if (converged) *converged = hs->converged;
+  if (max_f) { double mfv = INFINITY; if (max_iterations > 0) memcpy(&mfv, &hs->max_f_bits, sizeof(double)); *max_f = mfv; }
+  CK(cudaGetLastError());
+  return VJX_OK;
+}
+
+// ---- transient --------------------------------------------------------------------------
+static StepArgs make_step_args(vjx_handle* h) {
+  StepArgs a;
+  a.ts = h->ts.p; a.st = h->st.p; a.ctl = h->ctl.p; a.o = h->o;
+  a.n_total = h->n_total; a.n_unknowns = h->n_unknowns; a.n_vs = h->n_vs; a.n_is = h->n_is; a.n_ext = h->n_ext;
+  a.n_lim = h->total_lim; a.H = h->H;
+  a.vsrc_desc = h->vsrc_desc.p; a.isrc_desc = h->isrc_desc.p; a.pwl_t = h->pwl_t.p; a.pwl_v = h->pwl_v.p;
+  a.vsrc = h->vsrc_val.p; a.isrc = h->isrc_val.p;
+  a.X = h->X.p; a.Xw = h->Xw.p; a.Vpred = h->Vpred.p; a.Vhist = h->Vhist.p; a.Vmax = h->Vmax.p;
+  a.Q_prev = h->Q_prev.p; a.dQdt_prev = h->dQdt_prev.p; a.Q_prev2 = h->Q_prev2.p; a.Qw = h->Qw.p; a.dQdtw = h->dQdtw.p;
+  a.Ivs = h->Ivs.p; a.maxres_w = h->maxres_w.p; a.hist_mrc = h->hist_mrc.p; a.res_tol_floor = h->res_tol_floor.p;
+  a.limit_state = h->limit_state.p; a.limit_w = h->limit_w.p;
+  a.times_out = h->times_out.p; a.V_out = h->V_out.p; a.I_out = h->I_out.p; a.records = h->records.p;
+  a.max_records = h->max_records;
+  return a;
+}
+
+__global__ void k_abs_copy(int n, const double* src, double* dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = fabs(src[i]);
+}
+__global__ void k_dec_attempts(TranScalars* s) { s->attempts -= 1; }
+__global__ void k_set_attempts_limit(TranScalars* s, int limit) { s->attempts_limit = limit; }
+
+__global__ void k_tran_init(TranScalars* s, NRStat* st, double t_stop, double dt, double max_dt, int max_steps, int H) {
+  memset(s, 0, sizeof(TranScalars));
+  s->t = 0.0; s->dt = dt; s->t_stop = t_stop; s->max_dt = max_dt; s->min_dt_used = dt; s->max_dt_used = dt;
+  for (int k = 0; k < 4; ++k) s->dt_hist[k] = dt;
+  s->hist_count = 1; s->step_idx = 1; s->warmup = 0; s->max_steps = max_steps; s->hist_head = 0; s->cont = 1;
+  st->error = 0;
+  (void)H;
+}
+
+extern "C" int vjx_tran_begin(vjx_handle* h, const double* X0, const double* Q_init, const double* I0,
+                              const double* hist_maxres, double t_stop, double dt, double max_dt, int max_steps,
+                              vjx_stream stream) {
+  if (!h || !X0) return fail(VJX_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nt = h->n_total, nu = std::max(h->n_unknowns, 1), nx = h->n_total + h->n_vs, nvs1 = std::max(h->n_vs, 1);
+  h->H = h->o.max_order + 2;
+  if (h->H > 4 || h->H < 3) return fail(VJX_ERR_INVALID, "max_order must be 1 or 2");
+  if (max_steps != h->max_steps || !h->X.p) {
+    h->max_steps = max_steps;
+    h->max_records = 4 * max_steps + 64;
+    CK(h->X.alloc(nx)); CK(h->Vpred.alloc(nt)); CK(h->Vhist.alloc((size_t)h->H * nt)); CK(h->Vmax.alloc(nt));
+    CK(h->Q_prev.alloc(nu)); CK(h->dQdt_prev.alloc(nu)); CK(h->Q_prev2.alloc(nu)); CK(h->hist_mrc.alloc(nu));
+    CK(h->res_tol_floor.alloc(nu)); CK(h->limit_state.alloc(std::max(h->total_lim, 1)));
+    CK(h->times_out.alloc(max_steps)); CK(h->V_out.alloc((size_t)max_steps * h->n_ext));
+    CK(h->I_out.alloc((size_t)max_steps * nvs1)); CK(h->records.alloc((size_t)h->max_records * 8));
+    if (h->g_tran) { cudaGraphExecDestroy(h->g_tran); h->g_tran = nullptr; }
+  }
+  CK(cudaMemsetAsync(h->Vhist.p, 0, sizeof(double) * h->H * nt, s));
+  CK(cudaMemsetAsync(h->dQdt_prev.p, 0, sizeof(double) * nu, s));
+  CK(cudaMemsetAsync(h->Q_prev2.p, 0, sizeof(double) * nu, s));
+  CK(cudaMemsetAsync(h->limit_state.p, 0, sizeof(double) * std::max(h->total_lim, 1), s));
+  CK(cudaMemsetAsync(h->times_out.p, 0, sizeof(double) * max_steps, s));
+  CK(cudaMemsetAsync(h->V_out.p, 0, sizeof(double) * (size_t)max_steps * h->n_ext, s));
+  CK(cudaMemsetAsync(h->I_out.p, 0, sizeof(double) * (size_t)max_steps * nvs1, s));
+  CK(cudaMemcpyAsync(h->X.p, X0, sizeof(double) * nx, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(h->Vhist.p, X0, sizeof(double) * nt, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(h->V_out.p, X0, sizeof(double) * h->n_ext, cudaMemcpyDeviceToDevice, s));
+  k_copy<<<grid_for(h, nu), 256, 0, s>>>(h->n_unknowns, Q_init, h->Q_prev.p);
+  k_copy<<<grid_for(h, nu), 256, 0, s>>>(h->n_unknowns, hist_maxres, h->hist_mrc.p);
+  if (h->n_vs > 0 && I0) CK(cudaMemcpyAsync(h->I_out.p, I0, sizeof(double) * h->n_vs, cudaMemcpyDeviceToDevice, s));
+  k_tran_init<<<1, 1, 0, s>>>(h->ts.p, h->st.p, t_stop, dt, max_dt, max_steps, h->H);
+  h->launches += 3;
+  k_abs_copy<<<grid_for(h, nt), 256, 0, s>>>(nt, X0, h->Vmax.p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return VJX_OK;
+}
+
+
+static void tran_build_ptrs(vjx_handle* h, BuildPtrs& b) {
+  fill_build_ptrs_nr(h, b, h->Xw.p, h->vsrc_val.p, h->isrc_val.p, h->Q_prev.p, h->dQdt_prev.p, h->Q_prev2.p,
+                     h->res_tol_floor.p);
+}
+
+static int launch_step_pre(vjx_handle* h, cudaGraphConditionalHandle nr_handle, int use_handle, cudaStream_t s) {
+  StepArgs a = make_step_args(h);
+  k_pre_step<<<1, 256, 0, s>>>(a, nr_handle, use_handle);
+  k_predict<<<grid_for(h, h->n_total + h->n_vs + h->total_lim), 256, 0, s>>>(a);
+  h->launches += 2;
+  return VJX_OK;
+}
+
+static int launch_step_post(vjx_handle* h, cudaGraphConditionalHandle handle, int use_handle, int attempts_limit,
+                            cudaStream_t s) {
+  BuildPtrs b{};
+  tran_build_ptrs(h, b);
+  BuildPtrs bf = b;
+  bf.csr = nullptr; bf.f = h->f.p; bf.Q = h->Qw.p; bf.Ivs = h->Ivs.p; bf.maxres = h->maxres_w.p;
+  int rc = launch_eval(h, bf, s);
+  if (rc) return rc;
+  launch_residual(h, bf, 0, s);
+  k_dqdt<<<grid_for(h, h->n_unknowns), 256, 0, s>>>(h->n_unknowns, h->ctl.p, h->Qw.p, h->Q_prev.p, h->dQdt_prev.p,
+                                                   h->Q_prev2.p, h->dQdtw.p);
+  StepArgs a = make_step_args(h);
+  k_lte<<<grid_for(h, h->n_total), 256, 0, s>>>(a);
+  k_step_decide<<<1, 1, 0, s>>>(a, handle, 0, attempts_limit);
+  k_step_commit<<<grid_for(h, h->n_total + h->n_vs + h->total_lim), 256, 0, s>>>(a, handle, 0, attempts_limit);
+  k_step_finish<<<1, 1, 0, s>>>(a, handle, use_handle, attempts_limit);
+  h->launches += 5;
+  return VJX_OK;
+}
+
+// Build the device-resident loop: WHILE(step){ pre; WHILE(nr){ iteration }; post } as one graph.
+static int build_tran_graph(vjx_handle* h, int attempts_limit, cudaStream_t s) {
+  if (h->g_tran) { cudaGraphExecDestroy(h->g_tran); h->g_tran = nullptr; }
+  cudaGraph_t g;
+  CK(cudaGraphCreate(&g, 0));
+  cudaGraphConditionalHandle h_step, h_nr;
+  CK(cudaGraphConditionalHandleCreate(&h_step, g, 1, cudaGraphCondAssignDefault));
+  CK(cudaGraphConditionalHandleCreate(&h_nr, g, 1, cudaGraphCondAssignDefault));
+  cudaGraphNodeParams cp = {};
+  cp.type = cudaGraphNodeTypeConditional;
+  cp.conditional.handle = h_step;
+  cp.conditional.type = cudaGraphCondTypeWhile;
+  cp.conditional.size = 1;
+  cudaGraphNode_t step_node;
+  CK(cudaGraphAddNode(&step_node, g, nullptr, 0, &cp));
+  cudaGraph_t step_body = cp.conditional.phGraph_out[0];
+  // capture pre-step into step_body
+  cudaStream_t cs = h->own_stream;
+  long long launches_before = h->launches;
+  CK(cudaStreamBeginCaptureToGraph(cs, step_body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  launch_step_pre(h, h_nr, 1, cs);
+  cudaGraph_t tmp;
+  CK(cudaStreamEndCapture(cs, &tmp));
+  // find leaf nodes of step_body to chain the NR while node after them
+  size_t nn = 0;
+  CK(cudaGraphGetNodes(step_body, nullptr, &nn));
+  std::vector<cudaGraphNode_t> nodes(nn);
+  CK(cudaGraphGetNodes(step_body, nodes.data(), &nn));
+  // the capture is linear: the last node added is the leaf
+  std::vector<cudaGraphNode_t> leaves;
+  for (auto nd : nodes) {
+    size_t nd_dep = 0;
+    CK(cudaGraphNodeGetDependentNodes(nd, nullptr, &nd_dep));
+    if (nd_dep == 0) leaves.push_back(nd);
+  }
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = h_nr;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t nr_node;
+  CK(cudaGraphAddNode(&nr_node, step_body, leaves.data(), leaves.size(), &np));
+  cudaGraph_t nr_body = np.conditional.phGraph_out[0];
+  BuildPtrs b{};
+  tran_build_ptrs(h, b);
+  CK(cudaStreamBeginCaptureToGraph(cs, nr_body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  int rc = launch_nr_iteration(h, b, h->Xw.p, h_nr, 1, cs);
+  CK(cudaStreamEndCapture(cs, &tmp));
+  if (rc) return rc;
+  // post-step after the NR while node
+  CK(cudaStreamBeginCaptureToGraph(cs, step_body, &nr_node, nullptr, 1, cudaStreamCaptureModeRelaxed));
+  rc = launch_step_post(h, h_step, 1, attempts_limit, cs);
+  CK(cudaStreamEndCapture(cs, &tmp));
+  if (rc) return rc;
+  h->launches = launches_before;
+  CK(cudaGraphInstantiate(&h->g_tran, g, 0));
+  CK(cudaGraphDestroy(g));
+  h->g_tran_limit = attempts_limit;
+  (void)s;
+  return VJX_OK;
+}
+
+extern "C" int vjx_tran_run(vjx_handle* h, int max_attempts, int* attempts, vjx_stream stream) {
+  if (!h || !h->X.p) return fail(VJX_ERR_INVALID, "vjx_tran_begin not called");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TranScalars* hts = (TranScalars*)((char*)h->pinned + 512);
+  CK(cudaMemcpyAsync(hts, h->ts.p, sizeof(TranScalars), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int start_attempts = hts->attempts;
+  const int limit = start_attempts + (max_attempts > 0 ? max_attempts : 0x3fffffff - start_attempts);
+  if (!(hts->t < hts->t_stop) || hts->step_idx >= hts->max_steps) {
+    if (attempts) *attempts = 0;
+    return VJX_OK;
+  }
+  BuildPtrs b{};
+  tran_build_ptrs(h, b);
+  if (!h->lu_ready) {
+    // analyse on the first system of the run (coefficients of the first step)
+    launch_step_pre(h, 0, 0, s);
+    k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
+    int rc = launch_eval(h, b, s);
+    if (rc) return rc;
+    launch_stamp(h, h->csr.p, 1, s);
+    rc = ensure_lu(h, h->csr.p, s);
+    if (rc) return rc;
+    // undo the attempt counter bump of the probe
+    k_dec_attempts<<<1, 1, 0, s>>>(h->ts.p);
+  }
+  k_set_attempts_limit<<<1, 1, 0, s>>>(h->ts.p, limit);
+  if (h->o.use_device_graph) {
+    if (!h->g_tran) {
+      int rc = build_tran_graph(h, limit, s);
+      if (rc) return rc;
+    }
+    CK(cudaGraphLaunch(h->g_tran, s));
+    CK(cudaStreamSynchronize(s));
+  } else {
+    NRStat* hs = (NRStat*)h->pinned;
+    while (true) {
+      launch_step_pre(h, 0, 0, s);
+      while (true) {
+        int rc = launch_nr_iteration(h, b, h->Xw.p, 0, 0, s);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(hs, h->st.p, sizeof(NRStat), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (hs->error & (1 | 4 | 8)) return fail(VJX_ERR_HANG, "dependency wait watchdog fired in the LU kernels");
+        if (!hs->cont) break;
+      }
+      int rc = launch_step_post(h, 0, 0, limit, s);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(hts, h->ts.p, sizeof(TranScalars), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (!hts->cont) break;
+    }
+  }
+  CK(cudaMemcpyAsync(hts, h->ts.p, sizeof(TranScalars), cudaMemcpyDeviceToHost, s));
+  int rc = check_device_error(h, s);
+  if (rc) return rc;
+  if (attempts) *attempts = hts->attempts - start_attempts;
+  CK(cudaGetLastError());
+  return VJX_OK;
+}
+
+
+extern "C" int vjx_tran_scalars(vjx_handle* h, double* out, vjx_stream stream) {
+  if (!h || !h->ts.p) return fail(VJX_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TranScalars* hts = (TranScalars*)((char*)h->pinned + 512);
+  NRStat* hs = (NRStat*)h->pinned;
+  CK(cudaMemcpyAsync(hts, h->ts.p, sizeof(TranScalars), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hs, h->st.p, sizeof(NRStat), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  out[0] = hts->t; out[1] = hts->dt; out[2] = hts->step_idx; out[3] = hts->total_nr; out[4] = hts->rejected;
+  out[5] = hts->min_dt_used; out[6] = hts->max_dt_used; out[7] = hts->hist_count; out[8] = hts->warmup;
+  out[9] = hts->consec; out[10] = hts->attempts; out[11] = hs->error;
+  return VJX_OK;
+}
+
+extern "C" int vjx_tran_read(vjx_handle* h, int row0, int rows, double* times, double* V_out, double* I_out, vjx_stream stream) {
+  if (!h || !h->X.p) return fail(VJX_ERR_INVALID, "no transient state");
+  if (row0 < 0 || rows < 0 || row0 + rows > h->max_steps) return fail(VJX_ERR_INVALID, "row range");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nvs1 = std::max(h->n_vs, 1);
+  if (times) CK(cudaMemcpyAsync(times, h->times_out.p + row0, sizeof(double) * rows, cudaMemcpyDeviceToHost, s));
+  if (V_out) CK(cudaMemcpyAsync(V_out, h->V_out.p + (size_t)row0 * h->n_ext, sizeof(double) * (size_t)rows * h->n_ext, cudaMemcpyDeviceToHost, s));
+  if (I_out) CK(cudaMemcpyAsync(I_out, h->I_out.p + (size_t)row0 * nvs1, sizeof(double) * (size_t)rows * nvs1, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VJX_OK;
+}
+
+extern "C" int vjx_tran_records(vjx_handle* h, int first, int count, double* out, vjx_stream stream) {
+  if (!h || !h->records.p) return fail(VJX_ERR_INVALID, "no transient state");
+  if (first < 0 || count < 0 || first + count > h->max_records) return fail(VJX_ERR_INVALID, "record range");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(out, h->records.p + (size_t)first * 8, sizeof(double) * 8 * count, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return VJX_OK;
+}
+
+extern "C" int vjx_tran_state(vjx_handle* h, double* X, double* Q_prev, double* dQdt_prev, vjx_stream stream) {
+  if (!h || !h->X.p) return fail(VJX_ERR_INVALID, "no transient state");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (X) CK(cudaMemcpyAsync(X, h->X.p, sizeof(double) * (h->n_total + h->n_vs), cudaMemcpyDeviceToHost, s));
+  if (Q_prev) CK(cudaMemcpyAsync(Q_prev, h->Q_prev.p, sizeof(double) * h->n_unknowns, cudaMemcpyDeviceToHost, s));
+  if (dQdt_prev) CK(cudaMemcpyAsync(dQdt_prev, h->dQdt_prev.p, sizeof(double) * h->n_unknowns, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VJX_OK;
+}
+
+extern "C" long long vjx_launch_count(vjx_handle* h) { return h ? h->launches : 0; }
+
+// Phase timing probe on the transient working state (Xw etc.), CUDA events on the launch stream.
+extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg, int* launches, vjx_stream stream) {
+  if (!h || !h->X.p || !h->lu_ready) return fail(VJX_ERR_INVALID, "run a transient first");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  BuildPtrs b{};
+  tran_build_ptrs(h, b);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int nl = 0;
+  UpdateArgs ua = make_update_args(h, h->Xw.p, b.limit_in, b.limit_out);
+  float total = 0.f;
+  for (int r = 0; r < reps + 1; ++r) {
+    long long l0 = h->launches;
+    if (phase == 3 || phase == 4 || phase == 5) {
+      // each LU phase needs a fresh epoch and the preceding phases' results
+      k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
+      if (phase >= 4) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p);
+      if (phase >= 5) k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+    }
+    CK(cudaEventRecord(e0, s));
+    l0 = h->launches;
+    switch (phase) {
+      case 0: { int rc = launch_eval(h, b, s); if (rc) return rc; break; }
+      case 1: launch_stamp(h, h->csr.p, 1, s); break;
+      case 2: launch_residual(h, b, 0, s); break;
+      case 3: k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p); h->launches++; break;
+      case 4: k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p); h->launches++; break;
+      case 5: k_lu_usolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->delta.p, h->st.p); h->launches++; break;
+      case 6: k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua); h->launches++; break;
+      default: return fail(VJX_ERR_INVALID, "unknown phase");
+    }
+    nl = (int)(h->launches - l0);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0) total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_avg) *ms_avg = total / std::max(reps, 1);
+  if (launches) *launches = nl;
+  return check_device_error(h, s);
+}

@@ -1,0 +1,55 @@
+// Host-side symbolic analysis for the GPU sparse LU.
+//
+// The reference delegates this to cuDSS (via spineax, vajax/analysis/solver_factories.py:882-930)
+// or UMFPACK (vajax/sparse/umfpack_ffi.cpp:253-300: symbolic cached by (n, nnz), numeric + solve per
+// call, pivot tolerance 0.1).  Here the analysis runs once per circuit on the first Jacobian
+// ("pivot order fixed at the DC operating point", BASELINE.json north_star item 3):
+//   1. approximate-minimum-degree ordering of the pattern of A + A^T (dense rows deferred),
+//   2. left-looking Gilbert-Peierls LU with threshold partial pivoting that prefers the diagonal
+//      (the KLU strategy) to fix the row permutation and the structural pattern of L and U,
+//   3. row-wise (CSR) storage of L+U in the permuted space, the map from CSR slots of A into it,
+//   4. dependency levels for the factorisation / forward solve (L pattern) and back solve (U),
+//   5. the per-entry gather program (contributor pairs + in-row waves) of the numeric kernel.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+struct VjxSymbolic {
+  int n = 0;
+  std::vector<int> perm_r;     // permuted row i  <- original row perm_r[i]
+  std::vector<int> perm_c;     // permuted col j  <- original col perm_c[j]
+  std::vector<int> lu_ptr;     // [n+1] row pointers of L+U (permuted space)
+  std::vector<int> lu_col;     // column indices, ascending per row
+  std::vector<int> lu_diag;    // [n] position of the diagonal entry of row i
+  std::vector<int> lu_src;     // per L+U entry: slot of A's CSR values, or -1 for fill
+  std::vector<int> order_l;    // rows sorted by L-dependency level (factor + forward solve order)
+  std::vector<int> order_u;    // rows sorted by U-dependency level (back solve order)
+  std::vector<int> level_l, level_u;
+  int n_levels_l = 0, n_levels_u = 0, max_row_len = 0;
+  // Gather program of the numeric refactorisation.  Entry (i,j) of L+U is
+  //   w = A(i,j) - sum_{k in L(i,:), k < min(i,j), U(k,j) != 0} L(i,k) * U(k,j)   (ascending k)
+  // and L(i,j) = w / U(j,j) for j < i.  pair_l / pair_u are absolute indices into the L+U value
+  // array of L(i,k) and U(k,j).  Entries of a row are grouped in waves: every contributor L(i,k)
+  // of an entry lies in an earlier wave, so a wave's entries are independent.
+  std::vector<int64_t> pair_ptr;  // [nnz_lu+1]
+  std::vector<int> pair_l, pair_u;
+  std::vector<int> ent_order;     // [nnz_lu] absolute entry positions, per row sorted by wave
+  std::vector<int> row_wave_ptr;  // [n+1] -> wave_end
+  std::vector<int> wave_end;      // absolute end index into ent_order of each wave
+  int max_waves = 0;
+  double flops = 0.0;             // 2 * sum_k nnz(L(:,k)) * nnz(U(k,:)) + nnz(L)
+  int64_t nnz_lu = 0;
+};
+
+// Returns 0 on success; <0 and fills err otherwise.
+int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const double* values,
+                         double pivot_tol, bool build_update_stream, VjxSymbolic& out, std::string& err);
+
+// Approximate minimum degree ordering on the pattern of A + A^T. perm[k] = k-th pivot.
+void vjx_amd_order(int n, const int* indptr, const int* indices, std::vector<int>& perm);
+
+// Host emulation of the GPU numeric algorithm (diagnostics for CPU-only tests of the symbolic
+// structures; never used by the product path): refactor + solve, returns max-norm residual.
+double vjx_symbolic_selfcheck(const VjxSymbolic& s, int n, const int* indptr, const int* indices,
+                              const double* values, const double* b, double* x_out);
