@@ -106,14 +106,25 @@ def test_nr_solve_parity(name, limiting, bundles):
     ro = o.nr_solve(X0, vs, isv, np.zeros(nu), 0.0, 1e-12)
     rg = g.nr_solve(X0, vs, isv, np.zeros(nu), 0.0, 1e-12)
     assert rg[1] == ro[1] and rg[2] == ro[2], (rg[1], ro[1], rg[2], ro[2])
-    assert relerr(rg[0], ro[0], 1e-6) < 1e-9
-    assert relerr(rg[4], ro[4], max(1e-24, 1e-9 * np.max(np.abs(ro[4])))) < 1e-8
-    # a transient-style solve from the DC point
     c0 = 2.0 / 1e-11
-    r2o = o.nr_solve(ro[0], vs, isv, ro[4], c0, 1e-12, 0.0, -c0, -1.0, np.zeros(nu), 0.0, None, ro[7], None)
-    r2g = g.nr_solve(ro[0], vs, isv, ro[4], c0, 1e-12, 0.0, -c0, -1.0, np.zeros(nu), 0.0, None, ro[7], None)
+    if ro[2]:
+        assert relerr(rg[0], ro[0], 1e-6) < 1e-9
+        assert relerr(rg[4], ro[4], max(1e-24, 1e-9 * np.max(np.abs(ro[4])))) < 1e-8
+        Xs, Qs, lim = ro[0], ro[4], ro[7]
+    else:
+        # the mid-rail DC solve diverges in the reference semantics too (the multipliers run with
+        # icmode=uic): iterates of a diverging NR are chaotic, so only flags are compared, and the
+        # transient-style solve starts from the UIC state (full_mna.py:882-921)
+        Xs = np.zeros_like(X0)
+        Qs = o.build_system(Xs, vs, isv, np.zeros(nu), 0.0)[2]
+        lim = None
+    # a transient-style solve (trapezoidal coefficients, dt = 10 ps)
+    r2o = o.nr_solve(Xs, vs, isv, Qs, c0, 1e-12, 0.0, -c0, -1.0, np.zeros(nu), 0.0, None, lim, None)
+    r2g = g.nr_solve(Xs, vs, isv, Qs, c0, 1e-12, 0.0, -c0, -1.0, np.zeros(nu), 0.0, None, lim, None)
     assert r2g[1] == r2o[1] and r2g[2] == r2o[2]
+    assert r2o[2], "transient-style solve must converge in the oracle"
     assert relerr(r2g[0], r2o[0], 1e-6) < 1e-9
+    assert relerr(r2g[4], r2o[4], max(1e-24, 1e-9 * np.max(np.abs(r2o[4])))) < 1e-8
     g.close()
 
 
@@ -135,8 +146,10 @@ def test_transient_parity(name, graph, bundles):
     assert len(gr) == len(rec)
     for a, b in zip(gr, rec):
         assert int(a[0]) == b["step"] and int(a[3]) == b["nr_iters"] and bool(a[4]) == b["accept"]
-        assert abs(a[1] - b["t_next"]) <= 1e-12 * abs(b["t_next"]) and abs(a[2] - b["dt"]) <= 1e-12 * b["dt"]
-    assert np.max(np.abs(tg[:n] - to[:n])) <= 1e-12 * to[n - 1]
+        # dt is a function of the LTE norm, i.e. of (V_new - V_pred): it can only agree to the accuracy
+        # of the solves (1e-9 relative, north_star), not to 1 ulp
+        assert abs(a[1] - b["t_next"]) <= 1e-9 * abs(b["t_next"]) and abs(a[2] - b["dt"]) <= 1e-9 * b["dt"]
+    assert np.max(np.abs(tg[:n] - to[:n])) <= 1e-9 * to[n - 1]
     span = max(np.max(Vo[:n]) - np.min(Vo[:n]), 1e-12)
     rms = np.sqrt(np.mean((Vg[:n] - Vo[:n]) ** 2)) / span
     assert rms < 1e-6, rms
