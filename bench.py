@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py - ms per accepted transient step of the Newton-Raphson hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c6288|mul|ring]
+
+One "step" = one accepted timestep of the adaptive transient (all of its NR iterations, rejected
+attempts included in the time - the reference's own definition, full_mna.py:1142-1148,1176).
+
+* ``value``  device-resident loop, inputs already in HBM, CUDA events on the launch stream tight
+  around each step's graph launch, a 256 MB L2 flush between steps (not timed).
+* ``value_l2_resident``  the same K steps as ONE uninterrupted device-side loop (production mode: the
+  working set of one circuit lives in L2; no host involvement between steps).
+* ``e2e``  the same K steps through ``B200Engine.run_transient`` (the reference-facing API) with
+  host buffers: initial state host->device, recorded waveforms device->host, wall clock.
+* ``roofline``  the dominant kernel of a step, timed alone with CUDA events (vjx_time_phase).
+* ``cpu_baseline``  the NumPy/SciPy oracle port timed on this box's host cores on a bounded sample.
+
+N > 1 (torchrun): whole-circuit replicas = PVT corners, ``--corners`` per GPU (weak scaling), no
+collective inside the step loop; the recorded waveforms are gathered to rank 0 with NCCL afterwards.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ms/transient step (c6288) on B200"
+UNIT = "ms/step"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm"):
+                if k in d:
+                    return float(d[k]), "measured"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+def make_circuit(workload: str, nbits: int, corner: int = 0):
+    from vajax_b200.benchmarks import circuits
+
+    if workload == "ring":
+        return circuits.ring_circuit(), "9-stage ring oscillator (47 unknowns)"
+    if workload == "mul":
+        nb = nbits
+    else:
+        nb = 16
+    circ = circuits.multiplier_circuit(nb)
+    if corner:
+        from vajax_b200.analysis.corners import apply_corner, sweep_corners
+
+        circ = apply_corner(circ, sweep_corners(64)[corner % 64])
+    desc = (f"{nb}x{nb} carry-save array multiplier in the c6288/mul64 gate library "
+            f"({sum(1 for d in circ['devices'] if d['model'] == 'psp103')} PSP103-shaped MOSFETs), trap, uic")
+    return circ, desc
+
+
+def get_bundles():
+    from vajax_b200.models.fixtures import get_bundle
+
+    return {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def phase_bytes(eng, lu):
+    """Algorithmic bytes per launch of each phase."""
+    ev = 0
+    jc = 0
+    rc = 0
+    for m in eng.models.values():
+        D, R, J, L = m["n_dev"], m["R"], m["J"], m["num_limit_states"]
+        nv, P, Cd = m["vnode1"].shape[1], m["dev_params"].shape[1], m["dev_cache"].shape[1]
+        ev += D * 8 * (2 * nv + P + Cd + L) + D * 8 * (J + 4 * R + L)
+        jc += D * J
+        rc += D * R
+    n, nse = eng.n_aug, eng.nse
+    nnz = lu["nnz_lu"]
+    return {
+        "device_eval": ev,
+        "jacobian_stamp": jc * (8 + 4) + nse * 8 + n * (8 + 4),
+        "residual": 4 * rc * (8 + 4) + rc * (8 + 4) + 5 * n * 8,
+        "lu_factor": 8 * (nse + 2 * nnz),
+        "lu_lsolve": 8 * ((nnz - n) // 2 + n) + 3 * 8 * n,
+        "lu_usolve": 8 * ((nnz - n) // 2 + n) + 3 * 8 * n,
+        "nr_update": 14 * n * 8,
+    }
+
+
+PHASES = ["device_eval", "jacobian_stamp", "residual", "lu_factor", "lu_lsolve", "lu_usolve", "nr_update"]
+
+
+def launches_per(eng):
+    nm = len(eng.models)
+    isrc = 1 if eng.n_is > 0 else 0
+    per_iter = 1 + isrc + nm + 1 + 1 + 3 + 2
+    per_attempt = 2 + (isrc + nm + 1 + 1 + 1 + 1 + 1 + 1)
+    return per_iter, per_attempt
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+
+    from vajax_b200.analysis.engine import B200Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - vajax_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    bundles = get_bundles()
+    K, W = args.steps, max(args.warmup, 3)
+    n_corners = args.corners
+    engines = []
+    desc = ""
+    for c in range(n_corners):
+        gid = rank * n_corners + c
+        circ, desc = make_circuit(args.workload, args.nbits, corner=gid if (world > 1 or n_corners > 1) else 0)
+        engines.append(B200Engine(circ, bundles, device=local_rank, use_device_graph=not args.no_graph).prepare())
+    eng = engines[0]
+    rows = 1 + K
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: W steps of every engine (LU analysis, graph build, caches)
+    for e in engines:
+        e.tran_begin(max_steps=1 + W)
+        e.tran_run()
+    # ---- value: per-step graph launches with an L2 flush in between (events inside vjx_tran_run)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    total_ms, steps_done, attempts, nr_total, rejected = 0.0, 0, 0, 0, 0
+    t_wall0 = time.perf_counter()
+    for e in engines:
+        e.tran_begin(max_steps=rows)
+        step = 1
+        while step < rows:
+            flush.fill_(1.0)
+            a = e.tran_run(step_limit=step + 1)
+            if a == 0:
+                break
+            total_ms += e.tran_run_ms()[0]
+            step += 1
+        sc = e.tran_scalars()
+        steps_done += sc["step_idx"] - 1
+        attempts += sc["attempts"]
+        nr_total += sc["total_nr"]
+        rejected += sc["rejected"]
+        if sc["error_flags"]:
+            raise SystemExit(f"bench.py: device error flags {sc['error_flags']}")
+    barrier()
+    wall_flushed = time.perf_counter() - t_wall0
+    # ---- value_l2_resident: the same steps as one uninterrupted device loop per engine
+    barrier()
+    res_ms, res_steps = 0.0, 0
+    for e in engines:
+        e.tran_begin(max_steps=rows)
+        e.tran_run(step_limit=rows)
+        res_ms += e.tran_run_ms()[0]
+        res_steps += e.tran_scalars()["step_idx"] - 1
+    barrier()
+    clocks = sampler.stop()
+    # ---- e2e through the public API with host buffers (H2D of the initial state, D2H of the waveforms)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps, h2d, d2h = 0, 0, 0
+    outs = []
+    for e in engines:
+        times, V_out, st = e.run_transient(max_steps=rows)
+        e2e_steps += st["n_steps"] - 1
+        h2d += e._tran["h2d_bytes"]
+        d2h += e._tran.get("d2h_bytes", 0)
+        outs.append((times, V_out))
+    torch.cuda.synchronize()
+    e2e_local = time.perf_counter() - t0
+    gather_s = 0.0
+    if world > 1:
+        import torch.distributed as dist
+
+        # K13: gather the recorded waveforms of every corner on rank 0 (NCCL over NVLink)
+        tg = time.perf_counter()
+        mine = torch.from_numpy(np.stack([o[1] for o in outs])).to(dev)
+        bufs = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, bufs, dst=0)
+        torch.cuda.synchronize()
+        gather_s = time.perf_counter() - tg
+        e2e_local += gather_s
+    # ---- reduce over ranks: MAX time, SUM steps
+    vals = torch.tensor([total_ms, res_ms, e2e_local, wall_flushed], dtype=torch.float64, device=dev)
+    cnts = torch.tensor([steps_done, res_steps, e2e_steps, attempts, nr_total, rejected, h2d, d2h], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
+    vals, cnts = vals.cpu().numpy(), cnts.cpu().numpy()
+    if rank != 0:
+        return
+    g_steps, g_res_steps, g_e2e_steps = int(cnts[0]), int(cnts[1]), int(cnts[2])
+    ms_per_step = vals[0] / max(g_steps, 1)
+    per_iter, per_attempt = launches_per(eng)
+    gpu_launches = int(cnts[4] * per_iter + cnts[3] * per_attempt)
+    # ---- roofline of the dominant kernel (rank 0, engine 0), timed alone
+    lu = eng.lu_stats()
+    pb = phase_bytes(eng, lu)
+    peak, peak_kind = load_peaks()
+    iters_per_step = cnts[4] / max(g_steps, 1)
+    att_per_step = cnts[3] / max(g_steps, 1)
+    phase = {}
+    for i, nm in enumerate(PHASES):
+        ms, nl = eng.time_phase(i, 20)
+        calls = {"device_eval": iters_per_step + att_per_step, "residual": iters_per_step + att_per_step}.get(nm, iters_per_step)
+        phase[nm] = {"ms": ms, "launches": nl, "calls_per_step": calls, "ms_per_step": ms * calls,
+                     "alg_bytes": pb[nm], "gbs": pb[nm] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0}
+    dom = max(phase, key=lambda k: phase[k]["ms_per_step"])
+    pd = phase[dom]
+    roof = {"kernel": dom, "bound": "hbm", "achieved": pd["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": pd["gbs"] / peak, "traffic": None, "peak_source": peak_kind,
+            "launch_ms": pd["ms"], "share_of_step": pd["ms_per_step"] / max(ms_per_step, 1e-12),
+            "note": "timed alone with CUDA events, L2-warm (working set < L2 at this size); latency-bound"}
+    out = {
+        "metric": METRIC, "value": ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "circuit": args.workload, "n_unknowns": eng.n_aug, "csr_nnz": eng.nse,
+                   "corners_per_gpu": n_corners, "parallelism": f"replicas x{world}" if world > 1 else "single circuit",
+                   "l2": "256 MB flush between timed steps (value); value_l2_resident is the uninterrupted device loop",
+                   "steps_timed": g_steps, "attempts": int(cnts[3]), "nr_iterations": int(cnts[4]), "rejected": int(cnts[5])},
+        "value_l2_resident": vals[1] / max(g_res_steps, 1),
+        "e2e": {"value": vals[2] * 1e3 / max(g_e2e_steps, 1), "unit": UNIT,
+                "h2d_bytes_per_step": cnts[6] / max(g_e2e_steps, 1), "d2h_bytes_per_step": cnts[7] / max(g_e2e_steps, 1),
+                "gather_s": gather_s},
+        "gpu_launches": gpu_launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "phases": {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in phase.items()},
+        "lu": lu,
+        "reported_reference": {"c6288_jax_gpu_T4_ms_per_step": 19.81, "c6288_jax_cpu_ms_per_step": 88.06,
+                               "note": "reference README numbers on its real c6288 netlist + PSP103; not the same circuit/model"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
+    print(json.dumps(out))
+
+
+def cpu_baseline(args, sample_steps: int, threads_note: str = "") -> dict:
+    """The oracle port (NumPy MIR interpreter + SciPy SuperLU) on the host cores, bounded sample."""
+    from oracle.engine import OracleEngine
+
+    circ, _ = make_circuit(args.workload, args.nbits)
+    o = OracleEngine(circ, get_bundles())
+    o.setup()
+    o.run_transient(max_steps=3)  # warm-up (imports, first factorisation)
+    t0 = time.perf_counter()
+    _, _, st = o.run_transient(max_steps=1 + sample_steps)
+    dt = time.perf_counter() - t0
+    n = max(st["n_steps"] - 1, 1)
+    return {"value": dt * 1e3 / n, "unit": UNIT, "cores": 1, "kind": "port",
+            "host_cores_available": os.cpu_count(),
+            "sample": f"first {n} accepted steps of the same transient (NumPy interpreter + SuperLU, 1 thread){threads_note}"}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's JAX implementation cannot be installed here (no jax, no
+    openvaf_py), so the CPU restatement of its algorithm (oracle/) is timed."""
+    if rank != 0:
+        return
+    K, W = args.steps, max(args.warmup, 3)
+    sample = min(K, args.cpu_steps)
+    cb = cpu_baseline(args, sample_steps=sample)
+    _, desc = make_circuit(args.workload, args.nbits)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": K,
+           "warmup": W, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": desc, "circuit": args.workload},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c6288", choices=["c6288", "mul", "ring"])
+    ap.add_argument("--nbits", type=int, default=16)
+    ap.add_argument("--corners", type=int, default=1, help="circuit replicas (PVT corners) per GPU")
+    ap.add_argument("--cpu-steps", type=int, default=25)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="host-polled NR/step loops (for ncu launch lists)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -130,9 +130,10 @@ int vjx_build_system(vjx_handle* h, const double* X_dev, const double* vsrc_dev,
 int vjx_lu_solve(vjx_handle* h, const double* csr_data_dev, const double* b_dev, double* x_dev, vjx_stream stream);
 /* Force a new analysis (ordering + pivot sequence) from the given values. */
 int vjx_lu_analyze(vjx_handle* h, const double* csr_data_dev, vjx_stream stream);
-/* Symbolic statistics: [0]=nnz(L+U) incl. diag, [1]=factor flops, [2]=levels(L), [3]=levels(U),
- * [4]=max row length, [5]=n */
-int vjx_lu_stats(vjx_handle* h, double* out6);
+/* Symbolic statistics, 10 doubles: [0]=nnz(L+U) incl. diag, [1]=factor flops, [2]=levels(L),
+ * [3]=levels(U), [4]=max row length, [5]=n, [6]=peeled singleton pivots, [7]=core size,
+ * [8]=longest L part of a row, [9]=entries of the scatter program */
+int vjx_lu_stats(vjx_handle* h, double* out10);
 
 /* ---- Seam S3: nr_solve (vajax/analysis/solver_factories.py:604-725) ---------------------- */
 int vjx_nr_solve(vjx_handle* h, const double* X_init_dev, const double* vsrc_dev, const double* isrc_dev,
@@ -151,6 +152,10 @@ int vjx_tran_begin(vjx_handle* h, const double* X0_dev, const double* Q_init_dev
 /* Run until t >= t_stop, step_idx >= max_steps, or `max_attempts` step attempts were made.
  * Returns the number of attempts made in *attempts. */
 int vjx_tran_run(vjx_handle* h, int max_attempts, int* attempts, vjx_stream stream);
+/* Change the accepted-step bound (1 <= step_limit <= max_steps of vjx_tran_begin); the next
+ * vjx_tran_run stops when step_idx reaches it.  Chunked runs a la _run_with_checkpoints
+ * (full_mna.py:1443-1699) and bench.py's warm-up / timed split use it. */
+int vjx_tran_set_step_limit(vjx_handle* h, int step_limit, vjx_stream stream);
 /* scalars: [0]=t [1]=dt [2]=step_idx [3]=total_nr_iters [4]=rejected [5]=min_dt_used
  *          [6]=max_dt_used [7]=history_count [8]=warmup_count [9]=consecutive_rejects
  *          [10]=attempts [11]=error_flags */
@@ -168,6 +173,9 @@ int vjx_tran_state(vjx_handle* h, double* X, double* Q_prev, double* dQdt_prev, 
  * on the handle's current state: 0=device eval, 1=jacobian stamp, 2=residual, 3=LU refactor,
  * 4=L solve, 5=U solve, 6=NR update. Also returns the number of kernels launched per phase. */
 int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg, int* launches, vjx_stream stream);
+/* Device time in ms (CUDA events recorded on `stream` tightly around the loop launch) of the last
+ * vjx_tran_run and the total since vjx_tran_begin. */
+int vjx_tran_run_ms(vjx_handle* h, double* last_ms, double* total_ms);
 /* Number of kernels launched by this handle since creation (for bench.py's gpu_launches). */
 long long vjx_launch_count(vjx_handle* h);
 

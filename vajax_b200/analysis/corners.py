@@ -1,0 +1,235 @@
+"""PVT corner / Monte-Carlo sweep definitions and the multi-GPU sweep driver.
+
+Mirrors the reference's corner vocabulary (reference: vajax/analysis/corners.py:39-376 -
+``ProcessCorner``, ``VoltageCorner``, ``CornerConfig``, ``PROCESS_CORNERS``,
+``TEMPERATURE_CORNERS``, ``create_standard_corners``, ``create_pvt_corners``,
+``apply_process_corner``, ``apply_voltage_corner``) and replaces the serial loop of
+``CircuitEngine.run_corners`` (reference: vajax/analysis/engine.py:2235-2320) by whole-circuit
+replicas: corner ``i`` runs on GPU ``i mod world_size``; nothing is exchanged during a run and the
+recorded waveforms are gathered once at the end.
+
+Parity target: "fresh engine per corner".  The reference re-uses a topology-keyed setup cache, so
+same-temperature process/voltage edits are silently dropped there; here every
+corner gets its own parameter / init-cache upload.
+"""
+
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+DEFAULT_TEMPERATURE_K = 300.15  # reference: vajax/config.py
+
+
+@dataclass
+class ProcessCorner:
+    name: str
+    mobility_scale: float = 1.0
+    vth_shift: float = 0.0
+    tox_scale: float = 1.0
+    length_delta: float = 0.0
+    model_params: Dict[str, Dict[str, float]] = field(default_factory=dict)
+
+
+@dataclass
+class VoltageCorner:
+    name: str
+    vdd_scale: float = 1.0
+    source_values: Dict[str, float] = field(default_factory=dict)
+
+
+@dataclass
+class CornerConfig:
+    name: str
+    process: Optional[ProcessCorner] = None
+    voltage: Optional[VoltageCorner] = None
+    temperature: float = DEFAULT_TEMPERATURE_K
+
+
+@dataclass
+class CornerResult:
+    corner: CornerConfig
+    times: Any = None
+    voltages: Any = None
+    stats: Dict[str, Any] = field(default_factory=dict)
+    converged: bool = True
+
+
+@dataclass
+class CornerSweepResult:
+    corners: List[CornerConfig] = field(default_factory=list)
+    results: List[CornerResult] = field(default_factory=list)
+
+    @property
+    def num_corners(self) -> int:
+        return len(self.results)
+
+    @property
+    def num_converged(self) -> int:
+        return sum(1 for r in self.results if r.converged)
+
+    @property
+    def all_converged(self) -> bool:
+        return all(r.converged for r in self.results)
+
+    def get_result(self, corner_name: str) -> Optional[CornerResult]:
+        return next((r for r in self.results if r.corner.name == corner_name), None)
+
+    def converged_results(self) -> List[CornerResult]:
+        return [r for r in self.results if r.converged]
+
+
+# values: reference corners.py:162-196
+PROCESS_CORNERS: Dict[str, ProcessCorner] = {
+    "FF": ProcessCorner("FF", mobility_scale=1.15, vth_shift=-0.05, tox_scale=0.95),
+    "TT": ProcessCorner("TT"),
+    "SS": ProcessCorner("SS", mobility_scale=0.85, vth_shift=0.05, tox_scale=1.05),
+    "FS": ProcessCorner("FS", mobility_scale=1.15, vth_shift=0.05),
+    "SF": ProcessCorner("SF", mobility_scale=0.85, vth_shift=-0.05),
+}
+TEMPERATURE_CORNERS: Dict[str, float] = {"cold": 233.15, "room": 300.15, "hot": 398.15}
+
+# Parameter names touched per knob.  The first group of each tuple is the reference's list
+# (corners.py:283-300); the names after the bar belong to the PSP103-shaped fixture model
+# (vajax_b200/models/fixtures.py), which has no uo/vth0/tox parameters.
+MOBILITY_PARAMS = ("uo", "mu0", "u0", "betn", "betp", "mue") + ("kp",)
+VTH_PARAMS = ("vth0", "vfb", "delvto", "dvt0") + ("vto",)
+TOX_PARAMS = ("tox", "toxe", "toxo", "toxp")
+COX_PARAMS = ("cox",)  # cox ~ 1/tox
+
+
+def _temp_tag(temp_k: float) -> str:
+    c = temp_k - 273.15
+    return {-40.0: "m40C", 27.0: "27C", 125.0: "125C"}.get(round(c, 6), f"{c:.0f}C")
+
+
+def create_standard_corners(processes: Optional[Sequence[str]] = None, temperatures: Optional[Sequence[float]] = None,
+                            vdd_scales: Optional[Sequence[float]] = None) -> List[CornerConfig]:
+    """All process x temperature x vdd combinations, named ``<proc>_<temp>_V<pct>pct``."""
+    out: List[CornerConfig] = []
+    for pn in (processes or ["TT"]):
+        if pn not in PROCESS_CORNERS:
+            raise ValueError(f"Unknown process corner: {pn}")
+        for t in (temperatures or [DEFAULT_TEMPERATURE_K]):
+            for v in (vdd_scales or [1.0]):
+                out.append(CornerConfig(name=f"{pn}_{_temp_tag(t)}_V{v * 100:.0f}pct", process=PROCESS_CORNERS[pn],
+                                        voltage=VoltageCorner(name=f"VDD_{v}", vdd_scale=v), temperature=float(t)))
+    return out
+
+
+def create_pvt_corners(processes: Optional[Sequence[str]] = None, temperatures: Optional[Sequence[Any]] = None,
+                       voltages: Optional[Sequence[float]] = None) -> List[CornerConfig]:
+    """Default 3 x 3 x 3 = 27 corners (FF/TT/SS, cold/room/hot, 0.9/1.0/1.1)."""
+    temps = [TEMPERATURE_CORNERS[t] if t in TEMPERATURE_CORNERS else float(t)
+             for t in (temperatures or ["cold", "room", "hot"])]
+    return create_standard_corners(list(processes or ["FF", "TT", "SS"]), temps, list(voltages or [0.9, 1.0, 1.1]))
+
+
+def apply_process_corner(devices: List[Dict[str, Any]], corner: Optional[ProcessCorner]) -> None:
+    """In-place edit of the OpenVAF devices' parameters."""
+    if corner is None:
+        return
+    for dev in devices:
+        if not dev.get("is_openvaf", False):
+            continue
+        p = dev.setdefault("params", {})
+        for k in MOBILITY_PARAMS:
+            if k in p:
+                p[k] = float(p[k]) * corner.mobility_scale
+        for k in VTH_PARAMS:
+            if k in p:
+                p[k] = float(p[k]) + corner.vth_shift
+        for k in TOX_PARAMS:
+            if k in p:
+                p[k] = float(p[k]) * corner.tox_scale
+        for k in COX_PARAMS:
+            if k in p:
+                p[k] = float(p[k]) / corner.tox_scale
+        if corner.length_delta != 0 and "l" in p:
+            p["l"] = float(p["l"]) + corner.length_delta
+        for k, v in corner.model_params.get(dev.get("model", ""), {}).items():
+            p[k] = v
+
+
+def apply_voltage_corner(devices: List[Dict[str, Any]], corner: Optional[VoltageCorner]) -> None:
+    """In-place edit of the voltage sources' DC values."""
+    if corner is None:
+        return
+    for dev in devices:
+        if dev.get("model") != "vsource":
+            continue
+        p = dev.setdefault("params", {})
+        if dev.get("name", "") in corner.source_values:
+            p["dc"] = corner.source_values[dev["name"]]
+        elif "dc" in p:
+            p["dc"] = float(p["dc"]) * corner.vdd_scale
+
+
+def apply_corner(circuit: dict, corner: CornerConfig) -> dict:
+    """A fresh circuit dict with the corner applied (the input is left untouched)."""
+    c = dict(circuit)
+    c["devices"] = copy.deepcopy(circuit["devices"])
+    apply_process_corner(c["devices"], corner.process)
+    apply_voltage_corner(c["devices"], corner.voltage)
+    c["temperature_k"] = float(corner.temperature)
+    c["corner_name"] = corner.name
+    return c
+
+
+def sweep_corners(n: int = 64) -> List[CornerConfig]:
+    """The 64-point sweep of BASELINE.json configs[4]: {FF,TT,SS,FS} x {233.15,273.15,300.15,398.15} K
+    x vdd {0.9,1.0,1.05,1.1}, truncated / cycled to ``n``."""
+    base = create_standard_corners(["FF", "TT", "SS", "FS"], [233.15, 273.15, 300.15, 398.15], [0.9, 1.0, 1.05, 1.1])
+    return [base[i % len(base)] for i in range(n)]
+
+
+def monte_carlo_corners(n: int = 64, seed: int = 64) -> List[CornerConfig]:
+    """Monte-Carlo draws applied like a process corner: mobility ~ N(1, 0.05), vth ~ N(0, 0.02 V),
+    tox ~ N(1, 0.02)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        pc = ProcessCorner(f"MC{i}", mobility_scale=float(rng.normal(1.0, 0.05)), vth_shift=float(rng.normal(0.0, 0.02)),
+                           tox_scale=float(rng.normal(1.0, 0.02)))
+        out.append(CornerConfig(name=f"MC{i}", process=pc, voltage=VoltageCorner("VDD_1.0"), temperature=DEFAULT_TEMPERATURE_K))
+    return out
+
+
+def shard(n_items: int, rank: int, world_size: int) -> List[int]:
+    """Static block-cyclic assignment: item i -> rank i mod world_size."""
+    return [i for i in range(n_items) if i % world_size == rank]
+
+
+def run_corners(circuit: dict, bundles: Dict[str, dict], corners: Sequence[CornerConfig], *, rank: int = 0,
+                world_size: int = 1, device: int = 0, engine_factory=None, gather=None, max_steps: Optional[int] = None,
+                **engine_kwargs) -> CornerSweepResult:
+    """Run this rank's share of ``corners`` (one fresh engine per corner) and gather.
+
+    ``engine_factory(circuit, bundles, device=..., **kw)`` defaults to ``B200Engine``; ``gather``
+    is a callable ``(list_of_local_payloads) -> list_of_all_payloads`` (bench.py / the tests pass a
+    ``torch.distributed`` gather; None = single process).  Results come back in corner order on
+    every rank that ``gather`` returns data to.
+    """
+    if engine_factory is None:
+        from .engine import B200Engine as engine_factory  # noqa: N813
+    local = []
+    for i in shard(len(corners), rank, world_size):
+        eng = engine_factory(apply_corner(circuit, corners[i]), bundles, device=device, **engine_kwargs)
+        times, V, st = eng.run_transient(max_steps=max_steps)
+        n = int(st["n_steps"])
+        local.append(dict(index=i, times=np.asarray(times[:n]), voltages=np.asarray(V[:n]),
+                          stats={k: v for k, v in st.items() if np.isscalar(v)}))
+        if hasattr(eng, "close"):
+            eng.close()
+    payloads = gather(local) if gather is not None else local
+    res = CornerSweepResult(corners=list(corners))
+    if payloads is None:
+        return res
+    for p in sorted(payloads, key=lambda d: d["index"]):
+        st = p["stats"]
+        res.results.append(CornerResult(corner=corners[p["index"]], times=p["times"], voltages=p["voltages"], stats=st,
+                                        converged=int(st.get("error_flags", 0)) == 0))
+    return res

@@ -686,10 +686,11 @@ class B200Engine:
         return x.cpu().numpy()
 
     def lu_stats(self) -> dict:
-        out = np.zeros(6)
+        out = np.zeros(10)
         vlib.check(vlib.load().vjx_lu_stats(self.handle, out.ctypes.data_as(C.c_void_p)))
         return dict(nnz_lu=int(out[0]), flops=float(out[1]), levels_l=int(out[2]), levels_u=int(out[3]),
-                    max_row_len=int(out[4]), n=int(out[5]))
+                    max_row_len=int(out[4]), n=int(out[5]), n_singletons=int(out[6]), n_core=int(out[7]),
+                    max_l_len=int(out[8]), scatter_entries=int(out[9]))
 
     # ---- Seam S3 -----------------------------------------------------------------------
     def nr_solve(self, X_init, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0, integ_c1=0.0,
@@ -745,8 +746,9 @@ class B200Engine:
         return V
 
     # ---- FullMNAStrategy.run (full_mna.py:780-1196) --------------------------------------
-    def run_transient(self, t_stop: Optional[float] = None, dt: Optional[float] = None, max_steps: Optional[int] = None,
-                      chunk_attempts: int = 0, read_outputs: bool = True):
+    def tran_begin(self, t_stop: Optional[float] = None, dt: Optional[float] = None, max_steps: Optional[int] = None):
+        """Initial condition (UIC or DC operating point, full_mna.py:882-957) and device state
+        allocation; host arrays go host->device here."""
         self.prepare()
         torch = self._torch()
         lib = vlib.load()
@@ -780,45 +782,87 @@ class B200Engine:
                                       float(max_dt), int(max_steps), None))
         torch.cuda.synchronize()
         self.timings["tran_setup"] = time.perf_counter() - t_setup
+        self._tran = dict(t_stop=t_stop, max_steps=int(max_steps),
+                          h2d_bytes=8 * (dX0.numel() + dQ.numel() + dI.numel() + dM.numel()))
+        return self._tran
+
+    def tran_run(self, step_limit: Optional[int] = None, max_attempts: int = 0) -> int:
+        """Advance the device-resident loop until t_stop, ``step_limit`` accepted rows (row 0 is the
+        initial condition) or ``max_attempts`` attempts; returns the attempts made."""
+        lib = vlib.load()
+        if step_limit is not None:
+            vlib.check(lib.vjx_tran_set_step_limit(self.handle, int(step_limit), None))
+        att = C.c_int(0)
+        vlib.check(lib.vjx_tran_run(self.handle, int(max_attempts), C.byref(att), None))
+        return att.value
+
+    def tran_run_ms(self) -> Tuple[float, float]:
+        """(last, total) device milliseconds of the loop launches inside vjx_tran_run (CUDA events)."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        vlib.check(vlib.load().vjx_tran_run_ms(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def tran_scalars(self) -> dict:
+        sc = np.zeros(12)
+        vlib.check(vlib.load().vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), None))
+        keys = ["t", "dt", "step_idx", "total_nr", "rejected", "min_dt_used", "max_dt_used", "history_count", "warmup",
+                "consecutive_rejects", "attempts", "error_flags"]
+        return {k: (float(v) if k in ("t", "dt", "min_dt_used", "max_dt_used") else int(v)) for k, v in zip(keys, sc)}
+
+    def tran_read(self, rows: Optional[int] = None):
+        """Device -> host copy of the recorded outputs (times, V_out, I_out)."""
+        max_steps = self._tran["max_steps"]
+        rows = max_steps if rows is None else min(int(rows), max_steps)
+        nvs = self.n_vs
+        times = np.zeros(max_steps)
+        V_out = np.zeros((max_steps, self.n_external))
+        I_out = np.zeros((max_steps, max(nvs, 1)))
+        if rows > 0:
+            vlib.check(vlib.load().vjx_tran_read(self.handle, 0, rows, times.ctypes.data_as(C.c_void_p),
+                                                 V_out.ctypes.data_as(C.c_void_p), I_out.ctypes.data_as(C.c_void_p), None))
+        self._tran["d2h_bytes"] = 8 * rows * (1 + self.n_external + max(nvs, 1))
+        return times, V_out, I_out
+
+    def run_transient(self, t_stop: Optional[float] = None, dt: Optional[float] = None, max_steps: Optional[int] = None,
+                      chunk_attempts: int = 0, read_outputs: bool = True):
+        torch = self._torch()
+        tr = self.tran_begin(t_stop, dt, max_steps)
+        t_stop, max_steps = tr["t_stop"], tr["max_steps"]
+        nvs = self.n_vs
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_start = time.perf_counter()
         ev0.record()
-        att = C.c_int(0)
-        total_att = 0
         while True:
-            vlib.check(lib.vjx_tran_run(self.handle, int(chunk_attempts), C.byref(att), None))
-            total_att += att.value
-            if att.value == 0 or chunk_attempts <= 0:
+            att = self.tran_run(None, chunk_attempts)
+            if att == 0 or chunk_attempts <= 0:
                 break
-            sc = np.zeros(12)
-            vlib.check(lib.vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), None))
-            if not (sc[0] < t_stop) or sc[2] >= max_steps:
+            sc = self.tran_scalars()
+            if not (sc["t"] < t_stop) or sc["step_idx"] >= max_steps:
                 break
         ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t_start
-        sc = np.zeros(12)
-        vlib.check(lib.vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), None))
-        n_steps = int(sc[2])
-        times = np.zeros(max_steps)
-        V_out = np.zeros((max_steps, self.n_external))
-        I_out = np.zeros((max_steps, max(nvs, 1)))
+        sc = self.tran_scalars()
+        n_steps = sc["step_idx"]
         if read_outputs:
-            vlib.check(lib.vjx_tran_read(self.handle, 0, max_steps, times.ctypes.data_as(C.c_void_p),
-                                         V_out.ctypes.data_as(C.c_void_p), I_out.ctypes.data_as(C.c_void_p), None))
+            times, V_out, I_out = self.tran_read(max_steps)
+        else:
+            times = np.zeros(max_steps)
+            V_out = np.zeros((max_steps, self.n_external))
+            I_out = np.zeros((max_steps, max(nvs, 1)))
         node_indices = {name: idx for name, idx in self.node_names.items() if 0 < idx < self.n_external}
-        rejected = int(sc[4])
+        rejected = sc["rejected"]
         stats = {
             "n_steps": n_steps, "total_timesteps": n_steps, "accepted_steps": n_steps, "rejected_steps": rejected,
-            "total_nr_iterations": int(sc[3]), "avg_nr_iterations": float(sc[3]) / max(n_steps, 1),
+            "total_nr_iterations": sc["total_nr"], "avg_nr_iterations": float(sc["total_nr"]) / max(n_steps, 1),
             "wall_time": wall, "time_per_step_ms": wall / n_steps * 1000 if n_steps > 0 else 0,
             "device_time_ms": ev0.elapsed_time(ev1),
-            "min_dt_used": float(sc[5]), "max_dt_used": float(sc[6]),
+            "min_dt_used": sc["min_dt_used"], "max_dt_used": sc["max_dt_used"],
             "convergence_rate": n_steps / max(n_steps + rejected, 1),
             "strategy": "adaptive_full_mna_b200", "solver": "b200_sparse_lu",
             "V_out": V_out, "I_out": I_out, "node_indices": node_indices,
             "current_indices": {d["name"]: i for i, d in enumerate(self.vsources)},
-            "attempts": int(sc[10]), "error_flags": int(sc[11]),
+            "attempts": sc["attempts"], "error_flags": sc["error_flags"],
         }
         return times, V_out, stats
 

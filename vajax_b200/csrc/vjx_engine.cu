@@ -83,12 +83,8 @@ struct LUDev {
   const int* order_u;
   const int* perm_r;
   const int* perm_c;
-  const long long* pair_ptr;   // [nnz+1] contributor pairs of each L+U entry
-  const int* pair_l;           // absolute index of L(i,k)
-  const int* pair_u;           // absolute index of U(k,j)
-  const int* ent_order;        // [nnz] entries per row sorted by wave
-  const int* row_wave_ptr;     // [n+1]
-  const int* wave_end;         // end offset into ent_order per wave
+  const long long* upd_ptr;    // [nnz+1] start of each L entry's scatter list
+  const int* upd_pos;          // position inside row i of each column of U(k,:)
   double* val;
   double* inv_diag;
   double* y;
@@ -197,27 +193,70 @@ __global__ void k_isrc(int n2, const int* __restrict__ dest, const double* __res
 
 enum { SLOT_DIAG = 1, SLOT_NOI_ZERO = 2, SLOT_NOI_ONE = 4 };
 
+// Segments longer than this are reduced by a whole CTA (supply-rail diagonals collect one
+// contribution per attached transistor: 10^4 at c6288 size, 10^5 at mul64 size).
+#define VJX_LONG_SEG 96
+
+// Deterministic CTA sum: fixed strided partials, fixed shuffle butterfly, fixed warp order.
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  const int nw = blockDim.x >> 5;
+  for (int w = 0; w < nw; ++w) t += sh[w];
+  return t;
+}
+__device__ __forceinline__ double block_max_256(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  const int nw = blockDim.x >> 5;
+  for (int w = 0; w < nw; ++w) t = fmax(t, sh[w]);
+  return t;
+}
+
 // csr[s] = sum of the slot's contributions in the reference's scatter order
 // (model order, instance, entry; vajax/analysis/mna_builder.py:953-958), then the diagonal
 // regularisation (:969) and the vsource incidence constants (:972-989).  With enforce_noi the
 // NOI rows/columns are rewritten as in solver_factories.py:1268-1276.
-__global__ void k_stamp_jacobian(int nse, const int* __restrict__ seg, const double* __restrict__ jsorted,
-                                 const unsigned char* __restrict__ flags, const float* __restrict__ cst,
-                                 const double* __restrict__ ctl, int enforce_noi, double* __restrict__ csr) {
+__device__ __forceinline__ double finish_slot(double acc, unsigned char f, float c, double reg, int enforce_noi) {
+  if (f & SLOT_DIAG) acc += reg;
+  if (c != 0.0f) acc += (double)c;
+  if (enforce_noi) {
+    if (f & SLOT_NOI_ZERO) acc = 0.0;
+    if (f & SLOT_NOI_ONE) acc = 1.0;
+  }
+  return acc;
+}
+
+// Grid layout: CTAs [0, n_long) each reduce one long segment; the rest stride over all slots and
+// skip the long ones.
+__global__ void __launch_bounds__(256) k_stamp_jacobian(int nse, const int* __restrict__ seg,
+                                 const double* __restrict__ jsorted, const unsigned char* __restrict__ flags,
+                                 const float* __restrict__ cst, const double* __restrict__ ctl, int enforce_noi,
+                                 const int* __restrict__ long_slots, int n_long, double* __restrict__ csr) {
+  __shared__ double sh[8];
   const double reg = ctl[VJX_CTL_DIAGREG] + ctl[VJX_CTL_GSHUNT];
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nse; s += gridDim.x * blockDim.x) {
+  if ((int)blockIdx.x < n_long) {
+    const int s = long_slots[blockIdx.x];
+    const int b = seg[s], e = seg[s + 1];
+    double acc = 0.0;
+    for (int p = b + threadIdx.x; p < e; p += blockDim.x) acc += jsorted[p];
+    acc = block_sum_256(acc, sh);
+    if (threadIdx.x == 0) csr[s] = finish_slot(acc, flags[s], cst[s], reg, enforce_noi);
+    return;
+  }
+  const int nb = gridDim.x - n_long;
+  for (int s = (blockIdx.x - n_long) * blockDim.x + threadIdx.x; s < nse; s += nb * blockDim.x) {
     int b = seg[s], e = seg[s + 1];
+    if (e - b > VJX_LONG_SEG) continue;
     double acc = 0.0;
     for (int p = b; p < e; ++p) acc += jsorted[p];
-    unsigned char f = flags[s];
-    if (f & SLOT_DIAG) acc += reg;
-    float c = cst[s];
-    if (c != 0.0f) acc += (double)c;
-    if (enforce_noi) {
-      if (f & SLOT_NOI_ZERO) acc = 0.0;
-      if (f & SLOT_NOI_ONE) acc = 1.0;
-    }
-    csr[s] = acc;
+    csr[s] = finish_slot(acc, flags[s], cst[s], reg, enforce_noi);
   }
 }
 
@@ -245,20 +284,85 @@ struct ResidualArgs {
   double* maxres;
   NRStat* st;
   int check;                  // accumulate convergence statistics
+  const int* long_rows;       // node rows with more than VJX_LONG_SEG contributions
+  int n_long;
 };
 
-// reference: _build_residual vajax/analysis/mna_builder.py:1012-1076, combine_transient_residual
-// vajax/analysis/mna.py:673-719, residual test solver_factories.py:271-281
-__global__ void k_residual(ResidualArgs a) {
+// One node row of the residual once its five segment reductions are known
+// (reference: _build_residual vajax/analysis/mna_builder.py:1012-1076, combine_transient_residual
+// vajax/analysis/mna.py:673-719, residual tolerance solver_factories.py:271-281).
+__device__ __forceinline__ void finish_node_row(const ResidualArgs& a, int i, double fr, double q, double lr, double lq,
+                                                double mx, double c0, double c1, double d1, double c2, double eff,
+                                                double& f, double& tol) {
+  fr = fr - lr;
+  double fb = 0.0;
+  for (int p = a.att_ptr[i]; p < a.att_ptr[i + 1]; ++p) {
+    int v = a.att_idx[p];
+    if (a.att_sign[p] > 0) {
+      if (a.Ivs) a.Ivs[v] = -fr;
+      fb += a.X[a.n_total + v];
+    } else {
+      fb += -a.X[a.n_total + v];
+    }
+  }
+  if (a.n_vs > 0) fr = fr + fb;
+  double qp = a.Q_prev ? a.Q_prev[i] : 0.0;
+  double dq = a.dQdt_prev ? a.dQdt_prev[i] : 0.0;
+  double q2 = a.Q_prev2 ? a.Q_prev2[i] : 0.0;
+  f = fr - 0.0 + c0 * (q - lq) + c1 * qp + d1 * dq + c2 * q2;
+  f = f + eff * a.X[i + 1];
+  if (a.Q) a.Q[i] = q;
+  if (a.maxres) a.maxres[i] = mx;
+  double fl = a.res_tol_floor ? a.res_tol_floor[i] : a.abstol;
+  tol = fmax(mx * a.reltol, fl);
+  if (mx != mx || fl != fl) tol = mx * 0.0 + fl * 0.0 + tol;  // jnp.maximum propagates NaN
+}
+
+// Grid layout: CTAs [0, n_long) each reduce one long node row; the rest stride over all rows.
+__global__ void __launch_bounds__(256) k_residual(ResidualArgs a) {
+  __shared__ double sh[8];
   const int n_aug = a.n_unknowns + a.n_vs;
   const double c0 = a.ctl[VJX_CTL_C0], c1 = a.ctl[VJX_CTL_C1], d1 = a.ctl[VJX_CTL_D1], c2 = a.ctl[VJX_CTL_C2];
   const double eff = a.ctl[VJX_CTL_DIAGREG] + a.ctl[VJX_CTL_GSHUNT];
   int bad = 0;
   double mf = 0.0;
   bool mfnan = false;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_aug; i += gridDim.x * blockDim.x) {
+  if ((int)blockIdx.x < a.n_long) {
+    const int i = a.long_rows[blockIdx.x];
+    double fr = 0.0, q = 0.0, lr = 0.0, lq = 0.0, mx = 0.0;
+    for (int p = a.vseg[i] + threadIdx.x; p < a.vseg[i + 1]; p += blockDim.x) {
+      const double2* r = reinterpret_cast<const double2*>(a.vsorted + (size_t)p * 4);
+      double2 r0 = r[0], r1 = r[1];
+      fr += r0.x;
+      mx = fmax(mx, fabs(r0.x));
+      q += r0.y;
+      lr += r1.x;
+      lq += r1.y;
+    }
+    fr = block_sum_256(fr, sh);
+    q = block_sum_256(q, sh);
+    lr = block_sum_256(lr, sh);
+    lq = block_sum_256(lq, sh);
+    mx = block_max_256(mx, sh);
+    if (threadIdx.x == 0) {
+      double f, tol;
+      finish_node_row(a, i, fr, q, lr, lq, mx, c0, c1, d1, c2, eff, f, tol);
+      if (a.f) a.f[i] = f;
+      if (a.check) {
+        double fc = a.conv_mask[i] ? f : 0.0;
+        double af = fabs(fc);
+        if (af != af) atomicMax(&a.st->max_f_bits, 0x7ff8000000000000ULL);
+        else if (af > 0.0) atomic_max_pos(&a.st->max_f_bits, af);
+        if (!(af < tol)) atomicOr(&a.st->bad_res, 1);
+      }
+    }
+    return;
+  }
+  const int nb = gridDim.x - a.n_long;
+  for (int i = (blockIdx.x - a.n_long) * blockDim.x + threadIdx.x; i < n_aug; i += nb * blockDim.x) {
     double f, tol;
     if (i < a.n_unknowns) {
+      if (a.vseg[i + 1] - a.vseg[i] > VJX_LONG_SEG) continue;
       double fr = 0.0, q = 0.0, lr = 0.0, lq = 0.0, mx = 0.0;
       for (int p = a.vseg[i]; p < a.vseg[i + 1]; ++p) {
         const double2* r = reinterpret_cast<const double2*>(a.vsorted + (size_t)p * 4);
@@ -269,28 +373,7 @@ __global__ void k_residual(ResidualArgs a) {
         lr += r1.x;
         lq += r1.y;
       }
-      fr = fr - lr;
-      double fb = 0.0;
-      for (int p = a.att_ptr[i]; p < a.att_ptr[i + 1]; ++p) {
-        int v = a.att_idx[p];
-        if (a.att_sign[p] > 0) {
-          if (a.Ivs) a.Ivs[v] = -fr;
-          fb += a.X[a.n_total + v];
-        } else {
-          fb += -a.X[a.n_total + v];
-        }
-      }
-      if (a.n_vs > 0) fr = fr + fb;
-      double qp = a.Q_prev ? a.Q_prev[i] : 0.0;
-      double dq = a.dQdt_prev ? a.dQdt_prev[i] : 0.0;
-      double q2 = a.Q_prev2 ? a.Q_prev2[i] : 0.0;
-      f = fr - 0.0 + c0 * (q - lq) + c1 * qp + d1 * dq + c2 * q2;
-      f = f + eff * a.X[i + 1];
-      if (a.Q) a.Q[i] = q;
-      if (a.maxres) a.maxres[i] = mx;
-      double fl = a.res_tol_floor ? a.res_tol_floor[i] : a.abstol;
-      tol = fmax(mx * a.reltol, fl);
-      if (mx != mx || fl != fl) tol = mx * 0.0 + fl * 0.0 + tol;  // jnp.maximum propagates NaN
+      finish_node_row(a, i, fr, q, lr, lq, mx, c0, c1, d1, c2, eff, f, tol);
     } else {
       int v = i - a.n_unknowns;
       f = a.X[a.vs_p[v]] - a.X[a.vs_n[v]] - a.vsrc[v];
@@ -329,29 +412,25 @@ __global__ void k_residual(ResidualArgs a) {
 // ------------------------------------------------------------------------------------------
 #define VJX_SPIN_LIMIT (1u << 24)
 
-// Wait until every row in cols[b..e) carries the current epoch flag. Lanes poll different
-// dependencies in parallel. Returns false if the watchdog fired.
-__device__ __forceinline__ bool wait_deps(const unsigned* flags, const int* cols, int b, int e, unsigned epoch,
-                                          int lane, NRStat* st, int errbit) {
-  bool ok = true;
-  for (int p = b + lane; p < e; p += 32) {
-    const unsigned* f = flags + cols[p];
-    unsigned spins = 0;
-    while (ld_acquire_u32(f) != epoch) {
-      if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); ok = false; break; }
-      __nanosleep(32);
-    }
+__device__ __forceinline__ bool wait_flag(const unsigned* f, unsigned epoch, NRStat* st, int errbit) {
+  unsigned spins = 0;
+  while (ld_acquire_u32(f) != epoch) {
+    if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); return false; }
+    if (spins > 64) __nanosleep(20);
   }
-  __syncwarp();
-  return ok;
+  return true;
 }
 
-// Numeric refactorisation.  One warp per row, rows handed out in dependency-level order.  Inside
-// a row the entries are evaluated wave by wave: each entry gathers its contributor products
-// L(i,k)*U(k,j) in ascending k (bit-identical to the classic k-sequential row update), and the
-// entries of one wave are independent, so the 4,800-entry supply-rail rows take ~150 parallel
-// waves instead of 4,800 serial updates.
+// Numeric refactorisation, up-looking and k-sequential.  One warp per row, rows handed out in
+// dependency-level order.  The row lives in a shared-memory working vector w (rows longer than
+// VJX_ROWBUF work in place in global memory): for every L entry (i,k) in ascending k the warp waits
+// for row k, forms l = w[k] / U(k,k) and scatters w[pos] -= l * U(k,j) through the precomputed
+// position list, lanes striding over U(k,:).  Rounding is identical to the classic row update.
+// Everything static (k, row bounds, scatter base) is loaded before the wait, so once the awaited
+// row is published the critical path is: flag -> {1/U(k,k), U(k,:)} -> shared-memory update.
+#define VJX_ROWBUF 640
 __global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __restrict__ csr, NRStat* st) {
+  __shared__ double wbuf[8][VJX_ROWBUF];
   const unsigned epoch = st->epoch;
   const int lane = threadIdx.x & 31;
   const int n = lu.n;
@@ -361,32 +440,50 @@ __global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __res
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= (unsigned)n) break;
     const int i = lu.order_l[tk];
-    const int rb = lu.ptr[i], dg = lu.diag[i];
-    wait_deps(lu.flag_f, lu.col, rb, dg, epoch, lane, st, 1);
-    const int w0 = lu.row_wave_ptr[i], w1 = lu.row_wave_ptr[i + 1];
-    int eb = rb;
-    for (int w = w0; w < w1; ++w) {
-      const int ee = lu.wave_end[w];
-      for (int q = eb + lane; q < ee; q += 32) {
-        const int pos = lu.ent_order[q];
-        const int s = lu.src[pos];
-        double acc = s >= 0 ? csr[s] : 0.0;
-        const long long pb = lu.pair_ptr[pos], pe = lu.pair_ptr[pos + 1];
-        for (long long pr = pb; pr < pe; ++pr) acc -= lu.val[lu.pair_l[pr]] * __ldcg(lu.val + lu.pair_u[pr]);
-        if (pos < dg) acc *= __ldcg(lu.inv_diag + lu.col[pos]);
-        lu.val[pos] = acc;
+    const int rb = lu.ptr[i], dg = lu.diag[i], re = lu.ptr[i + 1];
+    double d;
+    if (dg == rb) {
+      // no L part (peeled singletons, leaves): the row is a copy of A's values
+      for (int p = rb + lane; p < re; p += 32) {
+        const int s = lu.src[p];
+        lu.val[p] = s >= 0 ? csr[s] : 0.0;
       }
-      eb = ee;
+      const int sd = lu.src[dg];
+      d = sd >= 0 ? csr[sd] : 0.0;
+    } else {
+      const bool in_smem = (re - rb) <= VJX_ROWBUF;
+      double* w = in_smem ? wbuf[threadIdx.x >> 5] : lu.val + rb;
+      for (int p = rb + lane; p < re; p += 32) {
+        const int s = lu.src[p];
+        w[p - rb] = s >= 0 ? csr[s] : 0.0;
+      }
       __syncwarp();
+      for (int p = rb; p < dg; ++p) {
+        const int k = lu.col[p];
+        const int ub = lu.diag[k] + 1, ue = lu.ptr[k + 1];
+        const long long mb = lu.upd_ptr[p];
+        int t0 = 0;
+        if (ub + lane < ue) t0 = lu.upd_pos[mb + lane];
+        wait_flag(lu.flag_f + k, epoch, st, 1);
+        const double l = w[p - rb] * __ldcg(lu.inv_diag + k);
+        if (ub + lane < ue) w[t0] -= l * __ldcg(lu.val + ub + lane);
+        for (int q = ub + lane + 32; q < ue; q += 32) w[lu.upd_pos[mb + (q - ub)]] -= l * __ldcg(lu.val + q);
+        __syncwarp();
+        if (lane == 0) w[p - rb] = l;
+      }
+      __syncwarp();
+      if (in_smem)
+        for (int p = rb + lane; p < re; p += 32) lu.val[p] = w[p - rb];
+      d = w[dg - rb];
     }
+    __syncwarp();
     if (lane == 0) {
-      double d = lu.val[dg];
       if (d == 0.0 || d != d) atomicOr(&st->error, 2);
       lu.inv_diag[i] = 1.0 / d;
+      __threadfence();
+      st_release_u32(lu.flag_f + i, epoch);
     }
-    __threadfence();
     __syncwarp();
-    if (lane == 0) st_release_u32(lu.flag_f + i, epoch);
   }
 }
 
@@ -396,7 +493,8 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Forward solve y = L^-1 P b: one warp per row, lanes stride over the row's L entries.
+// Forward solve y = L^-1 P b: one warp per row, lanes stride over the row's L entries; every lane
+// loads its matrix entry first and then waits for exactly the y it needs.
 __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __restrict__ b, double scale,
                                                    const unsigned char* __restrict__ zero_mask, NRStat* st) {
   const unsigned epoch = st->epoch;
@@ -409,13 +507,21 @@ __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __res
     if (tk >= (unsigned)n) break;
     const int i = lu.order_l[tk];
     const int rb = lu.ptr[i], dg = lu.diag[i];
-    wait_deps(lu.flag_l, lu.col, rb, dg, epoch, lane, st, 4);
-    double part = 0.0;
-    for (int p = rb + lane; p < dg; p += 32) part += lu.val[p] * __ldcg(lu.y + lu.col[p]);
-    part = warp_sum(part);
+    double bi = 0.0;
     if (lane == 0) {
       const int r = lu.perm_r[i];
-      const double bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
+      bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
+    }
+    double part = 0.0;
+    for (int p = rb + lane; p < dg; p += 32) {
+      const int c = lu.col[p];
+      const double v = lu.val[p];
+      wait_flag(lu.flag_l + c, epoch, st, 4);
+      part += v * __ldcg(lu.y + c);
+    }
+    if (dg - rb > 1) part = warp_sum(part);
+    else part = __shfl_sync(0xffffffffu, part, 0);
+    if (lane == 0) {
       lu.y[i] = bi - part;
       __threadfence();
       st_release_u32(lu.flag_l + i, epoch);
@@ -435,14 +541,26 @@ __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict_
     if (tk >= (unsigned)n) break;
     const int i = lu.order_u[tk];
     const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
-    wait_deps(lu.flag_u, lu.col, ub, re, epoch, lane, st, 8);
-    double part = 0.0;
-    for (int p = ub + lane; p < re; p += 32) part += lu.val[p] * __ldcg(lu.xp + lu.col[p]);
-    part = warp_sum(part);
+    double yi = 0.0, di = 0.0;
+    int pc = 0;
     if (lane == 0) {
-      const double xi = (lu.y[i] - part) * lu.inv_diag[i];
+      yi = lu.y[i];
+      di = lu.inv_diag[i];
+      pc = lu.perm_c[i];
+    }
+    double part = 0.0;
+    for (int p = ub + lane; p < re; p += 32) {
+      const int c = lu.col[p];
+      const double v = lu.val[p];
+      wait_flag(lu.flag_u + c, epoch, st, 8);
+      part += v * __ldcg(lu.xp + c);
+    }
+    if (re - ub > 1) part = warp_sum(part);
+    else part = __shfl_sync(0xffffffffu, part, 0);
+    if (lane == 0) {
+      const double xi = (yi - part) * di;
       lu.xp[i] = xi;
-      x_out[lu.perm_c[i]] = xi;
+      x_out[pc] = xi;
       __threadfence();
       st_release_u32(lu.flag_u + i, epoch);
     }
@@ -917,7 +1035,8 @@ struct vjx_handle {
   std::vector<int> h_indptr, h_indices;
   std::vector<ModelState*> models;
   // stamping tables
-  DevBuf<int> jseg, vseg, isrc_dest, att_ptr, att_idx, vs_p, vs_n;
+  DevBuf<int> jseg, vseg, isrc_dest, att_ptr, att_idx, vs_p, vs_n, long_slots, long_rows;
+  int n_long_slots = 0, n_long_rows = 0;
   DevBuf<signed char> att_sign;
   DevBuf<unsigned char> slot_flags, conv_mask, delta_mask, is_noi, noi_row_mask;
   DevBuf<float> slot_const;
@@ -933,8 +1052,8 @@ struct vjx_handle {
   bool lu_ready = false;
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_order_l, lu_order_u, lu_perm_r, lu_perm_c;
-  DevBuf<long long> lu_pair_ptr;
-  DevBuf<int> lu_pair_l, lu_pair_u, lu_ent_order, lu_row_wave_ptr, lu_wave_end;
+  DevBuf<long long> lu_upd_ptr;
+  DevBuf<int> lu_upd_pos;
   DevBuf<unsigned> lu_flags;
   DevBuf<double> lu_val, lu_inv, lu_y, lu_xp;
   LUDev lud{};
@@ -953,6 +1072,8 @@ struct vjx_handle {
   cudaStream_t own_stream = nullptr;
   void* pinned = nullptr;
   long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the loop launch inside vjx_tran_run
+  double last_run_ms = 0.0, total_run_ms = 0.0;
   int sm_count = 148;
   ~vjx_handle();
 };
@@ -969,6 +1090,8 @@ vjx_handle::~vjx_handle() {
   if (g_step_pre) cudaGraphExecDestroy(g_step_pre);
   if (g_step_post) cudaGraphExecDestroy(g_step_post);
   if (g_tran) cudaGraphExecDestroy(g_tran);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
   if (own_stream) cudaStreamDestroy(own_stream);
   if (pinned) cudaFreeHost(pinned);
 }
@@ -1082,6 +1205,14 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
   }
   CK(h->jseg.upload(jseg));
   CK(h->jsorted.alloc(std::max<size_t>(h->n_jcontrib, 1)));
+  {
+    std::vector<int> ls;
+    for (int s = 0; s < nse; ++s)
+      if (jcount[s] > VJX_LONG_SEG) ls.push_back(s);
+    h->n_long_slots = (int)ls.size();
+    if (ls.empty()) ls.push_back(0);
+    CK(h->long_slots.upload(ls));
+  }
   // ---- slot flags: diagonal regularisation, vsource incidence, NOI rows/cols
   std::vector<unsigned char> flags(nse, 0);
   std::vector<float> cst(nse, 0.0f);
@@ -1178,6 +1309,14 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
   }
   CK(h->vseg.upload(vseg));
   CK(h->vsorted.alloc(std::max<size_t>(h->n_vcontrib * 4, 4)));
+  {
+    std::vector<int> lr;
+    for (int i = 0; i < nu; ++i)
+      if (vcount[i] > VJX_LONG_SEG) lr.push_back(i);
+    h->n_long_rows = (int)lr.size();
+    if (lr.empty()) lr.push_back(0);
+    CK(h->long_rows.upload(lr));
+  }
   // ---- vsources attached to each node row, in the order of the concatenated [p..., n...] scatter
   {
     std::vector<int> cnt(std::max(nu, 1), 0);
@@ -1341,8 +1480,9 @@ static int launch_eval(vjx_handle* h, const BuildPtrs& b, cudaStream_t s) {
 }
 
 static void launch_stamp(vjx_handle* h, double* csr, int enforce_noi, cudaStream_t s) {
-  k_stamp_jacobian<<<grid_for(h, h->nse), 256, 0, s>>>(h->nse, h->jseg.p, h->jsorted.p, h->slot_flags.p,
-                                                       h->slot_const.p, h->ctl.p, enforce_noi, csr);
+  k_stamp_jacobian<<<grid_for(h, h->nse) + h->n_long_slots, 256, 0, s>>>(
+      h->nse, h->jseg.p, h->jsorted.p, h->slot_flags.p, h->slot_const.p, h->ctl.p, enforce_noi, h->long_slots.p,
+      h->n_long_slots, csr);
   h->launches++;
 }
 
@@ -1356,7 +1496,8 @@ static void launch_residual(vjx_handle* h, const BuildPtrs& b, int check, cudaSt
   a.res_tol_floor = b.res_tol_floor; a.conv_mask = h->conv_mask.p; a.ctl = h->ctl.p;
   a.reltol = h->o.reltol; a.abstol = h->o.abstol; a.vntol = h->o.vntol;
   a.f = b.f; a.Q = b.Q; a.Ivs = b.Ivs; a.maxres = b.maxres; a.st = h->st.p; a.check = check;
-  k_residual<<<grid_for(h, h->n_aug), 256, 0, s>>>(a);
+  a.long_rows = h->long_rows.p; a.n_long = h->n_long_rows;
+  k_residual<<<grid_for(h, h->n_aug) + h->n_long_rows, 256, 0, s>>>(a);
   h->launches++;
 }
 
@@ -1407,15 +1548,13 @@ static int upload_symbolic(vjx_handle* h) {
   CK(h->lu_order_u.upload(S.order_u));
   CK(h->lu_perm_r.upload(S.perm_r));
   CK(h->lu_perm_c.upload(S.perm_c));
-  std::vector<long long> pp(S.pair_ptr.begin(), S.pair_ptr.end());
-  CK(h->lu_pair_ptr.upload(pp));
-  std::vector<int> pl(S.pair_l), pu(S.pair_u);
-  if (pl.empty()) { pl.push_back(0); pu.push_back(0); }
-  CK(h->lu_pair_l.upload(pl));
-  CK(h->lu_pair_u.upload(pu));
-  CK(h->lu_ent_order.upload(S.ent_order));
-  CK(h->lu_row_wave_ptr.upload(S.row_wave_ptr));
-  CK(h->lu_wave_end.upload(S.wave_end));
+  std::vector<long long> pp(S.upd_ptr.begin(), S.upd_ptr.end());
+  CK(h->lu_upd_ptr.upload(pp));
+  {
+    std::vector<int> up(S.upd_pos);
+    if (up.empty()) up.push_back(0);
+    CK(h->lu_upd_pos.upload(up));
+  }
   CK(h->lu_val.alloc((size_t)S.nnz_lu));
   CK(h->lu_inv.alloc(S.n));
   CK(h->lu_y.alloc(S.n));
@@ -1425,8 +1564,7 @@ static int upload_symbolic(vjx_handle* h) {
   L.n = S.n;
   L.ptr = h->lu_ptr.p; L.col = h->lu_col.p; L.diag = h->lu_diag.p; L.src = h->lu_src.p;
   L.order_l = h->lu_order_l.p; L.order_u = h->lu_order_u.p; L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
-  L.pair_ptr = h->lu_pair_ptr.p; L.pair_l = h->lu_pair_l.p; L.pair_u = h->lu_pair_u.p;
-  L.ent_order = h->lu_ent_order.p; L.row_wave_ptr = h->lu_row_wave_ptr.p; L.wave_end = h->lu_wave_end.p;
+  L.upd_ptr = h->lu_upd_ptr.p; L.upd_pos = h->lu_upd_pos.p;
   L.val = h->lu_val.p; L.inv_diag = h->lu_inv.p; L.y = h->lu_y.p; L.xp = h->lu_xp.p;
   L.flag_f = h->lu_flags.p; L.flag_l = h->lu_flags.p + S.n; L.flag_u = h->lu_flags.p + 2 * (size_t)S.n;
   // persistent grids: every CTA must be resident (dependency waits), so size from occupancy
@@ -1464,7 +1602,7 @@ extern "C" int vjx_lu_analyze(vjx_handle* h, const double* csr_data_dev, vjx_str
   return ensure_lu(h, csr_data_dev, (cudaStream_t)stream);
 }
 
-extern "C" int vjx_lu_stats(vjx_handle* h, double* out6) {
+extern "C" int vjx_lu_stats(vjx_handle* h, double* out6 /* [10] */) {
   if (!h || !h->lu_ready) return fail(VJX_ERR_INVALID, "LU not analysed yet");
   out6[0] = (double)h->sym.nnz_lu;
   out6[1] = h->sym.flops;
@@ -1472,6 +1610,10 @@ extern "C" int vjx_lu_stats(vjx_handle* h, double* out6) {
   out6[3] = h->sym.n_levels_u;
   out6[4] = h->sym.max_row_len;
   out6[5] = h->sym.n;
+  out6[6] = (double)h->sym.n_singletons;
+  out6[7] = (double)h->sym.n_core;
+  out6[8] = (double)h->sym.max_l_len;
+  out6[9] = (double)h->sym.upd_pos.size();
   return VJX_OK;
 }
 
@@ -1665,6 +1807,8 @@ extern "C" int vjx_tran_begin(vjx_handle* h, const double* X0, const double* Q_i
   k_copy<<<grid_for(h, nu), 256, 0, s>>>(h->n_unknowns, Q_init, h->Q_prev.p);
   k_copy<<<grid_for(h, nu), 256, 0, s>>>(h->n_unknowns, hist_maxres, h->hist_mrc.p);
   if (h->n_vs > 0 && I0) CK(cudaMemcpyAsync(h->I_out.p, I0, sizeof(double) * h->n_vs, cudaMemcpyDeviceToDevice, s));
+  h->last_run_ms = 0.0;
+  h->total_run_ms = 0.0;
   k_tran_init<<<1, 1, 0, s>>>(h->ts.p, h->st.p, t_stop, dt, max_dt, max_steps, h->H);
   h->launches += 3;
   k_abs_copy<<<grid_for(h, nt), 256, 0, s>>>(nt, X0, h->Vmax.p);
@@ -1797,6 +1941,11 @@ extern "C" int vjx_tran_run(vjx_handle* h, int max_attempts, int* attempts, vjx_
     k_dec_attempts<<<1, 1, 0, s>>>(h->ts.p);
   }
   k_set_attempts_limit<<<1, 1, 0, s>>>(h->ts.p, limit);
+  if (!h->ev0) {
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+  }
+  CK(cudaEventRecord(h->ev0, s));
   if (h->o.use_device_graph) {
     if (!h->g_tran) {
       int rc = build_tran_graph(h, limit, s);
@@ -1823,14 +1972,39 @@ extern "C" int vjx_tran_run(vjx_handle* h, int max_attempts, int* attempts, vjx_
       if (!hts->cont) break;
     }
   }
+  CK(cudaEventRecord(h->ev1, s));
   CK(cudaMemcpyAsync(hts, h->ts.p, sizeof(TranScalars), cudaMemcpyDeviceToHost, s));
   int rc = check_device_error(h, s);
   if (rc) return rc;
+  {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_run_ms = ms;
+    h->total_run_ms += ms;
+  }
   if (attempts) *attempts = hts->attempts - start_attempts;
   CK(cudaGetLastError());
   return VJX_OK;
 }
 
+
+__global__ void k_set_step_limit(TranScalars* s, int limit) {
+  s->max_steps = limit;
+  s->cont = (s->t < s->t_stop) && (s->step_idx < limit);
+}
+
+// Lower / raise the accepted-step bound of the running transient (<= the rows allocated by
+// vjx_tran_begin): "run <= K steps, return state", the contract of the reference's
+// _run_with_checkpoints (full_mna.py:1443-1699).
+extern "C" int vjx_tran_set_step_limit(vjx_handle* h, int step_limit, vjx_stream stream) {
+  if (!h || !h->X.p) return fail(VJX_ERR_INVALID, "vjx_tran_begin not called");
+  if (step_limit < 1 || step_limit > h->max_steps) return fail(VJX_ERR_INVALID, "step limit outside the allocated rows");
+  CK(cudaSetDevice(h->device));
+  k_set_step_limit<<<1, 1, 0, (cudaStream_t)stream>>>(h->ts.p, step_limit);
+  h->launches++;
+  CK(cudaGetLastError());
+  return VJX_OK;
+}
 
 extern "C" int vjx_tran_scalars(vjx_handle* h, double* out, vjx_stream stream) {
   if (!h || !h->ts.p) return fail(VJX_ERR_INVALID, "null handle");
@@ -1877,6 +2051,15 @@ extern "C" int vjx_tran_state(vjx_handle* h, double* X, double* Q_prev, double* 
   if (Q_prev) CK(cudaMemcpyAsync(Q_prev, h->Q_prev.p, sizeof(double) * h->n_unknowns, cudaMemcpyDeviceToHost, s));
   if (dQdt_prev) CK(cudaMemcpyAsync(dQdt_prev, h->dQdt_prev.p, sizeof(double) * h->n_unknowns, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return VJX_OK;
+}
+
+// Device time (CUDA events on the launch stream, tight around the loop launch) of the last
+// vjx_tran_run call and the running total since vjx_tran_begin.
+extern "C" int vjx_tran_run_ms(vjx_handle* h, double* last_ms, double* total_ms) {
+  if (!h) return fail(VJX_ERR_INVALID, "null handle");
+  if (last_ms) *last_ms = h->last_run_ms;
+  if (total_ms) *total_ms = h->total_run_ms;
   return VJX_OK;
 }
 

@@ -165,6 +165,69 @@ CSC csr_to_csc(int n, const int* indptr, const int* indices, const double* value
     }
   return c;
 }
+
+// Singleton peeling (the first phase of UMFPACK / KLU-BTF).  A column with one active entry is a
+// pivot whose row becomes a (possibly long) U row that nothing depends on; a row with one active
+// entry is a pivot whose column becomes L entries without updates.  Either way no fill is created,
+// and the supply rails of an MNA matrix (a rail node pinned by a voltage source: branch row = row
+// singleton, branch-current column = column singleton) leave the core that AMD + Gilbert-Peierls
+// have to handle, together with every NOI row that was rewritten to identity.
+struct Peel {
+  std::vector<int> rows, cols;          // pivot sequence of the peeled part
+  std::vector<char> row_active, col_active;
+};
+
+Peel peel_singletons(int n, const int* indptr, const int* indices, const double* values, const CSC& A) {
+  Peel P;
+  P.row_active.assign(n, 1);
+  P.col_active.assign(n, 1);
+  std::vector<int> rc(n), cc(n);
+  for (int i = 0; i < n; ++i) rc[i] = indptr[i + 1] - indptr[i];
+  for (int j = 0; j < n; ++j) cc[j] = A.p[j + 1] - A.p[j];
+  std::vector<int> q;  // encoded: idx * 2 + (1 = column singleton, 0 = row singleton)
+  q.reserve(2 * (size_t)n);
+  for (int j = 0; j < n; ++j) if (cc[j] == 1) q.push_back(2 * j + 1);
+  for (int i = 0; i < n; ++i) if (rc[i] == 1) q.push_back(2 * i);
+  for (size_t h = 0; h < q.size(); ++h) {
+    const int idx = q[h] >> 1;
+    if (q[h] & 1) {
+      const int j = idx;
+      if (!P.col_active[j] || cc[j] != 1) continue;
+      int i = -1;
+      double v = 0.0;
+      for (int pp = A.p[j]; pp < A.p[j + 1]; ++pp)
+        if (P.row_active[A.i[pp]]) { i = A.i[pp]; v = A.x[pp]; break; }
+      if (i < 0 || !(std::fabs(v) > 0.0)) continue;
+      P.rows.push_back(i);
+      P.cols.push_back(j);
+      P.row_active[i] = 0;
+      P.col_active[j] = 0;
+      for (int kk = indptr[i]; kk < indptr[i + 1]; ++kk) {
+        int j2 = indices[kk];
+        if (P.col_active[j2] && --cc[j2] == 1) q.push_back(2 * j2 + 1);
+      }
+    } else {
+      const int i = idx;
+      if (!P.row_active[i] || rc[i] != 1) continue;
+      int j = -1;
+      double v = 0.0;
+      for (int kk = indptr[i]; kk < indptr[i + 1]; ++kk)
+        if (P.col_active[indices[kk]]) { j = indices[kk]; v = values ? values[kk] : 1.0; break; }
+      if (j < 0 || !(std::fabs(v) > 0.0)) continue;
+      P.rows.push_back(i);
+      P.cols.push_back(j);
+      P.row_active[i] = 0;
+      P.col_active[j] = 0;
+      for (int pp = A.p[j]; pp < A.p[j + 1]; ++pp) {
+        int i2 = A.i[pp];
+        if (P.row_active[i2] && --rc[i2] == 1) q.push_back(2 * i2);
+      }
+      // the row's other entries sit in already peeled columns; removing the row does not
+      // change any active column count
+    }
+  }
+  return P;
+}
 }  // namespace
 
 int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const double* values,
@@ -172,10 +235,50 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
   S = VjxSymbolic();
   S.n = n;
   if (n <= 0) { err = "empty matrix"; return -1; }
-  std::vector<int> q;
-  vjx_amd_order(n, indptr, indices, q);
-  if ((int)q.size() != n) { err = "ordering failed"; return -1; }
   CSC A = csr_to_csc(n, indptr, indices, values);
+  // --- pivot column order: peeled singletons first, then AMD on the remaining core
+  std::vector<int> q;
+  std::vector<int> pref_row(n, -1);   // preferred pivot row of each column
+  Peel P = peel_singletons(n, indptr, indices, values, A);
+  const int n_single = (int)P.cols.size();
+  S.n_singletons = n_single;
+  q.reserve(n);
+  for (int k = 0; k < n_single; ++k) {
+    q.push_back(P.cols[k]);
+    pref_row[P.cols[k]] = P.rows[k];
+  }
+  {
+    // pair the core's rows and columns: (i, i) when both are active, the rest in sorted order
+    std::vector<int> core_cols, loc(n, -1), pair_col_of_row(n, -1), free_rows, free_cols;
+    for (int j = 0; j < n; ++j) {
+      if (!P.col_active[j]) continue;
+      if (P.row_active[j]) pair_col_of_row[j] = j; else free_cols.push_back(j);
+    }
+    for (int i = 0; i < n; ++i)
+      if (P.row_active[i] && pair_col_of_row[i] < 0) free_rows.push_back(i);
+    if (free_rows.size() != free_cols.size()) { err = "singleton peeling left a non-square core"; return -1; }
+    for (size_t t = 0; t < free_rows.size(); ++t) pair_col_of_row[free_rows[t]] = free_cols[t];
+    for (int j = 0; j < n; ++j)
+      if (P.col_active[j]) { loc[j] = (int)core_cols.size(); core_cols.push_back(j); }
+    const int nc = (int)core_cols.size();
+    S.n_core = nc;
+    std::vector<int> row_of_loc(nc, -1);
+    for (int i = 0; i < n; ++i)
+      if (P.row_active[i]) { row_of_loc[loc[pair_col_of_row[i]]] = i; pref_row[pair_col_of_row[i]] = i; }
+    std::vector<int> lip(nc + 1, 0), lix;
+    for (int a = 0; a < nc; ++a) {
+      int i = row_of_loc[a];
+      for (int kk = indptr[i]; kk < indptr[i + 1]; ++kk)
+        if (P.col_active[indices[kk]]) lix.push_back(loc[indices[kk]]);
+      std::sort(lix.begin() + lip[a], lix.end());
+      lip[a + 1] = (int)lix.size();
+    }
+    std::vector<int> pl;
+    vjx_amd_order(nc, lip.data(), lix.data(), pl);
+    if ((int)pl.size() != nc) { err = "ordering failed"; return -1; }
+    for (int a = 0; a < nc; ++a) q.push_back(core_cols[pl[a]]);
+  }
+  if ((int)q.size() != n) { err = "ordering failed"; return -1; }
 
   // L: unit lower, column k holds original row ids (mapped through pinv at the end); U: upper.
   std::vector<int> Lp(n + 1, 0), Up(n + 1, 0), Li, Ui;
@@ -252,8 +355,14 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
       // candidate if any (pattern is what matters for refactorisation), else fail.
       if (ipiv == -1) { err = "structurally singular at column " + std::to_string(col); return -4; }
     }
-    if (pinv[col] < 0 && mark[col] == k && std::fabs(x[col]) >= amax * pivot_tol && std::fabs(x[col]) > 0.0)
-      ipiv = col;
+    {
+      // prefer the paired row (the diagonal for ordinary MNA unknowns; the peeled row for a
+      // singleton pivot, which is taken unconditionally unless it is numerically zero)
+      const int pr = pref_row[col];
+      if (pr >= 0 && pinv[pr] < 0 && mark[pr] == k && std::fabs(x[pr]) > 0.0 &&
+          (k < n_single || std::fabs(x[pr]) >= amax * pivot_tol))
+        ipiv = pr;
+    }
     double pivot = x[ipiv];
     Ui.push_back(k);
     Ux.push_back(pivot);
@@ -341,73 +450,42 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
     if (S.level_u[a] != S.level_u[b]) return S.level_u[a] < S.level_u[b];
     return a > b;
   });
-  // --- flops and the gather program
+  // --- flops and the scatter program
   double fl = 0.0;
-  int64_t npairs = 0;
+  int64_t nupd = 0;
   for (int i = 0; i < n; ++i) {
     int64_t c = 0;
     for (int pp = S.lu_ptr[i]; pp < S.lu_diag[i]; ++pp) {
       int k = S.lu_col[pp];
       c += S.lu_ptr[k + 1] - S.lu_diag[k] - 1;
     }
-    npairs += c;
+    nupd += c;
     fl += 2.0 * (double)c + (double)(S.lu_diag[i] - S.lu_ptr[i]);
+    S.max_l_len = std::max(S.max_l_len, S.lu_diag[i] - S.lu_ptr[i]);
   }
   S.flops = fl;
   if (build_update_stream) {
-    if (npairs > (int64_t)2000000000LL) { err = "gather program too large"; return -1; }
-    S.pair_ptr.assign((size_t)S.nnz_lu + 1, 0);
+    if (nupd > (int64_t)8000000000LL) { err = "scatter program too large"; return -1; }
+    S.upd_ptr.assign((size_t)S.nnz_lu + 1, 0);
+    S.upd_pos.resize((size_t)nupd);
     std::vector<int> pos_of(n, -1);
-    // pass 1: count contributors per entry
+    int64_t o = 0;
     for (int i = 0; i < n; ++i) {
-      int b = S.lu_ptr[i], e = S.lu_ptr[i + 1];
-      for (int pp = b; pp < e; ++pp) pos_of[S.lu_col[pp]] = pp;
-      for (int pp = b; pp < S.lu_diag[i]; ++pp) {
-        int k = S.lu_col[pp];
+      const int b = S.lu_ptr[i], e = S.lu_ptr[i + 1];
+      for (int pp = b; pp < e; ++pp) pos_of[S.lu_col[pp]] = pp - b;
+      for (int pp = b; pp < e; ++pp) {
+        S.upd_ptr[(size_t)pp] = o;
+        if (pp >= S.lu_diag[i]) continue;
+        const int k = S.lu_col[pp];
         for (int qq = S.lu_diag[k] + 1; qq < S.lu_ptr[k + 1]; ++qq) {
-          int t = pos_of[S.lu_col[qq]];
+          const int t = pos_of[S.lu_col[qq]];
           if (t < 0) { err = "LU pattern not closed under elimination"; return -1; }
-          S.pair_ptr[(size_t)t + 1]++;
+          S.upd_pos[(size_t)o++] = t;
         }
       }
       for (int pp = b; pp < e; ++pp) pos_of[S.lu_col[pp]] = -1;
     }
-    for (int64_t p2 = 0; p2 < S.nnz_lu; ++p2) S.pair_ptr[(size_t)p2 + 1] += S.pair_ptr[(size_t)p2];
-    S.pair_l.resize((size_t)npairs);
-    S.pair_u.resize((size_t)npairs);
-    std::vector<int64_t> fillp(S.pair_ptr.begin(), S.pair_ptr.end() - 1);
-    std::vector<int> elev((size_t)S.nnz_lu, 0);
-    S.ent_order.resize((size_t)S.nnz_lu);
-    S.row_wave_ptr.assign((size_t)n + 1, 0);
-    S.wave_end.clear();
-    std::vector<int> cnt;
-    for (int i = 0; i < n; ++i) {
-      int b = S.lu_ptr[i], e = S.lu_ptr[i + 1];
-      for (int pp = b; pp < e; ++pp) pos_of[S.lu_col[pp]] = pp;
-      int maxlev = 0;
-      for (int pp = b; pp < S.lu_diag[i]; ++pp) {   // ascending k: elev[pp] is final here
-        int k = S.lu_col[pp];
-        for (int qq = S.lu_diag[k] + 1; qq < S.lu_ptr[k + 1]; ++qq) {
-          int t = pos_of[S.lu_col[qq]];
-          int64_t o = fillp[t]++;
-          S.pair_l[(size_t)o] = pp;
-          S.pair_u[(size_t)o] = qq;
-          if (elev[t] < elev[pp] + 1) elev[t] = elev[pp] + 1;
-        }
-      }
-      for (int pp = b; pp < e; ++pp) maxlev = std::max(maxlev, elev[pp]);
-      // counting sort of the row's entries by wave (stable: ascending column inside a wave)
-      cnt.assign((size_t)maxlev + 2, 0);
-      for (int pp = b; pp < e; ++pp) cnt[(size_t)elev[pp] + 1]++;
-      for (int l = 0; l <= maxlev; ++l) cnt[(size_t)l + 1] += cnt[(size_t)l];
-      S.row_wave_ptr[i] = (int)S.wave_end.size();
-      for (int l = 0; l <= maxlev; ++l) S.wave_end.push_back(b + cnt[(size_t)l + 1]);
-      std::vector<int> nx2(cnt.begin(), cnt.end() - 1);
-      for (int pp = b; pp < e; ++pp) S.ent_order[(size_t)b + nx2[(size_t)elev[pp]]++] = pp;
-      S.max_waves = std::max(S.max_waves, maxlev + 1);
-      for (int pp = b; pp < e; ++pp) pos_of[S.lu_col[pp]] = -1;
-    }
-    S.row_wave_ptr[n] = (int)S.wave_end.size();
+    S.upd_ptr[(size_t)S.nnz_lu] = o;
   }
   return 0;
 }
@@ -416,22 +494,19 @@ double vjx_symbolic_selfcheck(const VjxSymbolic& S, int n, const int* indptr, co
                               const double* values, const double* b, double* x_out) {
   std::vector<double> v((size_t)S.nnz_lu, 0.0), inv(n, 0.0), y(n, 0.0), xp(n, 0.0);
   for (int t = 0; t < n; ++t) {
-    int i = S.order_l[t];
-    int w0 = S.row_wave_ptr[i], w1 = S.row_wave_ptr[i + 1];
-    int eb = S.lu_ptr[i];
-    for (int w = w0; w < w1; ++w) {
-      int ee = S.wave_end[w];
-      for (int q = eb; q < ee; ++q) {
-        int pos = S.ent_order[q];
-        double acc = S.lu_src[pos] >= 0 ? values[S.lu_src[pos]] : 0.0;
-        for (int64_t pr = S.pair_ptr[pos]; pr < S.pair_ptr[(size_t)pos + 1]; ++pr)
-          acc -= v[S.pair_l[(size_t)pr]] * v[S.pair_u[(size_t)pr]];
-        if (pos < S.lu_diag[i]) acc *= inv[S.lu_col[pos]];
-        v[pos] = acc;
-      }
-      eb = ee;
+    const int i = S.order_l[t];
+    const int rb = S.lu_ptr[i], dg = S.lu_diag[i], re = S.lu_ptr[i + 1];
+    double* w = v.data() + rb;
+    for (int pp = rb; pp < re; ++pp) w[pp - rb] = S.lu_src[pp] >= 0 ? values[S.lu_src[pp]] : 0.0;
+    for (int pp = rb; pp < dg; ++pp) {
+      const int k = S.lu_col[pp];
+      const double l = w[pp - rb] * inv[k];
+      const int ub = S.lu_diag[k] + 1, ue = S.lu_ptr[k + 1];
+      const int64_t mb = S.upd_ptr[(size_t)pp];
+      for (int q = ub; q < ue; ++q) w[S.upd_pos[(size_t)(mb + (q - ub))]] -= l * v[q];
+      w[pp - rb] = l;
     }
-    inv[i] = 1.0 / v[S.lu_diag[i]];
+    inv[i] = 1.0 / w[dg - rb];
   }
   for (int t = 0; t < n; ++t) {
     int i = S.order_l[t];
@@ -459,7 +534,7 @@ double vjx_symbolic_selfcheck(const VjxSymbolic& S, int n, const int* indptr, co
 
 // C hooks for the CPU-only tests of the host logic (ctypes).
 extern "C" int vjx_symbolic_probe(int n, const int* indptr, const int* indices, const double* values,
-                                  double pivot_tol, const double* b, double* x_out, double* stats8) {
+                                  double pivot_tol, const double* b, double* x_out, double* stats8 /* [12] */) {
   VjxSymbolic S;
   std::string err;
   int rc = vjx_symbolic_analyze(n, indptr, indices, values, pivot_tol, true, S, err);
@@ -473,7 +548,29 @@ extern "C" int vjx_symbolic_probe(int n, const int* indptr, const int* indices, 
     stats8[4] = S.max_row_len;
     stats8[5] = (double)n;
     stats8[6] = r;
-    stats8[7] = (double)S.pair_l.size();
+    stats8[7] = (double)S.upd_pos.size();
+    stats8[8] = S.n_singletons;
+    stats8[9] = S.n_core;
+    stats8[10] = S.max_l_len;
+    stats8[11] = 0.0;
+  }
+  return 0;
+}
+
+// Per-row diagnostics of the analysis (CPU-only tests and offline tuning): L / U dependency level,
+// number of L and U entries and number of in-row waves, all indexed by permuted row.
+extern "C" int vjx_symbolic_rows(int n, const int* indptr, const int* indices, const double* values,
+                                 double pivot_tol, int* level_l, int* level_u, int* l_len, int* u_len, int* waves) {
+  VjxSymbolic S;
+  std::string err;
+  int rc = vjx_symbolic_analyze(n, indptr, indices, values, pivot_tol, true, S, err);
+  if (rc != 0) return rc;
+  for (int i = 0; i < n; ++i) {
+    if (level_l) level_l[i] = S.level_l[i];
+    if (level_u) level_u[i] = S.level_u[i];
+    if (l_len) l_len[i] = S.lu_diag[i] - S.lu_ptr[i];
+    if (u_len) u_len[i] = S.lu_ptr[i + 1] - S.lu_diag[i] - 1;
+    if (waves) waves[i] = S.lu_diag[i] - S.lu_ptr[i];
   }
   return 0;
 }

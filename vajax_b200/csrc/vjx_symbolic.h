@@ -4,12 +4,14 @@
 // or UMFPACK (vajax/sparse/umfpack_ffi.cpp:253-300: symbolic cached by (n, nnz), numeric + solve per
 // call, pivot tolerance 0.1).  Here the analysis runs once per circuit on the first Jacobian
 // ("pivot order fixed at the DC operating point", BASELINE.json north_star item 3):
-//   1. approximate-minimum-degree ordering of the pattern of A + A^T (dense rows deferred),
+//   0. singleton peeling (UMFPACK / KLU-BTF first phase): rail nodes pinned by voltage sources,
+//      branch-current columns and identity rows leave the core without fill,
+//   1. approximate-minimum-degree ordering of the core's pattern of A + A^T (dense rows deferred),
 //   2. left-looking Gilbert-Peierls LU with threshold partial pivoting that prefers the diagonal
 //      (the KLU strategy) to fix the row permutation and the structural pattern of L and U,
 //   3. row-wise (CSR) storage of L+U in the permuted space, the map from CSR slots of A into it,
 //   4. dependency levels for the factorisation / forward solve (L pattern) and back solve (U),
-//   5. the per-entry gather program (contributor pairs + in-row waves) of the numeric kernel.
+//   5. the scatter program (position of every U(k,j) inside row i, per L entry) of the numeric kernel.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -27,17 +29,16 @@ struct VjxSymbolic {
   std::vector<int> order_u;    // rows sorted by U-dependency level (back solve order)
   std::vector<int> level_l, level_u;
   int n_levels_l = 0, n_levels_u = 0, max_row_len = 0;
-  // Gather program of the numeric refactorisation.  Entry (i,j) of L+U is
-  //   w = A(i,j) - sum_{k in L(i,:), k < min(i,j), U(k,j) != 0} L(i,k) * U(k,j)   (ascending k)
-  // and L(i,j) = w / U(j,j) for j < i.  pair_l / pair_u are absolute indices into the L+U value
-  // array of L(i,k) and U(k,j).  Entries of a row are grouped in waves: every contributor L(i,k)
-  // of an entry lies in an earlier wave, so a wave's entries are independent.
-  std::vector<int64_t> pair_ptr;  // [nnz_lu+1]
-  std::vector<int> pair_l, pair_u;
-  std::vector<int> ent_order;     // [nnz_lu] absolute entry positions, per row sorted by wave
-  std::vector<int> row_wave_ptr;  // [n+1] -> wave_end
-  std::vector<int> wave_end;      // absolute end index into ent_order of each wave
-  int max_waves = 0;
+  // Scatter program of the numeric refactorisation (up-looking, k-sequential): row i is held in a
+  // working vector w; for every L entry (i,k) in ascending k,  l = w[k] / U(k,k)  and
+  // w[j] -= l * U(k,j) for every j in U(k,:).  upd_pos lists, for each L entry, the position inside
+  // row i (relative to the row start) of each column of U(k,:), in the order U(k,:) is stored, so the
+  // kernel never searches.  upd_ptr is indexed by the absolute position of the L entry.
+  std::vector<int64_t> upd_ptr;   // [nnz_lu+1]
+  std::vector<int> upd_pos;       // [sum over L entries (i,k) of |U(k,:)|]
+  int max_l_len = 0;              // longest L part of a row (sequential k-steps of one row)
+  int n_singletons = 0;           // pivots peeled as row / column singletons (no fill, no updates)
+  int n_core = 0;                 // unknowns left for AMD + Gilbert-Peierls
   double flops = 0.0;             // 2 * sum_k nnz(L(:,k)) * nnz(U(k,:)) + nnz(L)
   int64_t nnz_lu = 0;
 };
