@@ -1,5 +1,2 @@
-"""``jax.experimental`` placeholder: the sparse BCSR/BCOO paths (spineax/cuDSS, dense-from-BCOO) are
-not exercised by the golden generator, which uses the reference's dense and CSR-direct paths."""
-import types
-
-sparse = types.SimpleNamespace(BCSR=None, BCOO=None)
+"""``jax.experimental`` subset (see ../__init__.py)."""
+from . import sparse as sparse  # noqa: F401

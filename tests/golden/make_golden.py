@@ -62,6 +62,10 @@ from vajax.analysis.transient import adaptive as ref_adaptive  # noqa: E402
 from vajax_b200.benchmarks import circuits  # noqa: E402
 from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 
+# openvaf_models.py drops its openvaf_jax import when the Rust crate openvaf_py is missing (:63-70);
+# the code generator itself is pure Python, so hand it back.
+ref_models.openvaf_jax = openvaf_jax
+ref_models.HAS_OPENVAF = True
 logging.getLogger("vajax").setLevel(logging.ERROR)
 MODELS = ("resistor", "capacitor", "diode", "psp103")
 
@@ -183,7 +187,7 @@ def unit_vectors(out: dict):
                 Vmax = np.abs(rng.normal(size=6)) * 2
                 dt_new, norm = ref_adaptive.compute_lte_timestep_jax(
                     jnp.asarray(Vn), jnp.asarray(Vp), jnp.asarray(pe), jnp.asarray(dt), jnp.asarray(hc), cfg, ec,
-                    jnp.asarray(Vmax))
+                    V_max_historic=jnp.asarray(Vmax))
                 lte.append(np.concatenate([[hc, ec, pe, dt], Vn, Vp, Vmax, [float(dt_new), float(norm)]]))
     out["lte_cases"] = np.array(lte)
     vn = rng.uniform(-3, 3, 400)
@@ -252,7 +256,7 @@ def engine_vectors(name: str, limiting: bool, compiled: dict, out: dict, sparse:
     sdd = setup.source_device_data
     n_vs = len(sdd.get("vsource", {}).get("names", []))
     out[f"{tag}_sizes"] = np.array([n_total, nu, n_vs, strat._total_limit_states if hasattr(strat, "_total_limit_states") else -1])
-    bs = strat._cached_build_system
+    bs = strat._cached_build_system_jit
     dev_arrays = strat._device_arrays_full_mna
     # ---- build_system on seeded inputs (same seeds as tests/test_gpu_parity.py)
     rng = np.random.default_rng(7)

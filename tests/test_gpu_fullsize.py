@@ -1,0 +1,104 @@
+"""Size-independent properties at BASELINE.json's c6288 scale (the oracle is too slow to rerun a
+whole transient there): linear-solve residuals, run-to-run bit-identity of the stamped system,
+host-polled vs device-graph loops, chunked runs, logic-level sanity of the multiplier outputs."""
+import numpy as np
+import pytest
+
+from vajax_b200.benchmarks import circuits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c6288(bundles):
+    from vajax_b200.analysis.engine import B200Engine
+
+    e = B200Engine(circuits.multiplier_circuit(16), bundles, use_device_graph=True).prepare()
+    yield e
+    e.close()
+
+
+def test_c6288_sizes(c6288):
+    e = c6288
+    n_mos = sum(1 for d in e.devices if d["model"] == "psp103")
+    assert n_mos == 10048 and e.n_vs == 34
+    assert e.n_total == 5091 + 2 * n_mos  # two surviving internal unknowns per MOSFET
+    assert e.n_total < 30000  # tests/test_vacask_benchmarks.py:340-347
+
+
+def test_c6288_build_is_deterministic_and_lu_solves(c6288):
+    import scipy.sparse as sp
+
+    e = c6288
+    rng = np.random.default_rng(1)
+    X = np.zeros(e.n_total + e.n_vs)
+    X[1:e.n_total] = rng.uniform(0, 1.2, e.n_unknowns)
+    X[e.noi_indices] = 0.0
+    vs, isv = e.eval_sources(5e-11)
+    nu = e.n_unknowns
+    a = e.build_system(X, vs, isv, np.zeros(nu), 1e12, 1e-12, 0.0, -1e12, -1.0, None, 0.0, None, None, 1)
+    b = e.build_system(X, vs, isv, np.zeros(nu), 1e12, 1e-12, 0.0, -1e12, -1.0, None, 0.0, None, None, 1)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)  # bit-identical run to run
+    csr = a[0].copy()
+    # NOI rows/cols as the NR loop enforces them (solver_factories.py:1268-1276)
+    rows = np.repeat(np.arange(e.n_aug), np.diff(e.csr_indptr))
+    noi = np.zeros(e.n_aug, bool)
+    noi[e.noi_indices - 1] = True
+    csr[noi[rows] | ((rows < nu) & noi[e.csr_indices])] = 0.0
+    csr[noi[rows] & (rows == e.csr_indices)] = 1.0
+    A = sp.csr_matrix((csr, e.csr_indices, e.csr_indptr), shape=(e.n_aug, e.n_aug))
+    for k in range(2):
+        rhs = rng.normal(size=e.n_aug)
+        x = e.lu_solve(csr, rhs)
+        r = A @ x - rhs
+        assert np.max(np.abs(r)) <= 1e-9 * max(1.0, np.max(np.abs(rhs)), np.max(np.abs(A @ np.abs(x))))
+        assert np.array_equal(x, e.lu_solve(csr, rhs))  # deterministic
+    st = e.lu_stats()
+    assert st["n"] == e.n_aug and st["n_singletons"] + st["n_core"] == e.n_aug
+    assert st["n_singletons"] >= 2 * 10048  # NOI identity rows + branch flows + rails leave the core
+
+
+def test_c6288_graph_equals_host_loop_and_chunks(c6288, bundles):
+    from vajax_b200.analysis.engine import B200Engine
+
+    e = c6288
+    t1, V1, s1 = e.run_transient(max_steps=41)
+    assert s1["error_flags"] == 0 and s1["n_steps"] == 41
+    # chunked: same loop stopped and resumed every 7 attempts (checkpoint contract)
+    t2, V2, s2 = e.run_transient(max_steps=41, chunk_attempts=7)
+    assert s2["n_steps"] == 41 and np.array_equal(t1, t2) and np.array_equal(V1, V2)
+    h = B200Engine(circuits.multiplier_circuit(16), bundles, use_device_graph=False).prepare()
+    t3, V3, s3 = h.run_transient(max_steps=41)
+    h.close()
+    assert s3["total_nr_iterations"] == s1["total_nr_iterations"] and s3["rejected_steps"] == s1["rejected_steps"]
+    assert np.array_equal(t1, t3) and np.array_equal(V1, V3)
+    # physics sanity: rails hold, every recorded voltage is bounded by the rails (+ overshoot)
+    vdd = e.node_names["vdd"]
+    assert np.allclose(V1[1:41, vdd], 1.2, atol=1e-9)  # row 0 is the UIC state (all zeros)
+    assert np.all(np.isfinite(V1[:41])) and V1[:41].min() > -0.6 and V1[:41].max() < 1.8
+
+
+def test_mul4_settles_to_the_product(bundles):
+    """4x4 multiplier, operands 15 x 15 = 225: after the inputs have risen and the array has
+    settled, the product bits read 0b11100001."""
+    from vajax_b200.analysis.engine import B200Engine
+
+    circ = circuits.multiplier_circuit(4, stop=4e-9, step=2e-12)
+    e = B200Engine(circ, bundles, use_device_graph=True).prepare()
+    times, V, st = e.run_transient()
+    n = st["n_steps"]
+    assert st["error_flags"] == 0 and times[n - 1] >= 4e-9 * (1 - 1e-9)
+    names = e.node_names
+    bits = []
+    bits.append(V[n - 1, names["pp0_0"]])
+    bits.append(V[n - 1, names["s1_0"]])
+    bits.append(V[n - 1, names["s2_0"]])
+    bits.append(V[n - 1, names["s3_0"]])
+    for k in range(3):
+        bits.append(V[n - 1, names[f"p{4 + k}"]])
+    bits.append(V[n - 1, names["rc2"]])
+    got = sum((1 << i) for i, v in enumerate(bits) if v > 0.6)
+    assert all(v < 0.2 or v > 1.0 for v in bits), bits
+    assert got == 225, (got, bits)
+    e.close()

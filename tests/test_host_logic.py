@@ -1,0 +1,210 @@
+"""CPU-side tests of the product's host logic: the C-ABI library loads and exports every symbol
+declared in include/vajax_b200.h, refuses to run without a GPU (no CPU fallback), the symbolic LU
+analysis (C++) is correct on MNA-shaped matrices, the CUDA-C emitter produces compilable sources,
+and the corner tables / sharding mirror the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vajax_b200 import lib as vlib
+
+    vlib.build_library()
+    return vlib.load()
+
+
+def test_cabi_exports_every_declared_symbol(lib):
+    from vajax_b200 import lib as vlib
+
+    hdr = open(os.path.join(ROOT, "include", "vajax_b200.h")).read()
+    declared = set(re.findall(r"\b(vjx_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"vjx_handle", "vjx_stream"}
+    assert len(declared) >= 20
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(vlib.EXPORTS) <= declared | {"vjx_symbolic_probe"}, set(vlib.EXPORTS) - declared
+    assert lib.vjx_version() >= 100
+
+
+def test_no_cpu_fallback(lib, bundles):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vajax_b200 import lib as vlib
+    from vajax_b200.analysis.engine import B200Engine
+    from vajax_b200.benchmarks.circuits import rc_circuit
+
+    assert lib.vjx_device_count() == 0
+    desc = vlib.CircuitDesc()
+    h = C.c_void_p(None)
+    rc = lib.vjx_create(C.byref(desc), 0, C.byref(h))
+    assert rc != 0 and not h.value
+    with pytest.raises(vlib.VjxError):
+        B200Engine(rc_circuit(), bundles).prepare()
+
+
+def _probe(lib, A, b, tol=1e-3):
+    A = A.tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    ip = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    ix = np.ascontiguousarray(A.indices, dtype=np.int32)
+    dv = np.ascontiguousarray(A.data, dtype=np.float64)
+    x, st = np.zeros(n), np.zeros(12)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = lib.vjx_symbolic_probe(n, p(ip), p(ix), p(dv), tol, p(np.ascontiguousarray(b)), p(x), p(st))
+    keys = "nnz_lu flops lev_l lev_u max_row n resid scatter n_single n_core max_l_len".split()
+    return rc, x, dict(zip(keys, st))
+
+
+def _mna_like(n_nodes, n_vs, seed):
+    """Random conductance matrix + voltage-source incidence rows/cols (zero diagonal block)."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    for _ in range(3 * n_nodes):
+        a, b = rng.integers(0, n_nodes, 2)
+        g = rng.uniform(1e-4, 1e-2)
+        for r, c, v in ((a, a, g), (b, b, g), (a, b, -g), (b, a, -g)):
+            rows.append(r); cols.append(c); vals.append(v)
+    for i in range(n_nodes):
+        rows.append(i); cols.append(i); vals.append(1e-12)
+    vs_nodes = rng.choice(n_nodes, size=n_vs, replace=False)  # two sources on one node would be singular
+    for v in range(n_vs):
+        node = int(vs_nodes[v])
+        for r, c in ((node, n_nodes + v), (n_nodes + v, node)):
+            rows.append(r); cols.append(c); vals.append(1.0)
+    n = n_nodes + n_vs
+    return sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+
+
+@pytest.mark.parametrize("n_nodes,n_vs,seed", [(1, 1, 0), (3, 1, 1), (40, 3, 2), (400, 12, 3), (3000, 40, 4)])
+def test_symbolic_analysis_against_superlu(lib, n_nodes, n_vs, seed):
+    import scipy.sparse.linalg as spla
+
+    A = _mna_like(n_nodes, n_vs, seed)
+    b = np.random.default_rng(seed).normal(size=A.shape[0])
+    rc, x, st = _probe(lib, A, b)
+    assert rc == 0
+    xr = spla.splu(A.tocsc()).solve(b)
+    assert np.max(np.abs(x - xr)) <= 1e-9 * max(1.0, np.max(np.abs(xr)))
+    assert st["n_single"] + st["n_core"] == A.shape[0]
+    assert st["nnz_lu"] >= A.nnz and st["n"] == A.shape[0]
+
+
+def test_symbolic_peels_supply_rails(lib):
+    """A rail node pinned by a vsource and touched by every device must leave the core: the branch
+    row is a row singleton, the branch-current column a column singleton."""
+    import scipy.sparse as sp
+
+    n_int = 200
+    rows, cols, vals = [], [], []
+    rail, br = n_int, n_int + 1
+    for i in range(n_int):
+        j = (i + 1) % n_int
+        for r, c, v in ((i, i, 3e-3), (i, j, -1e-3), (j, i, -1e-3), (i, rail, -1e-3), (rail, i, -1e-3)):
+            rows.append(r); cols.append(c); vals.append(v)
+    rows += [rail, rail, br]; cols += [rail, br, rail]; vals += [0.2, 1.0, 1.0]
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(n_int + 2, n_int + 2))
+    b = np.arange(1.0, n_int + 3.0)
+    rc, x, st = _probe(lib, A, b)
+    assert rc == 0 and st["n_single"] >= 2 and st["n_core"] <= n_int
+    assert np.max(np.abs(A @ x - b)) < 1e-9 * np.max(np.abs(b))
+    assert st["max_l_len"] < 10  # the 200-long rail row never becomes an L row
+
+
+def test_symbolic_rejects_structurally_singular(lib):
+    import scipy.sparse as sp
+
+    A = sp.csr_matrix(np.array([[1.0, 2.0, 0.0], [0.0, 0.0, 0.0], [0.0, 3.0, 1.0]]))
+    A = sp.csr_matrix(([1.0, 2.0, 3.0, 1.0], ([0, 0, 2, 2], [0, 1, 1, 2])), shape=(3, 3))
+    rc, _, _ = _probe(lib, A, np.ones(3))
+    assert rc != 0
+
+
+@pytest.mark.parametrize("mt", ["resistor", "diode", "psp103"])
+def test_emitter_sources_compile(mt, bundles):
+    """MIR -> CUDA-C for init and eval; nvcc cross-compiles for sm_100a without a GPU."""
+    from vajax_b200.codegen import cuda_emitter as em
+
+    b = bundles[mt]
+    src, meta = em.emit_init_source(b)
+    assert "vjx_init_kernel" in src and meta["cache_size"] == len(b["init_mir_data"]["cache_mapping"])
+    so = em.compile_plugin(src, f"{mt}_init")
+    assert os.path.exists(so)
+    kinds = b["param_kinds"]
+    shared = [i for i, k in enumerate(kinds) if k not in ("voltage", "prev_state", "new_state", "enable_lim", "enable_integration")]
+    varying = [i for i, k in enumerate(kinds) if k == "voltage"]
+    lim = {i: (k, b["param_names"][i]) for i, k in enumerate(kinds) if k in ("prev_state", "new_state", "enable_lim", "enable_integration")}
+    nc = len(b["init_mir_data"]["cache_mapping"])
+    layout = em.compute_eval_layout(b, shared, varying, list(range(nc)), [], lim)
+    for use_lim in (False, True):
+        src, meta = em.emit_eval_source(b, layout, use_lim)
+        assert "vjx_eval_kernel" in src
+        assert meta["n_residuals"] == len(b["dae_data"]["residuals"]) and meta["n_jacobian"] == len(b["dae_data"]["jacobian"])
+        assert meta["flops_static"]["insts"] > 0
+    dll = C.CDLL(em.compile_plugin(src, f"{mt}_eval"))
+    assert dll.vjx_model_abi_version() == 1
+
+
+def test_emitter_rejects_loops(bundles):
+    import copy
+
+    from vajax_b200.mir.types import parse_function
+
+    b = copy.deepcopy(bundles["diode"])
+    mir = b["mir_data"]
+    # turn the first jmp into a back edge to block0
+    for ins in mir["instructions"]:
+        if ins["opcode"] == "jmp":
+            ins["destination"] = "block0"
+            mir["blocks"]["block0"]["predecessors"].append(ins["block"])
+            mir["blocks"][ins["block"]]["successors"] = ["block0"]
+            break
+    with pytest.raises(Exception):
+        parse_function("eval", mir, b["str_constants"]).topo_order()
+
+
+# ---- corners (reference: tests/test_corners.py:18-143; values corners.py:162-196) ------------
+def test_corner_tables_and_sweep():
+    from vajax_b200.analysis import corners as cz
+
+    ff, ss = cz.PROCESS_CORNERS["FF"], cz.PROCESS_CORNERS["SS"]
+    assert (ff.mobility_scale, ff.vth_shift, ff.tox_scale) == (1.15, -0.05, 0.95)
+    assert (ss.mobility_scale, ss.vth_shift, ss.tox_scale) == (0.85, 0.05, 1.05)
+    assert cz.TEMPERATURE_CORNERS == {"cold": 233.15, "room": 300.15, "hot": 398.15}
+    pvt = cz.create_pvt_corners()
+    assert len(pvt) == 27 and len({c.name for c in pvt}) == 27
+    assert pvt[0].name == "FF_m40C_V90pct"
+    sw = cz.sweep_corners(64)
+    assert len(sw) == 64 and len({c.name for c in sw}) == 64
+    mc = cz.monte_carlo_corners(8)
+    assert len(mc) == 8 and mc[0].process.mobility_scale != mc[1].process.mobility_scale
+    with pytest.raises(ValueError):
+        cz.create_standard_corners(["XX"])
+
+
+def test_apply_corner_is_pure_and_signed():
+    from vajax_b200.analysis import corners as cz
+    from vajax_b200.benchmarks.circuits import multiplier_circuit
+
+    circ = multiplier_circuit(2)
+    mos = next(d for d in circ["devices"] if d["model"] == "psp103")
+    vdd = next(d for d in circ["devices"] if d["name"] == "vdd")
+    kp0, vto0, dc0 = mos["params"]["kp"], mos["params"]["vto"], vdd["params"]["dc"]
+    c = cz.apply_corner(circ, cz.sweep_corners(64)[0])  # FF, 233.15 K, 0.9 vdd
+    m2 = next(d for d in c["devices"] if d["name"] == mos["name"])
+    v2 = next(d for d in c["devices"] if d["name"] == "vdd")
+    assert m2["params"]["kp"] == kp0 * 1.15 and m2["params"]["vto"] == vto0 - 0.05
+    assert v2["params"]["dc"] == dc0 * 0.9 and c["temperature_k"] == 233.15
+    assert mos["params"]["kp"] == kp0 and vdd["params"]["dc"] == dc0  # input untouched
+    assert cz.shard(10, 1, 4) == [1, 5, 9] and sum(len(cz.shard(64, r, 8)) for r in range(8)) == 64

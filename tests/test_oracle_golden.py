@@ -1,0 +1,91 @@
+"""Pins the oracle (oracle/engine.py) to the REFERENCE ITSELF: tests/golden/reference_*.npz hold
+outputs of the reference's own modules (CircuitEngine setup, make_mna_build_system_fn in COO/dense
+and CSR-direct mode, _make_nr_solver_common, FullMNAStrategy.run) executed in the build container
+on a NumPy stand-in for JAX (tests/golden/make_golden.py).  Bars: build_system outputs 1e-12
+relative (stamped Jacobian, north_star), transient same accepted-step sequence and 1e-9 on values.
+"""
+import numpy as np
+import pytest
+
+from golden_util import BS_CASES, BS_NAMES, CIRCUITS, bs_inputs, load, scaled_err, tag, tran_stats
+
+
+@pytest.fixture(scope="module")
+def oracle_cache(bundles):
+    from oracle.engine import OracleEngine
+
+    cache = {}
+
+    def get(name, limiting):
+        key = (name, limiting)
+        if key not in cache:
+            o = OracleEngine(CIRCUITS[name](), bundles, use_device_limiting=limiting)
+            o.setup()
+            cache[key] = o
+        return cache[key]
+
+    return get
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+@pytest.mark.parametrize("limiting", [False, True])
+def test_setup_sizes(name, limiting, oracle_cache):
+    g = load(name)
+    o = oracle_cache(name, limiting)
+    n_total, nu, n_vs, n_lim = g[tag(name, limiting) + "_sizes"]
+    assert (o.n_total, o.n_unknowns, o.n_vs, o.total_limit_states) == (n_total, nu, n_vs, n_lim)
+    assert o.nse == len(g[tag(name, limiting) + "_bs0_J"])
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+@pytest.mark.parametrize("limiting", [False, True])
+def test_build_system_csr_direct(name, limiting, oracle_cache):
+    """reference: _build_system_csr_direct (mna_builder.py:759-1010)"""
+    g = load(name)
+    o = oracle_cache(name, limiting)
+    t = tag(name, limiting)
+    X, vs, isv, Qp, dq, q2, ls = bs_inputs(g, t, o.n_vs)
+    for ci, (c0, c1, d1, c2, it) in enumerate(BS_CASES):
+        ro = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, ls, it)
+        for nm, a in zip(BS_NAMES, ro):
+            assert scaled_err(a, g[f"{t}_bs{ci}_{nm}"]) < 1e-12, (t, ci, nm)
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+def test_csr_pattern_against_dense_jacobian(name, oracle_cache):
+    """The reference's dense (COO) path gives J as a matrix: scattering the oracle's CSR values
+    through the oracle's (indptr, indices) must reproduce it, which pins the pattern discovery
+    (full_mna.py:423-513) and the slot maps (mna_builder.py:126-255)."""
+    g = load(name)
+    o = oracle_cache(name, False)
+    t = tag(name, False, sparse=False)
+    X, vs, isv, Qp, dq, q2, ls = bs_inputs(g, t, o.n_vs)
+    rows = np.repeat(np.arange(o.n_aug), np.diff(o.csr_indptr))
+    for ci, (c0, c1, d1, c2, it) in enumerate(BS_CASES):
+        csr = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, ls, it)[0]
+        dense = np.zeros((o.n_aug, o.n_aug))
+        dense[rows, o.csr_indices] = csr
+        Jd = g[f"{t}_bs{ci}_J"]
+        assert Jd.shape == dense.shape
+        assert scaled_err(dense, Jd) < 1e-12
+        assert np.all((Jd != 0) <= (dense != 0) | (np.abs(Jd) < 1e-300))
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+@pytest.mark.parametrize("limiting", [False, True])
+def test_transient_step_sequence_and_waveform(name, limiting, oracle_cache):
+    """reference: FullMNAStrategy.run + body_fn (full_mna.py:780-1196, 1840-2194), sparse solver
+    slot (UMFPACK FFI signature) filled with SuperLU in the generator."""
+    g = load(name)
+    o = oracle_cache(name, limiting)
+    t = tag(name, limiting)
+    times, V, st = o.run_transient()
+    ref_t, ref_V, ref_st = g[t + "_tran_times"], g[t + "_tran_V"], tran_stats(g, t)
+    n = st["n_steps"]
+    assert n == len(ref_t)
+    assert st["rejected_steps"] == int(ref_st["rejected_steps"])
+    assert st["total_nr_iterations"] == int(ref_st["total_nr_iterations"])
+    assert scaled_err(times[:n], ref_t, rel_floor=1e-30, abs_floor=1e-30) < 1e-9
+    span = max(float(np.max(ref_V) - np.min(ref_V)), 1e-12)
+    assert np.sqrt(np.mean((V[:n] - ref_V) ** 2)) / span < 1e-9
+    assert float(np.max(np.abs(V[:n] - ref_V))) < 1e-8 * max(1.0, float(np.max(np.abs(ref_V))))

@@ -1,0 +1,165 @@
+"""The reference's own known-answer tests for the hot path, restated against the oracle
+(SURVEY.md §8c), plus unit-level golden vectors computed by the reference's functions
+(tests/golden/reference_units.npz, see tests/golden/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN
+from oracle import engine as oe
+from oracle import mir_interp
+
+
+@pytest.fixture(scope="module")
+def units():
+    return np.load(os.path.join(GOLDEN, "reference_units.npz"))
+
+
+# ---- reference: tests/test_integration_methods.py:27-75 ------------------------------------
+def test_integration_coefficients_known_answers():
+    dt = 1e-12
+    be, tr, g2 = (oe.compute_coefficients(m, dt) for m in ("be", "trap", "gear2"))
+    assert (be["c0"], be["c1"], be["c2"], be["d1"]) == (1 / dt, -1 / dt, 0.0, 0.0)
+    assert (tr["c0"], tr["c1"], tr["c2"], tr["d1"]) == (2 / dt, -2 / dt, 0.0, -1.0)
+    assert np.allclose([g2["c0"], g2["c1"], g2["c2"], g2["d1"]], [1.5 / dt, -2 / dt, 0.5 / dt, 0.0], rtol=1e-15)
+    # error coefficients 1/2, 1/12, 2/9 (tests/test_adaptive_timestep.py:22-35)
+    assert (be["error_coeff"], tr["error_coeff"], g2["error_coeff"]) == (0.5, 1 / 12, 2 / 9)
+
+
+def test_integration_coefficients_golden(units):
+    for m in ("be", "trap", "gear2"):
+        c = oe.compute_coefficients(m, 1e-12)
+        ref = units[f"integ_{m}"]
+        assert np.array_equal([c["c0"], c["c1"], c["d1"], c["c2"], c["error_coeff"]], ref), m
+
+
+def test_variable_step_gear2_reduces_to_fixed_step():
+    c0, c1, d1, c2, ec = oe.step_coefficients("gear2", 1e-12, 1e-12)
+    assert np.allclose([c0, c1, c2, d1], [1.5e12, -2e12, 0.5e12, 0.0], rtol=1e-15) and ec == -2 / 9
+
+
+# ---- reference: tests/test_adaptive_timestep.py:49-148 -------------------------------------
+def test_predictor_known_answers():
+    dth = np.array([1e-9, 1e-9, 1e-9, 1e-9])
+    Vh = np.zeros((4, 1))
+    _, _, a = oe.predict_voltage(Vh, dth, 2, 1e-9, 2)
+    assert np.allclose(a, [2.0, -1.0, 0.0], atol=1e-14)
+    _, _, a = oe.predict_voltage(Vh, dth, 3, 1e-9, 2)
+    assert np.allclose(a, [3.0, -3.0, 1.0], atol=1e-12)
+    _, _, a = oe.predict_voltage(Vh, np.array([2e-9, 1e-9, 1e-9, 1e-9]), 3, 1e-9, 2)
+    assert abs(a.sum() - 1.0) < 1e-12
+    # quadratic 0,1,4 -> 9 and linear 1,2 -> 3 (most recent first)
+    Vp, _, _ = oe.predict_voltage(np.array([[4.0], [1.0], [0.0], [0.0]]), dth, 3, 1e-9, 2)
+    assert abs(Vp[0] - 9.0) < 1e-10
+    Vp, _, _ = oe.predict_voltage(np.array([[2.0], [1.0], [0.0], [0.0]]), dth, 2, 1e-9, 2)
+    assert abs(Vp[0] - 3.0) < 1e-12
+
+
+def test_predictor_golden(units):
+    for row in units["predict_cases"]:
+        hc, ndt = int(row[0]), row[1]
+        dth, Vh, Vp_ref, err_ref = row[2:6], row[6:30].reshape(4, 6), row[30:36], row[36]
+        Vp, err, _ = oe.predict_voltage(Vh, dth, hc, ndt, 2)
+        assert np.max(np.abs(Vp - Vp_ref)) <= 1e-13 * max(1.0, np.max(np.abs(Vp_ref)))
+        assert abs(err - err_ref) <= 1e-13 * max(1.0, abs(err_ref))
+
+
+# ---- reference: tests/test_adaptive_timestep.py:154-253 ------------------------------------
+def test_lte_rule_known_answers():
+    cfg = oe.AdaptiveConfig()
+    Vn, Vp = np.array([1.0]), np.array([1.0 + 1e-9])
+    dt_new, norm = oe.compute_lte_timestep(Vn, Vp, -1.0, 1e-9, 3, cfg, -0.5, None)
+    assert dt_new > 1e-9 and norm < 1  # tiny LTE -> step grows (capped by grow_factor)
+    assert dt_new <= 1e-9 * cfg.grow_factor * (1 + 1e-15)
+    Vp = np.array([1.5])
+    dt_new, norm = oe.compute_lte_timestep(Vn, Vp, -1.0, 1e-9, 3, cfg, -0.5, None)
+    assert dt_new < 1e-9 and norm > cfg.lte_ratio
+    # factor ei / (ei - ep)
+    lte = (Vn - Vp) * (-0.5 / (-0.5 - (-1.0)))
+    tol = cfg.reltol * 1.5 + cfg.abstol
+    assert abs(norm - abs(lte[0]) / tol) < 1e-12 * norm
+
+
+def test_lte_golden(units):
+    cfg = oe.AdaptiveConfig()
+    for row in units["lte_cases"]:
+        hc, ec, pe, dt = int(row[0]), row[1], row[2], row[3]
+        Vn, Vp, Vmax, dt_ref, norm_ref = row[4:10], row[10:16], row[16:22], row[22], row[23]
+        dt_new, norm = oe.compute_lte_timestep(Vn, Vp, pe, dt, hc, cfg, ec, Vmax)
+        assert abs(norm - norm_ref) <= 1e-13 * abs(norm_ref)
+        assert abs(dt_new - dt_ref) <= 1e-13 * abs(dt_ref)
+
+
+# ---- reference: vajax/analysis/limiting.py:22-107 ------------------------------------------
+def test_limiting_golden(units):
+    vn, vo = units["pnjlim_in"]
+    assert np.max(np.abs(mir_interp.pnjlim(vn, vo, 0.02585, 0.6145) - units["pnjlim_out"])) < 1e-14
+    assert np.max(np.abs(mir_interp.fetlim(vn, vo, 0.5) - units["fetlim_out"])) < 1e-14
+
+
+# ---- reference: vajax/analysis/sources.py:26-187 -------------------------------------------
+def test_sources_golden(units):
+    devs = json.loads(str(units["source_defs"]))
+    ts, ref = units["source_times"], units["source_values"]
+    for j, d in enumerate(devs):
+        fn = oe.make_source(d["params"])
+        got = np.array([fn(float(t)) for t in ts])
+        assert np.max(np.abs(got - ref[:, j])) <= 1e-12 * max(1.0, np.max(np.abs(ref[:, j]))), d["name"]
+
+
+# ---- the reference code generator's init functions vs the oracle's MIR interpreter ---------
+@pytest.mark.parametrize("mt", ["resistor", "capacitor", "diode", "psp103"])
+def test_model_init_golden(mt, units, bundles):
+    init_in = units[f"model_{mt}_init_in"]
+    n = init_in.shape[0]
+    cache, col = mir_interp.init_model(bundles[mt], [init_in[:, j] for j in range(init_in.shape[1])], n)
+    ref = units[f"model_{mt}_cache"]
+    assert cache.shape == ref.shape
+    if ref.size:
+        assert np.max(np.abs(cache - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-13
+    assert np.array_equal(col.astype(np.float64), units[f"model_{mt}_collapse"])
+
+
+# ---- reference: tests/test_fori_loop_nr.py:34-98 (resistive divider through nr_solve) -------
+def test_nr_resistive_divider(bundles):
+    from vajax_b200.benchmarks.circuits import _Net
+
+    n = _Net()
+    n.add("v1", "vsource", ["top", "0"], dict(dc=1.0, type="dc"), openvaf=False)
+    n.add("r1", "resistor", ["top", "mid"], dict(r=1e3))
+    n.add("r2", "resistor", ["mid", "0"], dict(r=1e3))
+    circ = n.circuit(dict(step=1e-6, stop=1e-5, icmode="op"))
+    o = oe.OracleEngine(circ, bundles)
+    o.setup()
+    X0 = np.zeros(o.n_total + o.n_vs)
+    X0[1:o.n_total] = 0.5
+    res = o.nr_solve(X0, np.array([1.0]), np.zeros(0), np.zeros(o.n_unknowns), 0.0, 1e-12)
+    X, iters, conv = res[0], res[1], res[2]
+    top, mid = circ["node_names"]["top"], circ["node_names"]["mid"]
+    assert conv and iters <= 3
+    # gmin = 1e-12 S on the node diagonals AND in the residual (mna_builder.py:969,1056) shifts the
+    # mid node by 0.5 * gmin * (R1 || R2) = 2.5e-10 V; the reference test's synthetic build_system
+    # has gmin in J only, hence its 1e-10
+    assert abs(X[mid] - 0.5) < 1e-9 and abs(X[top] - 1.0) < 1e-10 and X[0] == 0.0
+    assert abs(X[mid] - 0.5 / (1 + 1e-12 * 500.0)) < 1e-13
+    assert abs(abs(X[o.n_total]) - 0.5e-3) < 1e-10  # branch current 1 V / 2 kOhm
+
+
+# ---- reference: tests/test_vacask_benchmarks.py:187-218 (RC physics) -----------------------
+def test_rc_charging_curve(bundles):
+    from vajax_b200.benchmarks.circuits import rc_circuit
+
+    circ = rc_circuit(stop=1e-3)
+    o = oe.OracleEngine(circ, bundles)
+    times, V, st = o.run_transient()
+    n = st["n_steps"]
+    node = circ["node_names"]["2"]
+    t, v = times[:n], V[:n, node]
+    m = t > 2e-6  # after the 1 us input ramp: v = 1 - exp(-(t - 0.5us)/tau) to first order in rise/tau
+    expect = 1.0 - np.exp(-(t[m] - 0.5e-6) / 1e-3)
+    # the reference's own bar for rc is 5 % rel-RMS against VACASK; the oracle (bit-identical to the
+    # reference on this circuit, test_oracle_golden.py) tracks the analytic curve to 3e-5
+    assert np.max(np.abs(v[m] - expect)) < 1e-4
+    assert st["rejected_steps"] == 0

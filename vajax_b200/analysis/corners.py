@@ -233,3 +233,45 @@ def run_corners(circuit: dict, bundles: Dict[str, dict], corners: Sequence[Corne
         res.results.append(CornerResult(corner=corners[p["index"]], times=p["times"], voltages=p["voltages"], stats=st,
                                         converged=int(st.get("error_flags", 0)) == 0))
     return res
+
+
+def make_dist_gather(dst: int = 0):
+    """Gather callable for ``run_corners`` over ``torch.distributed`` (NCCL on the GPU box, gloo in
+    the CPU tests): waveforms travel as padded tensors through ``dist.gather`` (K13, SURVEY.md
+    §2.3), the small per-corner metadata through ``gather_object``.  Returns the full payload list
+    on rank ``dst`` and ``None`` elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    def gather(local: List[dict]):
+        rank, world = dist.get_rank(), dist.get_world_size()
+        backend = dist.get_backend()
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        meta = [dict(index=p["index"], n=int(len(p["times"])), n_ext=int(p["voltages"].shape[1]) if p["voltages"].ndim == 2 else 0,
+                     stats=p["stats"]) for p in local]
+        all_meta = [None] * world if rank == dst else None
+        dist.gather_object(meta, all_meta, dst=dst)
+        # common padded shape: (max corners per rank, max rows, 1 + n_ext)
+        shape = torch.tensor([len(local), max([m["n"] for m in meta] + [0]), max([m["n_ext"] for m in meta] + [0])],
+                             dtype=torch.int64, device=dev)
+        dist.all_reduce(shape, op=dist.ReduceOp.MAX)
+        nc, nr, ne = (int(v) for v in shape.tolist())
+        buf = torch.zeros((max(nc, 1), max(nr, 1), 1 + max(ne, 1)), dtype=torch.float64, device=dev)
+        for k, p in enumerate(local):
+            n = len(p["times"])
+            buf[k, :n, 0] = torch.from_numpy(np.ascontiguousarray(p["times"]))
+            if n and p["voltages"].size:
+                buf[k, :n, 1:1 + p["voltages"].shape[1]] = torch.from_numpy(np.ascontiguousarray(p["voltages"]))
+        bufs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+        dist.gather(buf, bufs, dst=dst)
+        if rank != dst:
+            return None
+        out = []
+        for r in range(world):
+            arr = bufs[r].cpu().numpy()
+            for k, m in enumerate(all_meta[r]):
+                out.append(dict(index=m["index"], times=arr[k, :m["n"], 0].copy(),
+                                voltages=arr[k, :m["n"], 1:1 + m["n_ext"]].copy(), stats=m["stats"]))
+        return out
+
+    return gather

@@ -83,6 +83,8 @@ struct LUDev {
   const int* order_u;
   const int* perm_r;
   const int* perm_c;
+  const int* order_f;          // all rows by level (factorisation); order_l / order_u hold the bulk rows
+  int tail_start;              // rows [tail_start, n): chain tail solved by one thread block
   const long long* upd_ptr;    // [nnz+1] start of each L entry's scatter list
   const int* upd_pos;          // position inside row i of each column of U(k,:)
   double* val;
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __res
     if (lane == 0) tk = atomicAdd(&st->ticket_f, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= (unsigned)n) break;
-    const int i = lu.order_l[tk];
+    const int i = lu.order_f[tk];
     const int rb = lu.ptr[i], dg = lu.diag[i], re = lu.ptr[i + 1];
     double d;
     if (dg == rb) {
@@ -493,18 +495,74 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Forward solve y = L^-1 P b: one warp per row, lanes stride over the row's L entries; every lane
-// loads its matrix entry first and then waits for exactly the y it needs.
+// Chain tails pass values through shared memory; an entry still holding this quiet-NaN payload has
+// not been produced yet (a computed NaN is the canonical 0x7ff8000000000000).
+#define VJX_TAIL_MAX 4096
+#define VJX_SENTINEL 0x7ff8dead0badbeefULL
+
+__device__ __forceinline__ double wait_smem(const double* slot, NRStat* st, int errbit) {
+  const volatile ull* p = reinterpret_cast<const volatile ull*>(slot);
+  unsigned spins = 0;
+  ull bits;
+  while ((bits = *p) == VJX_SENTINEL) {
+    if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); break; }
+  }
+  return __longlong_as_double((long long)bits);
+}
+
+// Forward solve y = L^-1 P b.  Rows outside the chain tail: one warp per row handed out by ticket in
+// level order, every lane loads its matrix entry first and then waits for exactly the y it needs.
+// Rows of the chain tail (the last levels, a few rows each, hundreds of levels deep): block 0 alone,
+// its warps taking the rows round-robin in level order and handing y over in shared memory.
 __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __restrict__ b, double scale,
                                                    const unsigned char* __restrict__ zero_mask, NRStat* st) {
+  __shared__ double ytail[VJX_TAIL_MAX];
   const unsigned epoch = st->epoch;
   const int lane = threadIdx.x & 31;
   const int n = lu.n;
+  const int n_bulk = lu.tail_start;
+  const int n_tail = n - lu.tail_start;
+  if (blockIdx.x == 0 && n_tail > 0) {
+    for (int t = threadIdx.x; t < n_tail; t += blockDim.x)
+      reinterpret_cast<ull*>(ytail)[t] = VJX_SENTINEL;
+    __syncthreads();
+    for (int t = threadIdx.x >> 5; t < n_tail; t += (blockDim.x >> 5)) {
+      const int i = n_bulk + t;
+      const int rb = lu.ptr[i], dg = lu.diag[i];
+      double bi = 0.0;
+      if (lane == 0) {
+        const int r = lu.perm_r[i];
+        bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
+      }
+      double part = 0.0;
+      for (int p = rb + lane; p < dg; p += 32) {
+        const int c = lu.col[p];
+        const double v = lu.val[p];
+        const int s = c - n_bulk;
+        double yc;
+        if (s >= 0) {
+          yc = wait_smem(ytail + s, st, 4);
+        } else {
+          wait_flag(lu.flag_l + c, epoch, st, 4);
+          yc = __ldcg(lu.y + c);
+        }
+        part += v * yc;
+      }
+      if (dg - rb > 1) part = warp_sum(part);
+      else part = __shfl_sync(0xffffffffu, part, 0);
+      if (lane == 0) {
+        const double yi = bi - part;
+        *reinterpret_cast<volatile double*>(ytail + t) = yi;
+        lu.y[i] = yi;
+      }
+    }
+    return;
+  }
   while (true) {
     unsigned tk = 0;
     if (lane == 0) tk = atomicAdd(&st->ticket_l, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= (unsigned)n) break;
+    if (tk >= (unsigned)n_bulk) break;
     const int i = lu.order_l[tk];
     const int rb = lu.ptr[i], dg = lu.diag[i];
     double bi = 0.0;
@@ -529,16 +587,54 @@ __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __res
   }
 }
 
-// Back solve x = U^-1 y, scattered through the column permutation.
+// Back solve x = U^-1 y, scattered through the column permutation.  Here the chain comes first
+// (the trailing block of U): block 0 walks it through shared memory and publishes every x for the
+// wide remainder, which the other blocks solve by ticket.
 __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict__ x_out, NRStat* st) {
+  __shared__ double xtail[VJX_TAIL_MAX];
   const unsigned epoch = st->epoch;
   const int lane = threadIdx.x & 31;
   const int n = lu.n;
+  const int n_bulk = lu.tail_start;
+  const int n_tail = n - lu.tail_start;
+  if (blockIdx.x == 0 && n_tail > 0) {
+    for (int t = threadIdx.x; t < n_tail; t += blockDim.x)
+      reinterpret_cast<ull*>(xtail)[t] = VJX_SENTINEL;
+    __syncthreads();
+    for (int t = threadIdx.x >> 5; t < n_tail; t += (blockDim.x >> 5)) {
+      const int i = n - 1 - t;
+      const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
+      double yi = 0.0, di = 0.0;
+      int pc = 0;
+      if (lane == 0) {
+        yi = lu.y[i];
+        di = lu.inv_diag[i];
+        pc = lu.perm_c[i];
+      }
+      double part = 0.0;
+      for (int p = ub + lane; p < re; p += 32) {
+        const int c = lu.col[p];
+        const double v = lu.val[p];
+        part += v * wait_smem(xtail + (n - 1 - c), st, 8);   // a tail row's U entries point into the tail
+      }
+      if (re - ub > 1) part = warp_sum(part);
+      else part = __shfl_sync(0xffffffffu, part, 0);
+      if (lane == 0) {
+        const double xi = (yi - part) * di;
+        *reinterpret_cast<volatile double*>(xtail + t) = xi;
+        lu.xp[i] = xi;
+        x_out[pc] = xi;
+        __threadfence();
+        st_release_u32(lu.flag_u + i, epoch);
+      }
+    }
+    return;
+  }
   while (true) {
     unsigned tk = 0;
     if (lane == 0) tk = atomicAdd(&st->ticket_u, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= (unsigned)n) break;
+    if (tk >= (unsigned)n_bulk) break;
     const int i = lu.order_u[tk];
     const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
     double yi = 0.0, di = 0.0;
@@ -1052,6 +1148,7 @@ struct vjx_handle {
   bool lu_ready = false;
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_order_l, lu_order_u, lu_perm_r, lu_perm_c;
+  DevBuf<int> lu_order_f;
   DevBuf<long long> lu_upd_ptr;
   DevBuf<int> lu_upd_pos;
   DevBuf<unsigned> lu_flags;
@@ -1565,6 +1662,9 @@ static int upload_symbolic(vjx_handle* h) {
   L.ptr = h->lu_ptr.p; L.col = h->lu_col.p; L.diag = h->lu_diag.p; L.src = h->lu_src.p;
   L.order_l = h->lu_order_l.p; L.order_u = h->lu_order_u.p; L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
   L.upd_ptr = h->lu_upd_ptr.p; L.upd_pos = h->lu_upd_pos.p;
+  CK(h->lu_order_f.upload(S.order_f));
+  L.order_f = h->lu_order_f.p;
+  L.tail_start = S.tail_start;
   L.val = h->lu_val.p; L.inv_diag = h->lu_inv.p; L.y = h->lu_y.p; L.xp = h->lu_xp.p;
   L.flag_f = h->lu_flags.p; L.flag_l = h->lu_flags.p + S.n; L.flag_u = h->lu_flags.p + 2 * (size_t)S.n;
   // persistent grids: every CTA must be resident (dependency waits), so size from occupancy
@@ -1577,6 +1677,8 @@ static int upload_symbolic(vjx_handle* h) {
   long long warps_needed = S.n;
   h->lu_grid_f = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * std::min(occ_f, 4), (warps_needed + 7) / 8));
   h->lu_grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * std::min(occ_s, 4), (warps_needed + 7) / 8));
+  // block 0 of the solve kernels is dedicated to the chain tail; the other blocks take the tickets
+  if (S.tail_start < S.n && h->lu_grid_s < 2) h->lu_grid_s = 2;
   h->lu_ready = true;
   return VJX_OK;
 }

@@ -450,6 +450,24 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
     if (S.level_u[a] != S.level_u[b]) return S.level_u[a] < S.level_u[b];
     return a > b;
   });
+  // --- chain tail (see vjx_symbolic.h)
+  {
+    const int kMaxPerLevel = 16, kMaxTail = 4096;
+    std::vector<int> cl(S.n_levels_l, 0);
+    for (int i = 0; i < n; ++i) cl[S.level_l[i]]++;
+    int lcut = S.n_levels_l;   // first level of the all-narrow suffix of levels
+    while (lcut > 1 && cl[lcut - 1] <= kMaxPerLevel) --lcut;
+    int i0 = n;
+    while (i0 > 0 && n - (i0 - 1) <= kMaxTail && S.level_l[i0 - 1] >= lcut) --i0;
+    if (n - i0 < 8) i0 = n;
+    S.tail_start = i0;
+    S.order_f = S.order_l;
+    std::vector<int> bl, bu;
+    for (int i : S.order_l) if (i < i0) bl.push_back(i);
+    for (int i : S.order_u) if (i < i0) bu.push_back(i);
+    S.order_l.swap(bl);
+    S.order_u.swap(bu);
+  }
   // --- flops and the scatter program
   double fl = 0.0;
   int64_t nupd = 0;
@@ -494,7 +512,7 @@ double vjx_symbolic_selfcheck(const VjxSymbolic& S, int n, const int* indptr, co
                               const double* values, const double* b, double* x_out) {
   std::vector<double> v((size_t)S.nnz_lu, 0.0), inv(n, 0.0), y(n, 0.0), xp(n, 0.0);
   for (int t = 0; t < n; ++t) {
-    const int i = S.order_l[t];
+    const int i = S.order_f[t];
     const int rb = S.lu_ptr[i], dg = S.lu_diag[i], re = S.lu_ptr[i + 1];
     double* w = v.data() + rb;
     for (int pp = rb; pp < re; ++pp) w[pp - rb] = S.lu_src[pp] >= 0 ? values[S.lu_src[pp]] : 0.0;
@@ -508,18 +526,21 @@ double vjx_symbolic_selfcheck(const VjxSymbolic& S, int n, const int* indptr, co
     }
     inv[i] = 1.0 / w[dg - rb];
   }
-  for (int t = 0; t < n; ++t) {
-    int i = S.order_l[t];
+  // bulk rows in level order, then the tail in index order (exactly the kernels' schedule)
+  auto lrow = [&](int i) {
     double acc = b[S.perm_r[i]];
     for (int pp = S.lu_ptr[i]; pp < S.lu_diag[i]; ++pp) acc -= v[pp] * y[S.lu_col[pp]];
     y[i] = acc;
-  }
-  for (int t = 0; t < n; ++t) {
-    int i = S.order_u[t];
+  };
+  for (int i : S.order_l) lrow(i);
+  for (int i = S.tail_start; i < n; ++i) lrow(i);
+  auto urow = [&](int i) {
     double acc = y[i];
     for (int pp = S.lu_diag[i] + 1; pp < S.lu_ptr[i + 1]; ++pp) acc -= v[pp] * xp[S.lu_col[pp]];
     xp[i] = acc * inv[i];
-  }
+  };
+  for (int i = n - 1; i >= S.tail_start; --i) urow(i);
+  for (int i : S.order_u) urow(i);
   std::vector<double> x(n);
   for (int j = 0; j < n; ++j) x[S.perm_c[j]] = xp[j];
   double rmax = 0.0;
@@ -552,7 +573,7 @@ extern "C" int vjx_symbolic_probe(int n, const int* indptr, const int* indices, 
     stats8[8] = S.n_singletons;
     stats8[9] = S.n_core;
     stats8[10] = S.max_l_len;
-    stats8[11] = 0.0;
+    stats8[11] = S.n - S.tail_start;
   }
   return 0;
 }

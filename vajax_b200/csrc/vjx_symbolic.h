@@ -25,8 +25,9 @@ struct VjxSymbolic {
   std::vector<int> lu_col;     // column indices, ascending per row
   std::vector<int> lu_diag;    // [n] position of the diagonal entry of row i
   std::vector<int> lu_src;     // per L+U entry: slot of A's CSR values, or -1 for fill
-  std::vector<int> order_l;    // rows sorted by L-dependency level (factor + forward solve order)
-  std::vector<int> order_u;    // rows sorted by U-dependency level (back solve order)
+  std::vector<int> order_f;    // all rows sorted by L-dependency level (factorisation order)
+  std::vector<int> order_l;    // bulk rows sorted by L-dependency level (forward solve)
+  std::vector<int> order_u;    // bulk rows sorted by U-dependency level (back solve)
   std::vector<int> level_l, level_u;
   int n_levels_l = 0, n_levels_u = 0, max_row_len = 0;
   // Scatter program of the numeric refactorisation (up-looking, k-sequential): row i is held in a
@@ -37,6 +38,13 @@ struct VjxSymbolic {
   std::vector<int64_t> upd_ptr;   // [nnz_lu+1]
   std::vector<int> upd_pos;       // [sum over L entries (i,k) of |U(k,:)|]
   int max_l_len = 0;              // longest L part of a row (sequential k-steps of one row)
+  // Dependency-chain tail.  The last rows of the elimination order form the near-dense trailing
+  // block of the factor: a chain of hundreds of sequentially dependent rows with a handful of rows
+  // per dependency level.  Rows [tail_start, n) are solved by ONE thread block that hands values
+  // over in shared memory (~0.2 us per link) instead of global flags (~3 us per link): in index
+  // order for L (after the bulk), in reverse index order for U (before the bulk).  order_l / order_u
+  // list the bulk rows [0, tail_start) only, sorted by dependency level.
+  int tail_start = 0;
   int n_singletons = 0;           // pivots peeled as row / column singletons (no fill, no updates)
   int n_core = 0;                 // unknowns left for AMD + Gilbert-Peierls
   double flops = 0.0;             // 2 * sum_k nnz(L(:,k)) * nnz(U(k,:)) + nnz(L)
