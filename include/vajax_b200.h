@@ -176,6 +176,9 @@ int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg, int* laun
 /* Device time in ms (CUDA events recorded on `stream` tightly around the loop launch) of the last
  * vjx_tran_run and the total since vjx_tran_begin. */
 int vjx_tran_run_ms(vjx_handle* h, double* last_ms, double* total_ms);
+/* Debug probe (not on the product path): per permuted row, completion time in ns since kernel start
+ * and dependency level of one LU phase (3 = refactorisation, 4 = forward solve, 5 = back solve). */
+int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* level_out, vjx_stream stream);
 /* Number of kernels launched by this handle since creation (for bench.py's gpu_launches). */
 long long vjx_launch_count(vjx_handle* h);
 

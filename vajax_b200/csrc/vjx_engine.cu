@@ -85,8 +85,11 @@ struct LUDev {
   const int* perm_c;
   const int* order_f;          // all rows by level (factorisation); order_l / order_u hold the bulk rows
   int tail_start;              // rows [tail_start, n): chain tail solved by one thread block
+  const int* long_u;           // rows with a very long U part: one thread block each (last blocks of the grid)
+  int n_long_u, n_bulk_u;      // order_u holds n_bulk_u rows
   const long long* upd_ptr;    // [nnz+1] start of each L entry's scatter list
   const int* upd_pos;          // position inside row i of each column of U(k,:)
+  unsigned long long* ts;      // optional per-row completion timestamps (globaltimer, debug probe)
   double* val;
   double* inv_diag;
   double* y;
@@ -96,15 +99,27 @@ struct LUDev {
   unsigned* flag_u;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+// Dependency flags are polled with a RELAXED gpu-scope load.  ld.acquire.gpu compiles to
+// LDG.STRONG.GPU + CCTL.IVALL on sm_100a, i.e. every poll wipes the SM's whole L1, and with hundreds
+// of warps spinning nothing static (row pointers, columns, scatter lists) ever stays cached.  The
+// ordering that matters is kept without it: the producer publishes with st.release.gpu (MEMBAR +
+// store), the consumer's data loads are issued only after the poll has returned the new epoch
+// (control dependency; the asm carries a memory clobber for the compiler) and they read through
+// ld.global.cg, which never hits a stale L1 line.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ double nan0(double v) { return (v != v) ? 0.0 : v; }
+__device__ __forceinline__ ull global_ns() {
+  ull t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void atomic_max_pos(ull* addr, double v) {
   atomicMax(addr, (ull)__double_as_longlong(v));
 }
@@ -409,14 +424,14 @@ __global__ void __launch_bounds__(256) k_residual(ResidualArgs a) {
 // Sparse LU: numeric refactorisation on the fixed pattern / pivot order, dependency driven.
 // One warp per row; rows are handed out through a ticket counter in dependency-level order, so
 // with every warp resident the smallest unfinished row can always make progress (no deadlock).
-// Cross-SM visibility: producers __threadfence() + st.release a per-row epoch flag; consumers
-// ld.acquire the flag and read finished rows with ld.cg (L2), never through L1.
+// Cross-SM visibility: producers st.release.gpu a per-row epoch flag; consumers poll it with a relaxed
+// gpu-scope load (see ld_relaxed_u32) and read finished rows with ld.cg (L2), never through L1.
 // ------------------------------------------------------------------------------------------
 #define VJX_SPIN_LIMIT (1u << 24)
 
 __device__ __forceinline__ bool wait_flag(const unsigned* f, unsigned epoch, NRStat* st, int errbit) {
   unsigned spins = 0;
-  while (ld_acquire_u32(f) != epoch) {
+  while (ld_relaxed_u32(f) != epoch) {
     if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); return false; }
     if (spins > 64) __nanosleep(20);
   }
@@ -425,12 +440,22 @@ __device__ __forceinline__ bool wait_flag(const unsigned* f, unsigned epoch, NRS
 
 // Numeric refactorisation, up-looking and k-sequential.  One warp per row, rows handed out in
 // dependency-level order.  The row lives in a shared-memory working vector w (rows longer than
-// VJX_ROWBUF work in place in global memory): for every L entry (i,k) in ascending k the warp waits
-// for row k, forms l = w[k] / U(k,k) and scatters w[pos] -= l * U(k,j) through the precomputed
-// position list, lanes striding over U(k,:).  Rounding is identical to the classic row update.
-// Everything static (k, row bounds, scatter base) is loaded before the wait, so once the awaited
-// row is published the critical path is: flag -> {1/U(k,k), U(k,:)} -> shared-memory update.
+// VJX_ROWBUF work in place in global memory): for every L entry (i,k) in ascending k the warp forms
+// l = w[k] / U(k,k) and scatters w[pos] -= l * U(k,j) through the precomputed position list, lanes
+// striding over U(k,:).  Rounding is identical to the classic row update.
+//
+// The k-steps can be taken in batches of VJX_KB (lane b waits for row k_b and fetches its pivot and
+// row bounds, the warp prefetches the U values and scatter positions of the whole batch into
+// registers, then the order-dependent shared-memory updates run back to back).  Measured on B200
+// (gpurun_out/r1_kb_exp2.txt, profiles/r1_lu_notes.md): the unrolled batch code is ~1k straight-line
+// instructions per batch, and a lone warp resuming from a dependency wait executes it at
+// instruction-fetch latency (7-10 us per batch instead of 2 us when hot), so the dependency chain
+// gets SLOWER in proportion to VJX_KB (1.5 / 5.5 / 11.5 us per chain row for 1 / 4 / 8).  The default
+// therefore stays at 1 (compact code) until the chain tail moves to a dense shared-memory block.
 #define VJX_ROWBUF 640
+#ifndef VJX_KB
+#define VJX_KB 1
+#endif
 __global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __restrict__ csr, NRStat* st) {
   __shared__ double wbuf[8][VJX_ROWBUF];
   const unsigned epoch = st->epoch;
@@ -460,18 +485,61 @@ __global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __res
         w[p - rb] = s >= 0 ? csr[s] : 0.0;
       }
       __syncwarp();
-      for (int p = rb; p < dg; ++p) {
-        const int k = lu.col[p];
-        const int ub = lu.diag[k] + 1, ue = lu.ptr[k + 1];
-        const long long mb = lu.upd_ptr[p];
-        int t0 = 0;
-        if (ub + lane < ue) t0 = lu.upd_pos[mb + lane];
-        wait_flag(lu.flag_f + k, epoch, st, 1);
-        const double l = w[p - rb] * __ldcg(lu.inv_diag + k);
-        if (ub + lane < ue) w[t0] -= l * __ldcg(lu.val + ub + lane);
-        for (int q = ub + lane + 32; q < ue; q += 32) w[lu.upd_pos[mb + (q - ub)]] -= l * __ldcg(lu.val + q);
+#ifdef VJX_DEBUG_TS
+      int dbg_slot = 0;
+      const bool dbg = lu.ts && i == n - 1;
+      if (dbg && lane == 0) lu.ts[n + 2 + dbg_slot++] = global_ns();
+#endif
+      for (int pb = rb; pb < dg; pb += VJX_KB) {
+        const int nb = min(VJX_KB, dg - pb);
+        // lane b owns step b of the batch: wait for its row, fetch pivot + bounds + scatter base
+        int ub_l = 0, ue_l = 0;
+        long long mb_l = 0;
+        double inv_l = 0.0;
+        if (lane < nb) {
+          const int k = lu.col[pb + lane];
+          mb_l = lu.upd_ptr[pb + lane];
+          ub_l = lu.diag[k] + 1;
+          ue_l = lu.ptr[k + 1];
+          wait_flag(lu.flag_f + k, epoch, st, 1);
+          inv_l = __ldcg(lu.inv_diag + k);
+        }
         __syncwarp();
-        if (lane == 0) w[p - rb] = l;
+#ifdef VJX_DEBUG_TS
+        if (dbg && lane == 0 && dbg_slot < 4000) lu.ts[n + 2 + dbg_slot++] = global_ns();
+#endif
+        double u0[VJX_KB], u1[VJX_KB];
+        int t0[VJX_KB], t1[VJX_KB];
+#pragma unroll
+        for (int b = 0; b < VJX_KB; ++b) {
+          const int ub = __shfl_sync(0xffffffffu, ub_l, b), ue = __shfl_sync(0xffffffffu, ue_l, b);
+          const long long mb = __shfl_sync(0xffffffffu, mb_l, b);
+          u0[b] = 0.0; u1[b] = 0.0; t0[b] = -1; t1[b] = -1;
+          if (b < nb) {
+            if (ub + lane < ue) { u0[b] = __ldcg(lu.val + ub + lane); t0[b] = lu.upd_pos[mb + lane]; }
+            if (ub + lane + 32 < ue) { u1[b] = __ldcg(lu.val + ub + lane + 32); t1[b] = lu.upd_pos[mb + lane + 32]; }
+          }
+        }
+#ifdef VJX_DEBUG_TS
+        if (dbg && lane == 0 && dbg_slot < 4000) lu.ts[n + 2 + dbg_slot++] = global_ns() + (u0[0] != 1.2345e300 ? 0 : 1) + (u0[VJX_KB - 1] != 1.2345e300 ? 0 : 1);
+#endif
+#pragma unroll
+        for (int b = 0; b < VJX_KB; ++b) {
+          if (b < nb) {
+            const int ub = __shfl_sync(0xffffffffu, ub_l, b), ue = __shfl_sync(0xffffffffu, ue_l, b);
+            const long long mb = __shfl_sync(0xffffffffu, mb_l, b);
+            const double l = w[pb + b - rb] * __shfl_sync(0xffffffffu, inv_l, b);
+            if (t0[b] >= 0) w[t0[b]] -= l * u0[b];
+            if (t1[b] >= 0) w[t1[b]] -= l * u1[b];
+            for (int q = ub + lane + 64; q < ue; q += 32) w[lu.upd_pos[mb + (q - ub)]] -= l * __ldcg(lu.val + q);
+            __syncwarp();
+            if (lane == 0) w[pb + b - rb] = l;
+            __syncwarp();
+          }
+        }
+#ifdef VJX_DEBUG_TS
+        if (dbg && lane == 0 && dbg_slot < 4000) lu.ts[n + 2 + dbg_slot++] = global_ns();
+#endif
       }
       __syncwarp();
       if (in_smem)
@@ -482,8 +550,8 @@ __global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __res
     if (lane == 0) {
       if (d == 0.0 || d != d) atomicOr(&st->error, 2);
       lu.inv_diag[i] = 1.0 / d;
-      __threadfence();
       st_release_u32(lu.flag_f + i, epoch);
+      if (lu.ts) lu.ts[i] = global_ns();
     }
     __syncwarp();
   }
@@ -510,10 +578,32 @@ __device__ __forceinline__ double wait_smem(const double* slot, NRStat* st, int 
   return __longlong_as_double((long long)bits);
 }
 
+// Dot product of one row part with already solved unknowns.  Four (column, value) pairs are loaded
+// before the first dependency wait so that the matrix loads overlap the waits; the per-lane
+// summation order (ascending position, stride 32 or `stride`) does not depend on the unrolling.
+template <int STRIDE, typename WaitLoad>
+__device__ __forceinline__ double row_dot(const LUDev& lu, int first, int end, WaitLoad wl) {
+  double part = 0.0;
+  for (int p0 = first; p0 < end; p0 += 4 * STRIDE) {
+    int c[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * STRIDE;
+      c[u] = p < end ? lu.col[p] : -1;
+      v[u] = p < end ? lu.val[p] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c[u] >= 0) part += v[u] * wl(c[u]);
+  }
+  return part;
+}
+
 // Forward solve y = L^-1 P b.  Rows outside the chain tail: one warp per row handed out by ticket in
-// level order, every lane loads its matrix entry first and then waits for exactly the y it needs.
-// Rows of the chain tail (the last levels, a few rows each, hundreds of levels deep): block 0 alone,
-// its warps taking the rows round-robin in level order and handing y over in shared memory.
+// level order, every lane loads its matrix entries first and then waits for exactly the y it needs.
+// Rows of the chain tail [tail_start, n): block 0 alone, its warps taking the rows round-robin in
+// index order and handing y over in shared memory.
 __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __restrict__ b, double scale,
                                                    const unsigned char* __restrict__ zero_mask, NRStat* st) {
   __shared__ double ytail[VJX_TAIL_MAX];
@@ -534,26 +624,19 @@ __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __res
         const int r = lu.perm_r[i];
         bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
       }
-      double part = 0.0;
-      for (int p = rb + lane; p < dg; p += 32) {
-        const int c = lu.col[p];
-        const double v = lu.val[p];
+      double part = row_dot<32>(lu, rb + lane, dg, [&](int c) {
         const int s = c - n_bulk;
-        double yc;
-        if (s >= 0) {
-          yc = wait_smem(ytail + s, st, 4);
-        } else {
-          wait_flag(lu.flag_l + c, epoch, st, 4);
-          yc = __ldcg(lu.y + c);
-        }
-        part += v * yc;
-      }
+        if (s >= 0) return wait_smem(ytail + s, st, 4);
+        wait_flag(lu.flag_l + c, epoch, st, 4);
+        return __ldcg(lu.y + c);
+      });
       if (dg - rb > 1) part = warp_sum(part);
       else part = __shfl_sync(0xffffffffu, part, 0);
       if (lane == 0) {
         const double yi = bi - part;
         *reinterpret_cast<volatile double*>(ytail + t) = yi;
         lu.y[i] = yi;
+        if (lu.ts) lu.ts[i] = global_ns();
       }
     }
     return;
@@ -570,32 +653,29 @@ __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __res
       const int r = lu.perm_r[i];
       bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
     }
-    double part = 0.0;
-    for (int p = rb + lane; p < dg; p += 32) {
-      const int c = lu.col[p];
-      const double v = lu.val[p];
+    double part = row_dot<32>(lu, rb + lane, dg, [&](int c) {
       wait_flag(lu.flag_l + c, epoch, st, 4);
-      part += v * __ldcg(lu.y + c);
-    }
+      return __ldcg(lu.y + c);
+    });
     if (dg - rb > 1) part = warp_sum(part);
     else part = __shfl_sync(0xffffffffu, part, 0);
     if (lane == 0) {
       lu.y[i] = bi - part;
-      __threadfence();
       st_release_u32(lu.flag_l + i, epoch);
+      if (lu.ts) lu.ts[i] = global_ns();
     }
   }
 }
 
 // Back solve x = U^-1 y, scattered through the column permutation.  Here the chain comes first
 // (the trailing block of U): block 0 walks it through shared memory and publishes every x for the
-// wide remainder, which the other blocks solve by ticket.
+// wide remainder, which the other blocks solve by ticket.  The last n_long_u blocks each take one
+// very long row (a rail kept as column-singleton pivot: one entry per attached device).
 __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict__ x_out, NRStat* st) {
   __shared__ double xtail[VJX_TAIL_MAX];
   const unsigned epoch = st->epoch;
   const int lane = threadIdx.x & 31;
   const int n = lu.n;
-  const int n_bulk = lu.tail_start;
   const int n_tail = n - lu.tail_start;
   if (blockIdx.x == 0 && n_tail > 0) {
     for (int t = threadIdx.x; t < n_tail; t += blockDim.x)
@@ -611,12 +691,8 @@ __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict_
         di = lu.inv_diag[i];
         pc = lu.perm_c[i];
       }
-      double part = 0.0;
-      for (int p = ub + lane; p < re; p += 32) {
-        const int c = lu.col[p];
-        const double v = lu.val[p];
-        part += v * wait_smem(xtail + (n - 1 - c), st, 8);   // a tail row's U entries point into the tail
-      }
+      // a tail row's U entries point into the tail
+      double part = row_dot<32>(lu, ub + lane, re, [&](int c) { return wait_smem(xtail + (n - 1 - c), st, 8); });
       if (re - ub > 1) part = warp_sum(part);
       else part = __shfl_sync(0xffffffffu, part, 0);
       if (lane == 0) {
@@ -624,9 +700,27 @@ __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict_
         *reinterpret_cast<volatile double*>(xtail + t) = xi;
         lu.xp[i] = xi;
         x_out[pc] = xi;
-        __threadfence();
         st_release_u32(lu.flag_u + i, epoch);
+        if (lu.ts) lu.ts[i] = global_ns();
       }
+    }
+    return;
+  }
+  if ((int)blockIdx.x >= (int)gridDim.x - lu.n_long_u) {
+    double* sh = xtail;
+    const int i = lu.long_u[blockIdx.x - (gridDim.x - lu.n_long_u)];
+    const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
+    double part = row_dot<256>(lu, ub + threadIdx.x, re, [&](int c) {
+      wait_flag(lu.flag_u + c, epoch, st, 8);
+      return __ldcg(lu.xp + c);
+    });
+    part = block_sum_256(part, sh);
+    if (threadIdx.x == 0) {
+      const double xi = (lu.y[i] - part) * lu.inv_diag[i];
+      lu.xp[i] = xi;
+      x_out[lu.perm_c[i]] = xi;
+      st_release_u32(lu.flag_u + i, epoch);
+      if (lu.ts) lu.ts[i] = global_ns();
     }
     return;
   }
@@ -634,7 +728,7 @@ __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict_
     unsigned tk = 0;
     if (lane == 0) tk = atomicAdd(&st->ticket_u, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= (unsigned)n_bulk) break;
+    if (tk >= (unsigned)lu.n_bulk_u) break;
     const int i = lu.order_u[tk];
     const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
     double yi = 0.0, di = 0.0;
@@ -644,21 +738,18 @@ __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict_
       di = lu.inv_diag[i];
       pc = lu.perm_c[i];
     }
-    double part = 0.0;
-    for (int p = ub + lane; p < re; p += 32) {
-      const int c = lu.col[p];
-      const double v = lu.val[p];
+    double part = row_dot<32>(lu, ub + lane, re, [&](int c) {
       wait_flag(lu.flag_u + c, epoch, st, 8);
-      part += v * __ldcg(lu.xp + c);
-    }
+      return __ldcg(lu.xp + c);
+    });
     if (re - ub > 1) part = warp_sum(part);
     else part = __shfl_sync(0xffffffffu, part, 0);
     if (lane == 0) {
       const double xi = (yi - part) * di;
       lu.xp[i] = xi;
       x_out[pc] = xi;
-      __threadfence();
       st_release_u32(lu.flag_u + i, epoch);
+      if (lu.ts) lu.ts[i] = global_ns();
     }
   }
 }
@@ -1148,7 +1239,8 @@ struct vjx_handle {
   bool lu_ready = false;
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_order_l, lu_order_u, lu_perm_r, lu_perm_c;
-  DevBuf<int> lu_order_f;
+  DevBuf<int> lu_order_f, lu_long_u;
+  int lu_grid_u = 0;
   DevBuf<long long> lu_upd_ptr;
   DevBuf<int> lu_upd_pos;
   DevBuf<unsigned> lu_flags;
@@ -1604,7 +1696,7 @@ static void launch_lu(vjx_handle* h, const double* csr, const double* b, double 
                       double* x, cudaStream_t s) {
   k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, csr, h->st.p);
   k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, b, scale, zero_mask, h->st.p);
-  k_lu_usolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, x, h->st.p);
+  k_lu_usolve<<<h->lu_grid_u, 256, 0, s>>>(h->lud, x, h->st.p);
   h->launches += 3;
 }
 
@@ -1661,10 +1753,19 @@ static int upload_symbolic(vjx_handle* h) {
   L.n = S.n;
   L.ptr = h->lu_ptr.p; L.col = h->lu_col.p; L.diag = h->lu_diag.p; L.src = h->lu_src.p;
   L.order_l = h->lu_order_l.p; L.order_u = h->lu_order_u.p; L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
+  L.ts = nullptr;
   L.upd_ptr = h->lu_upd_ptr.p; L.upd_pos = h->lu_upd_pos.p;
   CK(h->lu_order_f.upload(S.order_f));
   L.order_f = h->lu_order_f.p;
   L.tail_start = S.tail_start;
+  {
+    std::vector<int> lg(S.long_u);
+    if (lg.empty()) lg.push_back(0);
+    CK(h->lu_long_u.upload(lg));
+  }
+  L.long_u = h->lu_long_u.p;
+  L.n_long_u = (int)S.long_u.size();
+  L.n_bulk_u = (int)S.order_u.size();
   L.val = h->lu_val.p; L.inv_diag = h->lu_inv.p; L.y = h->lu_y.p; L.xp = h->lu_xp.p;
   L.flag_f = h->lu_flags.p; L.flag_l = h->lu_flags.p + S.n; L.flag_u = h->lu_flags.p + 2 * (size_t)S.n;
   // persistent grids: every CTA must be resident (dependency waits), so size from occupancy
@@ -1679,6 +1780,7 @@ static int upload_symbolic(vjx_handle* h) {
   h->lu_grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * std::min(occ_s, 4), (warps_needed + 7) / 8));
   // block 0 of the solve kernels is dedicated to the chain tail; the other blocks take the tickets
   if (S.tail_start < S.n && h->lu_grid_s < 2) h->lu_grid_s = 2;
+  h->lu_grid_u = h->lu_grid_s + (int)S.long_u.size();
   h->lu_ready = true;
   return VJX_OK;
 }
@@ -2165,6 +2267,49 @@ extern "C" int vjx_tran_run_ms(vjx_handle* h, double* last_ms, double* total_ms)
   return VJX_OK;
 }
 
+__global__ void k_stamp_now(ull* out) { *out = global_ns(); }
+
+// Debug probe: run one LU phase (3 = factor, 4 = forward solve, 5 = back solve) on the handle's
+// current state and return, per permuted row, the completion time in ns since the kernel started,
+// together with the row's dependency level.  Used by scripts/lu_timeline.py to see where a
+// dependency chain spends its time; never called by the product path.
+extern "C" int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* level_out, vjx_stream stream) {
+  if (!h || !h->X.p || !h->lu_ready) return fail(VJX_ERR_INVALID, "run a transient first");
+  if (phase < 3 || phase > 5) return fail(VJX_ERR_INVALID, "phase must be 3, 4 or 5");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = h->sym.n;
+  DevBuf<ull> ts;
+  CK(ts.alloc((size_t)n + 1 + 4100));
+  LUDev lud = h->lud;
+  k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
+  if (phase >= 4) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p);
+  if (phase >= 5) k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+  lud.ts = ts.p;
+  k_stamp_now<<<1, 1, 0, s>>>(ts.p + n);
+  if (phase == 3) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(lud, h->csr.p, h->st.p);
+  if (phase == 4) k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+  if (phase == 5) k_lu_usolve<<<h->lu_grid_u, 256, 0, s>>>(lud, h->delta.p, h->st.p);
+  std::vector<ull> hts((size_t)n + 1);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+#ifdef VJX_DEBUG_TS
+  if (phase == 3) {
+    std::vector<ull> dbg(4100);
+    CK(cudaMemcpy(dbg.data(), ts.p + n + 1, sizeof(ull) * 4100, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "last-row batch trace (us since kernel start): start, then per batch [flags, loaded, applied]\n");
+    for (int k = 1; k < 4000 && dbg[k]; ++k)
+      fprintf(stderr, "%s%.2f", ((k - 2) % 3 == 0 && k > 1) ? "\n  " : " ", ((long long)dbg[k] - (long long)hts[n]) / 1e3);
+    fprintf(stderr, "\n");
+  }
+#endif
+  for (int i = 0; i < n; ++i) {
+    ns_out[i] = (double)((long long)hts[i] - (long long)hts[n]);
+    if (level_out) level_out[i] = phase == 5 ? h->sym.level_u[i] : h->sym.level_l[i];
+  }
+  return check_device_error(h, s);
+}
+
 extern "C" long long vjx_launch_count(vjx_handle* h) { return h ? h->launches : 0; }
 
 // Phase timing probe on the transient working state (Xw etc.), CUDA events on the launch stream.
@@ -2196,7 +2341,7 @@ extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg
       case 2: launch_residual(h, b, 0, s); break;
       case 3: k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p); h->launches++; break;
       case 4: k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p); h->launches++; break;
-      case 5: k_lu_usolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->delta.p, h->st.p); h->launches++; break;
+      case 5: k_lu_usolve<<<h->lu_grid_u, 256, 0, s>>>(h->lud, h->delta.p, h->st.p); h->launches++; break;
       case 6: k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua); h->launches++; break;
       default: return fail(VJX_ERR_INVALID, "unknown phase");
     }

@@ -464,7 +464,12 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
     S.order_f = S.order_l;
     std::vector<int> bl, bu;
     for (int i : S.order_l) if (i < i0) bl.push_back(i);
-    for (int i : S.order_u) if (i < i0) bu.push_back(i);
+    const int kLongRow = 1024;
+    for (int i : S.order_u) {
+      if (i >= i0) continue;
+      if (S.lu_ptr[i + 1] - S.lu_diag[i] - 1 > kLongRow) S.long_u.push_back(i);
+      else bu.push_back(i);
+    }
     S.order_l.swap(bl);
     S.order_u.swap(bu);
   }
@@ -526,21 +531,27 @@ double vjx_symbolic_selfcheck(const VjxSymbolic& S, int n, const int* indptr, co
     }
     inv[i] = 1.0 / w[dg - rb];
   }
-  // bulk rows in level order, then the tail in index order (exactly the kernels' schedule)
-  auto lrow = [&](int i) {
+  // any topological order gives the same per-row arithmetic: ascending rows for L, descending for U
+  for (int i = 0; i < n; ++i) {
     double acc = b[S.perm_r[i]];
     for (int pp = S.lu_ptr[i]; pp < S.lu_diag[i]; ++pp) acc -= v[pp] * y[S.lu_col[pp]];
     y[i] = acc;
-  };
-  for (int i : S.order_l) lrow(i);
-  for (int i = S.tail_start; i < n; ++i) lrow(i);
-  auto urow = [&](int i) {
+  }
+  for (int i = n - 1; i >= 0; --i) {
     double acc = y[i];
     for (int pp = S.lu_diag[i] + 1; pp < S.lu_ptr[i + 1]; ++pp) acc -= v[pp] * xp[S.lu_col[pp]];
     xp[i] = acc * inv[i];
-  };
-  for (int i = n - 1; i >= S.tail_start; --i) urow(i);
-  for (int i : S.order_u) urow(i);
+  }
+  {
+    // the schedule tables must cover every row exactly once
+    std::vector<char> seen_l(n, 0), seen_u(n, 0);
+    for (int i : S.order_l) seen_l[i]++;
+    for (int i : S.order_u) seen_u[i]++;
+    for (int i : S.long_u) seen_u[i]++;
+    for (int i = S.tail_start; i < n; ++i) { seen_l[i]++; seen_u[i]++; }
+    for (int i = 0; i < n; ++i)
+      if (seen_l[i] != 1 || seen_u[i] != 1) return 1e300;
+  }
   std::vector<double> x(n);
   for (int j = 0; j < n; ++j) x[S.perm_c[j]] = xp[j];
   double rmax = 0.0;

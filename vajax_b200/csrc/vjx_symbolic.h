@@ -45,6 +45,9 @@ struct VjxSymbolic {
   // order for L (after the bulk), in reverse index order for U (before the bulk).  order_l / order_u
   // list the bulk rows [0, tail_start) only, sorted by dependency level.
   int tail_start = 0;
+  // Rows whose U part is longer than kLongRow (a rail row kept as a column-singleton pivot has one
+  // entry per attached device) are left out of order_u and solved by a whole thread block each.
+  std::vector<int> long_u;
   int n_singletons = 0;           // pivots peeled as row / column singletons (no fill, no updates)
   int n_core = 0;                 // unknowns left for AMD + Gilbert-Peierls
   double flops = 0.0;             // 2 * sum_k nnz(L(:,k)) * nnz(U(k,:)) + nnz(L)

@@ -15,7 +15,7 @@ import subprocess
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvajax_b200.so")
+LIB_PATH = os.environ.get("VJX_LIB_PATH") or os.path.join(HERE, "libvajax_b200.so")  # override: kernel experiments
 CSRC = os.path.join(HERE, "csrc")
 
 NVCC_CMD = [
@@ -99,7 +99,7 @@ EXPORTS = [
     "vjx_last_error", "vjx_version", "vjx_device_count", "vjx_create", "vjx_destroy", "vjx_clear_cache",
     "vjx_update_model_data", "vjx_update_sources", "vjx_build_system", "vjx_lu_solve", "vjx_lu_analyze",
     "vjx_lu_stats", "vjx_nr_solve", "vjx_tran_begin", "vjx_tran_run", "vjx_tran_scalars", "vjx_tran_read",
-    "vjx_tran_set_step_limit", "vjx_tran_run_ms", "vjx_tran_records", "vjx_tran_state", "vjx_time_phase", "vjx_launch_count",
+    "vjx_tran_set_step_limit", "vjx_tran_run_ms", "vjx_tran_records", "vjx_tran_state", "vjx_time_phase", "vjx_lu_timeline", "vjx_launch_count",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -145,6 +145,7 @@ def load() -> C.CDLL:
     lib.vjx_tran_records.argtypes = [p, i, i, p, p]
     lib.vjx_tran_state.argtypes = [p, p, p, p, p]
     lib.vjx_time_phase.argtypes = [p, i, i, C.POINTER(C.c_double), C.POINTER(C.c_int), p]
+    lib.vjx_lu_timeline.argtypes = [p, i, p, p, p]
     lib.vjx_update_model_data.argtypes = [p, i, p, p, p, p]
     lib.vjx_update_sources.argtypes = [p, C.POINTER(SourceDesc), C.POINTER(SourceDesc)]
     lib.vjx_symbolic_probe.argtypes = [i, p, p, p, d, p, p, p]
