@@ -566,6 +566,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Chain tails pass values through shared memory; an entry still holding this quiet-NaN payload has
 // not been produced yet (a computed NaN is the canonical 0x7ff8000000000000).
 #define VJX_TAIL_MAX 4096
+// The triangular-solve kernels run 1024-thread blocks: the chain tail is walked by ONE block whose
+// warps take the tail rows round-robin, and a row costs a warp ~10 us of (mostly latency) time, so
+// the tail advances at (row time) / (warps per block) per row - 32 warps instead of 8 is a 4x.
+#define VJX_SOLVE_THREADS 1024
+#ifndef VJX_SMEM_SLEEP
+#define VJX_SMEM_SLEEP 0
+#endif
 #define VJX_SENTINEL 0x7ff8dead0badbeefULL
 
 __device__ __forceinline__ double wait_smem(const double* slot, NRStat* st, int errbit) {
@@ -574,28 +581,46 @@ __device__ __forceinline__ double wait_smem(const double* slot, NRStat* st, int 
   ull bits;
   while ((bits = *p) == VJX_SENTINEL) {
     if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); break; }
+#if VJX_SMEM_SLEEP > 0
+    __nanosleep(VJX_SMEM_SLEEP);   // leave the issue slots to the warp that is producing the value
+#endif
   }
   return __longlong_as_double((long long)bits);
 }
 
-// Dot product of one row part with already solved unknowns.  Four (column, value) pairs are loaded
-// before the first dependency wait so that the matrix loads overlap the waits; the per-lane
-// summation order (ascending position, stride 32 or `stride`) does not depend on the unrolling.
-template <int STRIDE, typename WaitLoad>
-__device__ __forceinline__ double row_dot(const LUDev& lu, int first, int end, WaitLoad wl) {
+// Dot product of one row part with already solved unknowns.  `tid` is the thread's index among the
+// STRIDE threads that share the row (lane for a warp, threadIdx.x for a whole block).  Four
+// (column, value) pairs are loaded before the first dependency wait so that the matrix loads overlap
+// the waits.  The waits are CONVERGENT: all lanes of a warp poll together until every lane's
+// dependency of the current slot has arrived.  Letting each lane spin on its own (lanes parked in
+// different unrolled spin loops) costs ~3,000 cycles per chain link on sm_100a - the scheduler keeps
+// running one divergent group's loop and the lane whose value has arrived is not looked at
+// (profiles/r1_lu_notes.md).  `peek(c, &x)` returns true once x_c is available.
+template <int STRIDE, typename Peek>
+__device__ __forceinline__ double row_dot(const LUDev& lu, int begin, int end, int tid, NRStat* st, int errbit, Peek peek) {
   double part = 0.0;
-  for (int p0 = first; p0 < end; p0 += 4 * STRIDE) {
+  for (int base = begin; base < end; base += 4 * STRIDE) {
     int c[4];
     double v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u * STRIDE;
+      const int p = base + tid + u * STRIDE;
       c[u] = p < end ? lu.col[p] : -1;
       v[u] = p < end ? lu.val[p] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (c[u] >= 0) part += v[u] * wl(c[u]);
+    for (int u = 0; u < 4; ++u) {
+      if (base + u * STRIDE >= end) break;   // uniform: no thread has an entry in this slot
+      bool ok = c[u] < 0;
+      double x = 0.0;
+      unsigned spins = 0;
+      while (true) {
+        if (!ok) ok = peek(c[u], &x);
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); break; }
+      }
+      if (c[u] >= 0) part += v[u] * x;
+    }
   }
   return part;
 }
@@ -604,7 +629,7 @@ __device__ __forceinline__ double row_dot(const LUDev& lu, int first, int end, W
 // level order, every lane loads its matrix entries first and then waits for exactly the y it needs.
 // Rows of the chain tail [tail_start, n): block 0 alone, its warps taking the rows round-robin in
 // index order and handing y over in shared memory.
-__global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __restrict__ b, double scale,
+__global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_lsolve(LUDev lu, const double* __restrict__ b, double scale,
                                                    const unsigned char* __restrict__ zero_mask, NRStat* st) {
   __shared__ double ytail[VJX_TAIL_MAX];
   const unsigned epoch = st->epoch;
@@ -618,23 +643,41 @@ __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __res
     __syncthreads();
     for (int t = threadIdx.x >> 5; t < n_tail; t += (blockDim.x >> 5)) {
       const int i = n_bulk + t;
+#ifdef VJX_DEBUG_TS
+      long long c_start = clock64(), c_dot = 0, c_sum = 0;
+#endif
       const int rb = lu.ptr[i], dg = lu.diag[i];
       double bi = 0.0;
       if (lane == 0) {
         const int r = lu.perm_r[i];
         bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
       }
-      double part = row_dot<32>(lu, rb + lane, dg, [&](int c) {
+      double part = row_dot<32>(lu, rb, dg, lane, st, 4, [&](int c, double* x) {
         const int s = c - n_bulk;
-        if (s >= 0) return wait_smem(ytail + s, st, 4);
-        wait_flag(lu.flag_l + c, epoch, st, 4);
-        return __ldcg(lu.y + c);
+        if (s >= 0) {
+          const ull bits = *reinterpret_cast<const volatile ull*>(ytail + s);
+          *x = __longlong_as_double((long long)bits);
+          return bits != VJX_SENTINEL;
+        }
+        if (ld_relaxed_u32(lu.flag_l + c) != epoch) return false;
+        *x = __ldcg(lu.y + c);
+        return true;
       });
+#ifdef VJX_DEBUG_TS
+      c_dot = clock64();
+      c_dot = __shfl_sync(0xffffffffu, c_dot, (dg - 1 - rb) & 31);
+#endif
       if (dg - rb > 1) part = warp_sum(part);
       else part = __shfl_sync(0xffffffffu, part, 0);
+#ifdef VJX_DEBUG_TS
+      c_sum = clock64();
+#endif
       if (lane == 0) {
         const double yi = bi - part;
         *reinterpret_cast<volatile double*>(ytail + t) = yi;
+#ifdef VJX_DEBUG_TS
+        if (lu.ts) { lu.ts[n + 2 + 4 * t] = (ull)c_start; lu.ts[n + 2 + 4 * t + 1] = (ull)c_dot; lu.ts[n + 2 + 4 * t + 2] = (ull)c_sum; lu.ts[n + 2 + 4 * t + 3] = (ull)clock64(); }
+#endif
         lu.y[i] = yi;
         if (lu.ts) lu.ts[i] = global_ns();
       }
@@ -653,9 +696,10 @@ __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __res
       const int r = lu.perm_r[i];
       bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
     }
-    double part = row_dot<32>(lu, rb + lane, dg, [&](int c) {
-      wait_flag(lu.flag_l + c, epoch, st, 4);
-      return __ldcg(lu.y + c);
+    double part = row_dot<32>(lu, rb, dg, lane, st, 4, [&](int c, double* x) {
+      if (ld_relaxed_u32(lu.flag_l + c) != epoch) return false;
+      *x = __ldcg(lu.y + c);
+      return true;
     });
     if (dg - rb > 1) part = warp_sum(part);
     else part = __shfl_sync(0xffffffffu, part, 0);
@@ -671,7 +715,7 @@ __global__ void __launch_bounds__(256) k_lu_lsolve(LUDev lu, const double* __res
 // (the trailing block of U): block 0 walks it through shared memory and publishes every x for the
 // wide remainder, which the other blocks solve by ticket.  The last n_long_u blocks each take one
 // very long row (a rail kept as column-singleton pivot: one entry per attached device).
-__global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict__ x_out, NRStat* st) {
+__global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_usolve(LUDev lu, double* __restrict__ x_out, NRStat* st) {
   __shared__ double xtail[VJX_TAIL_MAX];
   const unsigned epoch = st->epoch;
   const int lane = threadIdx.x & 31;
@@ -692,7 +736,11 @@ __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict_
         pc = lu.perm_c[i];
       }
       // a tail row's U entries point into the tail
-      double part = row_dot<32>(lu, ub + lane, re, [&](int c) { return wait_smem(xtail + (n - 1 - c), st, 8); });
+      double part = row_dot<32>(lu, ub, re, lane, st, 8, [&](int c, double* x) {
+        const ull bits = *reinterpret_cast<const volatile ull*>(xtail + (n - 1 - c));
+        *x = __longlong_as_double((long long)bits);
+        return bits != VJX_SENTINEL;
+      });
       if (re - ub > 1) part = warp_sum(part);
       else part = __shfl_sync(0xffffffffu, part, 0);
       if (lane == 0) {
@@ -710,9 +758,10 @@ __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict_
     double* sh = xtail;
     const int i = lu.long_u[blockIdx.x - (gridDim.x - lu.n_long_u)];
     const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
-    double part = row_dot<256>(lu, ub + threadIdx.x, re, [&](int c) {
-      wait_flag(lu.flag_u + c, epoch, st, 8);
-      return __ldcg(lu.xp + c);
+    double part = row_dot<VJX_SOLVE_THREADS>(lu, ub, re, threadIdx.x, st, 8, [&](int c, double* x) {
+      if (ld_relaxed_u32(lu.flag_u + c) != epoch) return false;
+      *x = __ldcg(lu.xp + c);
+      return true;
     });
     part = block_sum_256(part, sh);
     if (threadIdx.x == 0) {
@@ -738,9 +787,10 @@ __global__ void __launch_bounds__(256) k_lu_usolve(LUDev lu, double* __restrict_
       di = lu.inv_diag[i];
       pc = lu.perm_c[i];
     }
-    double part = row_dot<32>(lu, ub + lane, re, [&](int c) {
-      wait_flag(lu.flag_u + c, epoch, st, 8);
-      return __ldcg(lu.xp + c);
+    double part = row_dot<32>(lu, ub, re, lane, st, 8, [&](int c, double* x) {
+      if (ld_relaxed_u32(lu.flag_u + c) != epoch) return false;
+      *x = __ldcg(lu.xp + c);
+      return true;
     });
     if (re - ub > 1) part = warp_sum(part);
     else part = __shfl_sync(0xffffffffu, part, 0);
@@ -1695,8 +1745,8 @@ static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s);
 static void launch_lu(vjx_handle* h, const double* csr, const double* b, double scale, const unsigned char* zero_mask,
                       double* x, cudaStream_t s) {
   k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, csr, h->st.p);
-  k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, b, scale, zero_mask, h->st.p);
-  k_lu_usolve<<<h->lu_grid_u, 256, 0, s>>>(h->lud, x, h->st.p);
+  k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(h->lud, b, scale, zero_mask, h->st.p);
+  k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(h->lud, x, h->st.p);
   h->launches += 3;
 }
 
@@ -1771,13 +1821,16 @@ static int upload_symbolic(vjx_handle* h) {
   // persistent grids: every CTA must be resident (dependency waits), so size from occupancy
   int occ_f = 1, occ_s = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_lu_factor, 256, 0));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_lu_lsolve, 256, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_lu_lsolve, VJX_SOLVE_THREADS, 0));
   int occ_u = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_lu_usolve, 256, 0));
-  occ_s = std::min(occ_s, occ_u);
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_lu_usolve, VJX_SOLVE_THREADS, 0));
+  occ_s = std::max(1, std::min(occ_s, occ_u));
   long long warps_needed = S.n;
+  const int wps = VJX_SOLVE_THREADS / 32;
   h->lu_grid_f = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * std::min(occ_f, 4), (warps_needed + 7) / 8));
-  h->lu_grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * std::min(occ_s, 4), (warps_needed + 7) / 8));
+  // one block per SM slot, minus room for the long-row blocks, so that every block is resident
+  h->lu_grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_s - (long long)S.long_u.size(),
+                                                                  (warps_needed + wps - 1) / wps));
   // block 0 of the solve kernels is dedicated to the chain tail; the other blocks take the tickets
   if (S.tail_start < S.n && h->lu_grid_s < 2) h->lu_grid_s = 2;
   h->lu_grid_u = h->lu_grid_s + (int)S.long_u.size();
@@ -2284,16 +2337,28 @@ extern "C" int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* le
   LUDev lud = h->lud;
   k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
   if (phase >= 4) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p);
-  if (phase >= 5) k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+  if (phase >= 5) k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
   lud.ts = ts.p;
   k_stamp_now<<<1, 1, 0, s>>>(ts.p + n);
   if (phase == 3) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(lud, h->csr.p, h->st.p);
-  if (phase == 4) k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
-  if (phase == 5) k_lu_usolve<<<h->lu_grid_u, 256, 0, s>>>(lud, h->delta.p, h->st.p);
+  if (phase == 4) k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+  if (phase == 5) k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(lud, h->delta.p, h->st.p);
   std::vector<ull> hts((size_t)n + 1);
   CK(cudaStreamSynchronize(s));
   CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
 #ifdef VJX_DEBUG_TS
+  if (phase == 4) {
+    const int nt = n - h->sym.tail_start;
+    std::vector<ull> dbg(4100);
+    CK(cudaMemcpy(dbg.data(), ts.p + n + 1, sizeof(ull) * 4100, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "lsolve tail rows (SM cycles relative to previous row's publish): t, start, dot done, summed, published, Llen\n");
+    for (int t = std::max(1, nt - 30); t < nt && 4 * t + 4 < 4099; ++t) {
+      long long base = (long long)dbg[1 + 4 * (t - 1) + 3];
+      fprintf(stderr, "  %4d %8lld %8lld %8lld %8lld  %d\n", t, (long long)dbg[1 + 4 * t] - base, (long long)dbg[1 + 4 * t + 1] - base,
+              (long long)dbg[1 + 4 * t + 2] - base, (long long)dbg[1 + 4 * t + 3] - base,
+              h->sym.lu_diag[h->sym.tail_start + t] - h->sym.lu_ptr[h->sym.tail_start + t]);
+    }
+  }
   if (phase == 3) {
     std::vector<ull> dbg(4100);
     CK(cudaMemcpy(dbg.data(), ts.p + n + 1, sizeof(ull) * 4100, cudaMemcpyDeviceToHost));
@@ -2331,7 +2396,7 @@ extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg
       // each LU phase needs a fresh epoch and the preceding phases' results
       k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
       if (phase >= 4) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p);
-      if (phase >= 5) k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+      if (phase >= 5) k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
     }
     CK(cudaEventRecord(e0, s));
     l0 = h->launches;
@@ -2340,8 +2405,8 @@ extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg
       case 1: launch_stamp(h, h->csr.p, 1, s); break;
       case 2: launch_residual(h, b, 0, s); break;
       case 3: k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p); h->launches++; break;
-      case 4: k_lu_lsolve<<<h->lu_grid_s, 256, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p); h->launches++; break;
-      case 5: k_lu_usolve<<<h->lu_grid_u, 256, 0, s>>>(h->lud, h->delta.p, h->st.p); h->launches++; break;
+      case 4: k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p); h->launches++; break;
+      case 5: k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->delta.p, h->st.p); h->launches++; break;
       case 6: k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua); h->launches++; break;
       default: return fail(VJX_ERR_INVALID, "unknown phase");
     }
