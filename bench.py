@@ -15,8 +15,10 @@ attempts included in the time - the reference's own definition, full_mna.py:1142
 * ``roofline``  the dominant kernel of a step, timed alone with CUDA events (vjx_time_phase).
 * ``cpu_baseline``  the NumPy/SciPy oracle port timed on this box's host cores on a bounded sample.
 
-N > 1 (torchrun): whole-circuit replicas = PVT corners, ``--corners`` per GPU (weak scaling), no
-collective inside the step loop; the recorded waveforms are gathered to rank 0 with NCCL afterwards.
+Every rank runs ``--corners`` PVT corners of the circuit (default 8, so 8 GPUs run the 64-point sweep
+of BASELINE.json configs[4]; corner i goes to GPU i mod N, corner 0 is the nominal circuit and is
+reported alone as ``value_nominal``).  Weak scaling: fixed work per GPU, no collective inside the
+step loop; for N > 1 the recorded waveforms are gathered to rank 0 with NCCL afterwards (in ``e2e``).
 """
 from __future__ import annotations
 
@@ -62,7 +64,7 @@ def make_circuit(workload: str, nbits: int, corner: int = 0):
     else:
         nb = 16
     circ = circuits.multiplier_circuit(nb)
-    if corner:
+    if corner:  # corner 0 of the sweep is the nominal circuit itself
         from vajax_b200.analysis.corners import apply_corner, sweep_corners
 
         circ = apply_corner(circ, sweep_corners(64)[corner % 64])
@@ -177,9 +179,11 @@ def run_b200(args, rank, world, local_rank):
     n_corners = args.corners
     engines = []
     desc = ""
+    corner_ids = []
     for c in range(n_corners):
-        gid = rank * n_corners + c
-        circ, desc = make_circuit(args.workload, args.nbits, corner=gid if (world > 1 or n_corners > 1) else 0)
+        gid = c * world + rank  # block-cyclic: corner i -> GPU i mod world
+        corner_ids.append(gid)
+        circ, desc = make_circuit(args.workload, args.nbits, corner=gid)
         engines.append(B200Engine(circ, bundles, device=local_rank, use_device_graph=not args.no_graph).prepare())
     eng = engines[0]
     rows = 1 + K
@@ -201,10 +205,12 @@ def run_b200(args, rank, world, local_rank):
     sampler.start()
     barrier()
     total_ms, steps_done, attempts, nr_total, rejected = 0.0, 0, 0, 0, 0
+    per_corner = []
     t_wall0 = time.perf_counter()
     for e in engines:
         e.tran_begin(max_steps=rows)
         step = 1
+        ms0 = total_ms
         while step < rows:
             flush.fill_(1.0)
             a = e.tran_run(step_limit=step + 1)
@@ -213,6 +219,7 @@ def run_b200(args, rank, world, local_rank):
             total_ms += e.tran_run_ms()[0]
             step += 1
         sc = e.tran_scalars()
+        per_corner.append((total_ms - ms0) / max(sc["step_idx"] - 1, 1))
         steps_done += sc["step_idx"] - 1
         attempts += sc["attempts"]
         nr_total += sc["total_nr"]
@@ -298,6 +305,8 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "256 MB flush between timed steps (value); value_l2_resident is the uninterrupted device loop",
                    "steps_timed": g_steps, "attempts": int(cnts[3]), "nr_iterations": int(cnts[4]), "rejected": int(cnts[5])},
         "value_l2_resident": vals[1] / max(g_res_steps, 1),
+        "value_nominal": per_corner[0] if corner_ids[0] == 0 else None,
+        "rank0_corners": {"ids": corner_ids, "ms_per_step": per_corner},
         "e2e": {"value": vals[2] * 1e3 / max(g_e2e_steps, 1), "unit": UNIT,
                 "h2d_bytes_per_step": cnts[6] / max(g_e2e_steps, 1), "d2h_bytes_per_step": cnts[7] / max(g_e2e_steps, 1),
                 "gather_s": gather_s},
@@ -357,7 +366,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c6288", choices=["c6288", "mul", "ring"])
     ap.add_argument("--nbits", type=int, default=16)
-    ap.add_argument("--corners", type=int, default=1, help="circuit replicas (PVT corners) per GPU")
+    ap.add_argument("--corners", type=int, default=8,
+                    help="PVT corners (whole-circuit replicas) per GPU; 8 per GPU = the 64-point sweep at 8 GPUs; "
+                         "corner 0 is the nominal circuit (value_nominal)")
     ap.add_argument("--cpu-steps", type=int, default=25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="host-polled NR/step loops (for ncu launch lists)")

@@ -201,7 +201,10 @@ def test_apply_corner_is_pure_and_signed():
     mos = next(d for d in circ["devices"] if d["model"] == "psp103")
     vdd = next(d for d in circ["devices"] if d["name"] == "vdd")
     kp0, vto0, dc0 = mos["params"]["kp"], mos["params"]["vto"], vdd["params"]["dc"]
-    c = cz.apply_corner(circ, cz.sweep_corners(64)[0])  # FF, 233.15 K, 0.9 vdd
+    sw = cz.sweep_corners(64)
+    assert sw[0].name == "TT_27C_V100pct"  # nominal first
+    ff = next(c for c in sw if c.name == "FF_m40C_V90pct")
+    c = cz.apply_corner(circ, ff)  # FF, 233.15 K, 0.9 vdd
     m2 = next(d for d in c["devices"] if d["name"] == mos["name"])
     v2 = next(d for d in c["devices"] if d["name"] == "vdd")
     assert m2["params"]["kp"] == kp0 * 1.15 and m2["params"]["vto"] == vto0 - 0.05

@@ -182,7 +182,8 @@ def apply_corner(circuit: dict, corner: CornerConfig) -> dict:
 def sweep_corners(n: int = 64) -> List[CornerConfig]:
     """The 64-point sweep of BASELINE.json configs[4]: {FF,TT,SS,FS} x {233.15,273.15,300.15,398.15} K
     x vdd {0.9,1.0,1.05,1.1}, truncated / cycled to ``n``."""
-    base = create_standard_corners(["FF", "TT", "SS", "FS"], [233.15, 273.15, 300.15, 398.15], [0.9, 1.0, 1.05, 1.1])
+    # nominal first (TT, 27 C, 100 % vdd), so that corner 0 is the circuit of the single-transient benchmark
+    base = create_standard_corners(["TT", "FF", "SS", "FS"], [300.15, 233.15, 273.15, 398.15], [1.0, 0.9, 1.05, 1.1])
     return [base[i % len(base)] for i in range(n)]
 
 

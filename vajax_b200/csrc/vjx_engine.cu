@@ -444,17 +444,16 @@ __device__ __forceinline__ bool wait_flag(const unsigned* f, unsigned epoch, NRS
 // l = w[k] / U(k,k) and scatters w[pos] -= l * U(k,j) through the precomputed position list, lanes
 // striding over U(k,:).  Rounding is identical to the classic row update.
 //
-// The k-steps can be taken in batches of VJX_KB (lane b waits for row k_b and fetches its pivot and
-// row bounds, the warp prefetches the U values and scatter positions of the whole batch into
-// registers, then the order-dependent shared-memory updates run back to back).  Measured on B200
-// (gpurun_out/r1_kb_exp2.txt, profiles/r1_lu_notes.md): the unrolled batch code is ~1k straight-line
-// instructions per batch, and a lone warp resuming from a dependency wait executes it at
-// instruction-fetch latency (7-10 us per batch instead of 2 us when hot), so the dependency chain
-// gets SLOWER in proportion to VJX_KB (1.5 / 5.5 / 11.5 us per chain row for 1 / 4 / 8).  The default
-// therefore stays at 1 (compact code) until the chain tail moves to a dense shared-memory block.
+// The k-steps are taken in batches of VJX_KB: lane b fetches the bounds of row k_b, the whole warp
+// polls CONVERGENTLY until all rows of the batch are published (per-lane divergent spins starve the
+// lane whose flag has arrived, profiles/r1_lu_notes.md), prefetches the U values and scatter
+// positions of the batch into registers, then runs the order-dependent shared-memory updates back to
+// back.  Measured on B200 (gpurun_out/r1_kb_exp3.txt): 371 / 339 / 359 / 457 us per refactorisation
+// for VJX_KB = 1 / 2 / 4 / 8 - the dependency chain of the trailing block (1.6 us per link through
+// global memory) dominates, so small batches win.
 #define VJX_ROWBUF 640
 #ifndef VJX_KB
-#define VJX_KB 1
+#define VJX_KB 2
 #endif
 __global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __restrict__ csr, NRStat* st) {
   __shared__ double wbuf[8][VJX_ROWBUF];
@@ -496,15 +495,24 @@ __global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __res
         int ub_l = 0, ue_l = 0;
         long long mb_l = 0;
         double inv_l = 0.0;
+        int k = -1;
         if (lane < nb) {
-          const int k = lu.col[pb + lane];
+          k = lu.col[pb + lane];
           mb_l = lu.upd_ptr[pb + lane];
           ub_l = lu.diag[k] + 1;
           ue_l = lu.ptr[k + 1];
-          wait_flag(lu.flag_f + k, epoch, st, 1);
-          inv_l = __ldcg(lu.inv_diag + k);
         }
-        __syncwarp();
+        {
+          // convergent poll: the whole warp iterates until every row of the batch is published
+          bool ok = k < 0;
+          unsigned spins = 0;
+          while (true) {
+            if (!ok) ok = ld_relaxed_u32(lu.flag_f + k) == epoch;
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+          }
+        }
+        if (k >= 0) inv_l = __ldcg(lu.inv_diag + k);
 #ifdef VJX_DEBUG_TS
         if (dbg && lane == 0 && dbg_slot < 4000) lu.ts[n + 2 + dbg_slot++] = global_ns();
 #endif
