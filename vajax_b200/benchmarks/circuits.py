@@ -49,6 +49,18 @@ class _Net:
         p["pd"] = 2 * (w + ld)
         self.add(name, "psp103", [d, g, s, b], p)
 
+    def renumber_sorted(self):
+        """Node indices by sorted node name, ground = 0 (reference: build_node_mapping,
+        vajax/analysis/parsing.py:146-168)."""
+        order = ["0"] + sorted(n for n in self.names if n != "0")
+        new = {n: i for i, n in enumerate(order)}
+        remap = [0] * len(order)
+        for n, old in self.names.items():
+            remap[old] = new[n]
+        for d in self.devices:
+            d["nodes"] = [remap[x] for x in d["nodes"]]
+        self.names = new
+
     def circuit(self, analysis: dict, temperature_k: float = 300.15) -> dict:
         return dict(num_nodes=len(self.names), node_names=dict(self.names), devices=self.devices,
                     analysis=dict(analysis), temperature_k=temperature_k)
@@ -189,6 +201,109 @@ def multiplier_circuit(nbits: int = 16, stop: float = 2e-9, step: float = 2e-12,
         else:
             full_adder(s_prev[k + 1], c_prev[k], carry, so, co)
         carry = co
+    return net.circuit(dict(step=step, stop=stop, icmode="uic", nr_convtol=1, tran_lteratio=1.5, tran_method="trap"))
+
+
+def mul64_circuit(nbits: int = 64, stop: float = 2e-9, step: float = 2e-12, vdd: float = 1.2,
+                  wn: float = 0.5e-6, wp: float = 1e-6, l: float = 0.2e-6) -> dict:
+    """The reference's mul64 benchmark (vajax/benchmarks/data/mul64/runme.sim), flattened.
+
+    Gate library of the netlist's generate block (:23-59): not = 2 T, nor = 4 T, and = 6 T
+    (nand + inverter), xor = 3 not + 2 and + nor = 22 T, ha = xor + and = 28 T,
+    fa = 2 xor + 2 and + nor + not = 62 T.  Array topology (:61-139): n^2 partial products, a two
+    inverter buffer for p0, row 0 of n-1 half adders, rows 1..n-2 with a half adder in column 0
+    and full adders in columns 1..n-2.  Test bench (:141-292): one ``drv`` (pulse source behind a
+    1 ohm resistor, delay = rise = 0.1 ns) per operand bit, all bits driven high, rails vdd / vss
+    behind DC sources, ``tran stop=2n step=2p icmode=uic``, ``nr_convtol=1 tran_lteratio=1.5``.
+    n=64 gives 266,408 MOSFETs + 128 resistors + 130 vsources - the counts the reference reports
+    for mul64.  Instances are emitted in the order of the reference's flattening
+    (depth first, vajax/analysis/parsing.py:32-143) with its hierarchical names (``top.u1.fa_3_2.x1.a1.mn1.m``)
+    and its node numbering (sorted names, parsing.py:146-168); tests/golden/mul64_topology.json holds
+    the digest of the reference parser's own result for n=64."""
+    N = nbits
+    net = _Net()
+    net.node("vdd")
+    net.node("vss")
+    net.add("vdd", "vsource", ["vdd", "0"], dict(dc=vdd, type="dc"), openvaf=False)
+    net.add("vss", "vsource", ["vss", "0"], dict(dc=0.0, type="dc"), openvaf=False)
+
+    def inv(p, out, a):
+        net.mos(p + ".mp.m", "p", out, a, "vdd", "vdd", wp, l)
+        net.mos(p + ".mn.m", "n", out, a, "vss", "vss", wn, l)
+
+    def nor(p, out, a, b):
+        mid = p + ".int"
+        net.mos(p + ".mp2.m", "p", mid, b, "vdd", "vdd", wp, l)
+        net.mos(p + ".mp1.m", "p", out, a, mid, "vdd", wp, l)
+        net.mos(p + ".mn1.m", "n", out, a, "vss", "vss", wn, l)
+        net.mos(p + ".mn2.m", "n", out, b, "vss", "vss", wn, l)
+
+    def and2(p, out, a, b):
+        ox, mid = p + ".outx", p + ".int"
+        net.mos(p + ".mp2.m", "p", ox, b, "vdd", "vdd", wp, l)
+        net.mos(p + ".mp1.m", "p", ox, a, "vdd", "vdd", wp, l)
+        net.mos(p + ".mn1.m", "n", ox, a, mid, "vss", wn, l)
+        net.mos(p + ".mn2.m", "n", mid, b, "vss", "vss", wn, l)
+        net.mos(p + ".mp3.m", "p", out, ox, "vdd", "vdd", wp, l)
+        net.mos(p + ".mn3.m", "n", out, ox, "vss", "vss", wn, l)
+
+    def xor(p, out, a, b):
+        inv(p + ".inv_a", p + ".na", a)
+        inv(p + ".inv_b", p + ".nb", b)
+        and2(p + ".a1", p + ".t1", a, p + ".nb")
+        and2(p + ".a2", p + ".t2", p + ".na", b)
+        nor(p + ".n1", p + ".t3", p + ".t1", p + ".t2")
+        inv(p + ".inv_out", out, p + ".t3")
+
+    def ha(p, s, co, a, b):
+        xor(p + ".x1", s, a, b)
+        and2(p + ".a1", co, a, b)
+
+    def fa(p, s, co, a, b, cin):
+        xor(p + ".x1", p + ".ab_xor", a, b)
+        xor(p + ".x2", s, p + ".ab_xor", cin)
+        and2(p + ".a1", p + ".ab_and", a, b)
+        and2(p + ".a2", p + ".xor_cin", p + ".ab_xor", cin)
+        nor(p + ".n1", p + ".cout_n", p + ".ab_and", p + ".xor_cin")
+        inv(p + ".inv_cout", co, p + ".cout_n")
+
+    last_row = N - 2
+
+    def sum_name(row, col):
+        if col == 0:
+            return f"top.p{row + 1}"
+        if row == last_row:
+            return f"top.p{N + col - 1}" if col < N - 1 else f"top.u1.s{row}_{col}"
+        return f"top.u1.s{row}_{col}"
+
+    def carry_name(row, col):
+        if row == last_row and col == N - 2:
+            return f"top.p{2 * N - 2}"
+        return f"top.u1.c{row}_{col}"
+
+    for i in range(N):
+        for j in range(N):
+            and2(f"top.u1.pp_{i}_{j}", f"top.u1.pp{i}_{j}", f"top.a{i}", f"top.b{j}")
+    inv("top.u1.buf_p0_inv", "top.u1.p0_n", "top.u1.pp0_0")
+    inv("top.u1.buf_p0", "top.p0", "top.u1.p0_n")
+    for j in range(N - 1):
+        ha(f"top.u1.ha_0_{j}", sum_name(0, j), carry_name(0, j), f"top.u1.pp0_{j + 1}", f"top.u1.pp1_{j}")
+    for row in range(1, N - 1):
+        for j in range(N - 1):
+            sn, cn = sum_name(row, j), carry_name(row, j)
+            b_in = f"top.u1.pp{row + 1}_{j}"
+            a_in = sum_name(row - 1, j + 1) if j < N - 2 else carry_name(row - 1, N - 2)
+            if j == 0:
+                ha(f"top.u1.ha_{row}_{j}", sn, cn, a_in, b_in)
+            else:
+                fa(f"top.u1.fa_{row}_{j}", sn, cn, a_in, b_in, carry_name(row, j - 1))
+    for nm in ("a", "b"):
+        for i in range(N):
+            src = f"top.d{nm}{i}.int"
+            net.add(f"top.d{nm}{i}.vdrv", "vsource", [src, "0"],
+                    dict(dc=0.0, type="pulse", val0=0.0, val1=vdd, delay=0.1e-9, rise=0.1e-9), openvaf=False)
+            net.add(f"top.d{nm}{i}.rdrv", "resistor", [src, f"top.{nm}{i}"], dict(r=1.0))
+    net.renumber_sorted()
     return net.circuit(dict(step=step, stop=stop, icmode="uic", nr_convtol=1, tran_lteratio=1.5, tran_method="trap"))
 
 
