@@ -250,25 +250,69 @@ __device__ __forceinline__ double finish_slot(double acc, unsigned char f, float
   return acc;
 }
 
-// Grid layout: CTAs [0, n_long) each reduce one long segment; the rest stride over all slots and
-// skip the long ones.
+// Long segments are cut into chunks of VJX_CHUNK entries; one CTA reduces one chunk (fixed strided
+// partials, fixed butterfly), publishes the partial and takes a ticket on the segment's counter; the
+// CTA that takes the last ticket adds the partials in chunk order (warp 0: lane-strided, butterfly) and
+// finishes the slot.  The order of additions is a function of the tables only -> bit-identical runs.
+#define VJX_CHUNK 4096
+struct LongSeg {
+  const int* chunk_seg;      // [n_chunks] index into seg_id / first / count
+  const int* chunk_begin;    // [n_chunks] first entry of the chunk
+  const int* chunk_end;      // [n_chunks]
+  const int* seg_id;         // [n_long] CSR slot (or node row) of the long segment
+  const int* first;          // [n_long + 1] first chunk of each long segment
+  unsigned* count;           // [n_long] arrival counters (self-resetting)
+  double* partial;           // [n_chunks * width]
+  int n_chunks;
+};
+
+// Returns true in every thread of the CTA that took the last ticket of long segment k.
+__device__ __forceinline__ bool long_seg_arrive(const LongSeg& L, int k, int* sh_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned need = (unsigned)(L.first[k + 1] - L.first[k]);
+    const unsigned old = atomicAdd(L.count + k, 1u);
+    *sh_flag = (old + 1u == need);
+    if (old + 1u == need) { L.count[k] = 0u; __threadfence(); }
+  }
+  __syncthreads();
+  return *sh_flag != 0;
+}
+
+// Grid layout: CTAs [0, n_chunks) each reduce one chunk of a long segment; the rest stride over all
+// slots and skip the long ones.
 __global__ void __launch_bounds__(256) k_stamp_jacobian(int nse, const int* __restrict__ seg,
                                  const double* __restrict__ jsorted, const unsigned char* __restrict__ flags,
                                  const float* __restrict__ cst, const double* __restrict__ ctl, int enforce_noi,
-                                 const int* __restrict__ long_slots, int n_long, double* __restrict__ csr) {
+                                 LongSeg L, double* __restrict__ csr) {
   __shared__ double sh[8];
+  __shared__ int sh_flag;
   const double reg = ctl[VJX_CTL_DIAGREG] + ctl[VJX_CTL_GSHUNT];
-  if ((int)blockIdx.x < n_long) {
-    const int s = long_slots[blockIdx.x];
-    const int b = seg[s], e = seg[s + 1];
-    double acc = 0.0;
-    for (int p = b + threadIdx.x; p < e; p += blockDim.x) acc += jsorted[p];
-    acc = block_sum_256(acc, sh);
-    if (threadIdx.x == 0) csr[s] = finish_slot(acc, flags[s], cst[s], reg, enforce_noi);
+  if ((int)blockIdx.x < L.n_chunks) {
+    const int c = blockIdx.x;
+    const int k = L.chunk_seg[c];
+    const int b = L.chunk_begin[c], e = L.chunk_end[c];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int p = b + threadIdx.x;
+    for (; p + 3 * 256 < e; p += 4 * 256) {
+      a0 += jsorted[p]; a1 += jsorted[p + 256]; a2 += jsorted[p + 512]; a3 += jsorted[p + 768];
+    }
+    for (; p < e; p += 256) a0 += jsorted[p];
+    double acc = block_sum_256((a0 + a1) + (a2 + a3), sh);
+    if (threadIdx.x == 0) L.partial[c] = acc;
+    if (!long_seg_arrive(L, k, &sh_flag)) return;
+    if (threadIdx.x < 32) {
+      double t = 0.0;
+      for (int q = L.first[k] + threadIdx.x; q < L.first[k + 1]; q += 32) t += __ldcg(L.partial + q);
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      const int s = L.seg_id[k];
+      if (threadIdx.x == 0) csr[s] = finish_slot(t, flags[s], cst[s], reg, enforce_noi);
+    }
     return;
   }
-  const int nb = gridDim.x - n_long;
-  for (int s = (blockIdx.x - n_long) * blockDim.x + threadIdx.x; s < nse; s += nb * blockDim.x) {
+  const int nb = gridDim.x - L.n_chunks;
+  for (int s = (blockIdx.x - L.n_chunks) * blockDim.x + threadIdx.x; s < nse; s += nb * blockDim.x) {
     int b = seg[s], e = seg[s + 1];
     if (e - b > VJX_LONG_SEG) continue;
     double acc = 0.0;
@@ -301,8 +345,7 @@ struct ResidualArgs {
   double* maxres;
   NRStat* st;
   int check;                  // accumulate convergence statistics
-  const int* long_rows;       // node rows with more than VJX_LONG_SEG contributions
-  int n_long;
+  LongSeg L;                  // node rows with more than VJX_LONG_SEG contributions, in chunks
 };
 
 // One node row of the residual once its five segment reductions are known
@@ -335,19 +378,22 @@ __device__ __forceinline__ void finish_node_row(const ResidualArgs& a, int i, do
   if (mx != mx || fl != fl) tol = mx * 0.0 + fl * 0.0 + tol;  // jnp.maximum propagates NaN
 }
 
-// Grid layout: CTAs [0, n_long) each reduce one long node row; the rest stride over all rows.
+// Grid layout: CTAs [0, n_chunks) each reduce one chunk of a long node row (five partials per chunk);
+// the rest stride over all rows.
 __global__ void __launch_bounds__(256) k_residual(ResidualArgs a) {
   __shared__ double sh[8];
+  __shared__ int sh_flag;
   const int n_aug = a.n_unknowns + a.n_vs;
   const double c0 = a.ctl[VJX_CTL_C0], c1 = a.ctl[VJX_CTL_C1], d1 = a.ctl[VJX_CTL_D1], c2 = a.ctl[VJX_CTL_C2];
   const double eff = a.ctl[VJX_CTL_DIAGREG] + a.ctl[VJX_CTL_GSHUNT];
   int bad = 0;
   double mf = 0.0;
   bool mfnan = false;
-  if ((int)blockIdx.x < a.n_long) {
-    const int i = a.long_rows[blockIdx.x];
+  if ((int)blockIdx.x < a.L.n_chunks) {
+    const int c = blockIdx.x;
+    const int k = a.L.chunk_seg[c];
     double fr = 0.0, q = 0.0, lr = 0.0, lq = 0.0, mx = 0.0;
-    for (int p = a.vseg[i] + threadIdx.x; p < a.vseg[i + 1]; p += blockDim.x) {
+    for (int p = a.L.chunk_begin[c] + threadIdx.x; p < a.L.chunk_end[c]; p += blockDim.x) {
       const double2* r = reinterpret_cast<const double2*>(a.vsorted + (size_t)p * 4);
       double2 r0 = r[0], r1 = r[1];
       fr += r0.x;
@@ -362,6 +408,26 @@ __global__ void __launch_bounds__(256) k_residual(ResidualArgs a) {
     lq = block_sum_256(lq, sh);
     mx = block_max_256(mx, sh);
     if (threadIdx.x == 0) {
+      double* o = a.L.partial + (size_t)c * 5;
+      o[0] = fr; o[1] = q; o[2] = lr; o[3] = lq; o[4] = mx;
+    }
+    if (!long_seg_arrive(a.L, k, &sh_flag)) return;
+    if (threadIdx.x < 32) {
+      fr = 0.0; q = 0.0; lr = 0.0; lq = 0.0; mx = 0.0;
+      for (int g = a.L.first[k] + threadIdx.x; g < a.L.first[k + 1]; g += 32) {
+        const double* o = a.L.partial + (size_t)g * 5;
+        fr += __ldcg(o); q += __ldcg(o + 1); lr += __ldcg(o + 2); lq += __ldcg(o + 3); mx = fmax(mx, __ldcg(o + 4));
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        fr += __shfl_xor_sync(0xffffffffu, fr, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+        lr += __shfl_xor_sync(0xffffffffu, lr, o);
+        lq += __shfl_xor_sync(0xffffffffu, lq, o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+    }
+    if (threadIdx.x == 0) {
+      const int i = a.L.seg_id[k];
       double f, tol;
       finish_node_row(a, i, fr, q, lr, lq, mx, c0, c1, d1, c2, eff, f, tol);
       if (a.f) a.f[i] = f;
@@ -375,8 +441,8 @@ __global__ void __launch_bounds__(256) k_residual(ResidualArgs a) {
     }
     return;
   }
-  const int nb = gridDim.x - a.n_long;
-  for (int i = (blockIdx.x - a.n_long) * blockDim.x + threadIdx.x; i < n_aug; i += nb * blockDim.x) {
+  const int nb = gridDim.x - a.L.n_chunks;
+  for (int i = (blockIdx.x - a.L.n_chunks) * blockDim.x + threadIdx.x; i < n_aug; i += nb * blockDim.x) {
     double f, tol;
     if (i < a.n_unknowns) {
       if (a.vseg[i + 1] - a.vseg[i] > VJX_LONG_SEG) continue;
@@ -1261,6 +1327,46 @@ struct DevBuf {
   }
 };
 
+// Host owner of a LongSeg table (chunked long segments of the stamping kernels).
+struct LongSegBuf {
+  DevBuf<int> chunk_seg, chunk_begin, chunk_end, seg_id, first;
+  DevBuf<unsigned> count;
+  DevBuf<double> partial;
+  int n_chunks = 0, n_long = 0;
+  // seg: [n+1] segment pointers; ids: the long segments; width: partials per chunk
+  cudaError_t build(const std::vector<int>& seg, const std::vector<int>& ids, int width) {
+    std::vector<int> cs, cb, ce, first;
+    for (size_t k = 0; k < ids.size(); ++k) {
+      first.push_back((int)cs.size());
+      for (int b = seg[ids[k]]; b < seg[ids[k] + 1]; b += VJX_CHUNK) {
+        cs.push_back((int)k);
+        cb.push_back(b);
+        ce.push_back(std::min(b + VJX_CHUNK, seg[ids[k] + 1]));
+      }
+    }
+    first.push_back((int)cs.size());
+    n_chunks = (int)cs.size();
+    n_long = (int)ids.size();
+    std::vector<int> idv(ids);
+    if (cs.empty()) { cs.push_back(0); cb.push_back(0); ce.push_back(0); }
+    if (idv.empty()) idv.push_back(0);
+    cudaError_t e;
+    if ((e = chunk_seg.upload(cs)) != cudaSuccess) return e;
+    if ((e = chunk_begin.upload(cb)) != cudaSuccess) return e;
+    if ((e = chunk_end.upload(ce)) != cudaSuccess) return e;
+    if ((e = seg_id.upload(idv)) != cudaSuccess) return e;
+    if ((e = first.size() ? this->first.upload(first) : cudaSuccess) != cudaSuccess) return e;
+    if ((e = count.alloc(std::max<size_t>(idv.size(), 1))) != cudaSuccess) return e;
+    return partial.alloc(std::max<size_t>((size_t)n_chunks * width, 1));
+  }
+  LongSeg dev() const {
+    LongSeg L;
+    L.chunk_seg = chunk_seg.p; L.chunk_begin = chunk_begin.p; L.chunk_end = chunk_end.p;
+    L.seg_id = seg_id.p; L.first = first.p; L.count = count.p; L.partial = partial.p; L.n_chunks = n_chunks;
+    return L;
+  }
+};
+
 struct ModelState {
   void* dl = nullptr;
   vjx_model_eval_fn eval = nullptr;
@@ -1280,8 +1386,8 @@ struct vjx_handle {
   std::vector<int> h_indptr, h_indices;
   std::vector<ModelState*> models;
   // stamping tables
-  DevBuf<int> jseg, vseg, isrc_dest, att_ptr, att_idx, vs_p, vs_n, long_slots, long_rows;
-  int n_long_slots = 0, n_long_rows = 0;
+  DevBuf<int> jseg, vseg, isrc_dest, att_ptr, att_idx, vs_p, vs_n;
+  LongSegBuf long_slots, long_rows;
   DevBuf<signed char> att_sign;
   DevBuf<unsigned char> slot_flags, conv_mask, delta_mask, is_noi, noi_row_mask;
   DevBuf<float> slot_const;
@@ -1456,9 +1562,7 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
     std::vector<int> ls;
     for (int s = 0; s < nse; ++s)
       if (jcount[s] > VJX_LONG_SEG) ls.push_back(s);
-    h->n_long_slots = (int)ls.size();
-    if (ls.empty()) ls.push_back(0);
-    CK(h->long_slots.upload(ls));
+    CK(h->long_slots.build(jseg, ls, 1));
   }
   // ---- slot flags: diagonal regularisation, vsource incidence, NOI rows/cols
   std::vector<unsigned char> flags(nse, 0);
@@ -1560,9 +1664,7 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
     std::vector<int> lr;
     for (int i = 0; i < nu; ++i)
       if (vcount[i] > VJX_LONG_SEG) lr.push_back(i);
-    h->n_long_rows = (int)lr.size();
-    if (lr.empty()) lr.push_back(0);
-    CK(h->long_rows.upload(lr));
+    CK(h->long_rows.build(vseg, lr, 5));
   }
   // ---- vsources attached to each node row, in the order of the concatenated [p..., n...] scatter
   {
@@ -1727,9 +1829,8 @@ static int launch_eval(vjx_handle* h, const BuildPtrs& b, cudaStream_t s) {
 }
 
 static void launch_stamp(vjx_handle* h, double* csr, int enforce_noi, cudaStream_t s) {
-  k_stamp_jacobian<<<grid_for(h, h->nse) + h->n_long_slots, 256, 0, s>>>(
-      h->nse, h->jseg.p, h->jsorted.p, h->slot_flags.p, h->slot_const.p, h->ctl.p, enforce_noi, h->long_slots.p,
-      h->n_long_slots, csr);
+  k_stamp_jacobian<<<grid_for(h, h->nse) + h->long_slots.n_chunks, 256, 0, s>>>(
+      h->nse, h->jseg.p, h->jsorted.p, h->slot_flags.p, h->slot_const.p, h->ctl.p, enforce_noi, h->long_slots.dev(), csr);
   h->launches++;
 }
 
@@ -1743,8 +1844,8 @@ static void launch_residual(vjx_handle* h, const BuildPtrs& b, int check, cudaSt
   a.res_tol_floor = b.res_tol_floor; a.conv_mask = h->conv_mask.p; a.ctl = h->ctl.p;
   a.reltol = h->o.reltol; a.abstol = h->o.abstol; a.vntol = h->o.vntol;
   a.f = b.f; a.Q = b.Q; a.Ivs = b.Ivs; a.maxres = b.maxres; a.st = h->st.p; a.check = check;
-  a.long_rows = h->long_rows.p; a.n_long = h->n_long_rows;
-  k_residual<<<grid_for(h, h->n_aug) + h->n_long_rows, 256, 0, s>>>(a);
+  a.L = h->long_rows.dev();
+  k_residual<<<grid_for(h, h->n_aug) + h->long_rows.n_chunks, 256, 0, s>>>(a);
   h->launches++;
 }
 
