@@ -16,8 +16,9 @@ from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
-e = B200Engine(circuits.multiplier_circuit(nb), bundles, use_device_graph=True).prepare()
-e.run_transient(max_steps=12)
+circ = circuits.mul64_circuit(nb) if nb == 64 else circuits.multiplier_circuit(nb)
+e = B200Engine(circ, bundles, use_device_graph=True).prepare()
+e.run_transient(max_steps=6 if nb == 64 else 12)
 st = e.lu_stats()
 n = st["n"]
 print("lu", st)
@@ -34,8 +35,8 @@ for phase, name in ((3, "factor"), (4, "lsolve"), (5, "usolve")):
     nl = lv.max() + 1
     print(f"== {name}: {nl} levels, last row done at {ns.max() / 1e3:.1f} us, first at {ns.min() / 1e3:.1f} us")
     tail = np.arange(n) >= (n - 185)
-    for lo in range(0, nl, max(nl // 16, 1)):
-        hi = min(lo + max(nl // 16, 1), nl)
+    for lo in range(0, nl, max(nl // 32, 1)):
+        hi = min(lo + max(nl // 32, 1), nl)
         m = (lv >= lo) & (lv < hi)
         if m.any():
             print(f"   levels {lo:4d}-{hi - 1:4d}: rows {m.sum():6d}  done {ns[m].min() / 1e3:8.1f} .. {ns[m].max() / 1e3:8.1f} us"
