@@ -23,7 +23,7 @@ st = e.lu_stats()
 n = st["n"]
 print("lu", st)
 lib = vlib.load()
-for phase, name in ((3, "factor"), (4, "lsolve"), (5, "usolve")):
+for phase, name in ((3, "factor+fwd"), (5, "usolve")):
     best = None
     for rep in range(3):
         ns = np.zeros(n)

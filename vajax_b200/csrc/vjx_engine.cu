@@ -75,16 +75,22 @@ struct TranScalars {
 
 struct LUDev {
   int n;
+  long long nnz;
   const int* ptr;
   const int* col;
   const int* diag;
   const int* src;
-  const int* order_l;
+  const int* init;             // per L+U entry: what k_lu_load writes (slot of A / 0.0 / sentinel / nothing)
+  const int* kub;              // per L entry (i,k): start of U(k,:) in val (= diag[k] + 1)
   const int* order_u;
   const int* perm_r;
   const int* perm_c;
-  const int* order_f;          // all rows by level (factorisation); order_l / order_u hold the bulk rows
-  int tail_start;              // rows [tail_start, n): chain tail solved by one thread block
+  const int* order_f;          // all rows by L-dependency level; the first n_nol have no L part
+  int n_nol;                   // rows without an L part (finished by k_lu_load)
+  int rowbuf;                  // shared-memory working vector per warp of k_lu_rows (doubles)
+  int max_lrow;                // longest row with an L part
+  double* scratch;             // per-warp global working vectors, only when max_lrow > rowbuf
+  int tail_start;              // rows [tail_start, n): chain tail of the back solve, one thread block
   const int* long_u;           // rows with a very long U part: one thread block each (last blocks of the grid)
   int n_long_u, n_bulk_u;      // order_u holds n_bulk_u rows
   const long long* upd_ptr;    // [nnz+1] start of each L entry's scatter list
@@ -94,9 +100,6 @@ struct LUDev {
   double* inv_diag;
   double* y;
   double* xp;
-  unsigned* flag_f;
-  unsigned* flag_l;
-  unsigned* flag_u;
 };
 
 // Dependency flags are polled with a RELAXED gpu-scope load.  ld.acquire.gpu compiles to
@@ -487,146 +490,191 @@ __global__ void __launch_bounds__(256) k_residual(ResidualArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Sparse LU: numeric refactorisation on the fixed pattern / pivot order, dependency driven.
-// One warp per row; rows are handed out through a ticket counter in dependency-level order, so
-// with every warp resident the smallest unfinished row can always make progress (no deadlock).
-// Cross-SM visibility: producers st.release.gpu a per-row epoch flag; consumers poll it with a relaxed
-// gpu-scope load (see ld_relaxed_u32) and read finished rows with ld.cg (L2), never through L1.
+// Sparse LU: numeric refactorisation on the fixed pattern / pivot order, dependency driven, with the
+// forward solve folded in (y = L^-1 P b is one more column carried through the elimination), then a
+// dependency-driven back solve.
+//
+// Readiness travels WITH the data.  Everything another row may wait for - the U part of a row, its
+// 1/pivot, its y, and x in the back solve - is set to a sentinel bit pattern by k_lu_load at the start
+// of the factorisation and overwritten exactly once by its producer.  A consumer polls the value
+// itself (64-bit relaxed gpu-scope loads are single-copy atomic, every datum validates itself, no
+// fence is needed) instead of polling a flag and then fetching the data: one L2 round trip per
+// dependency link instead of two (profiles/r1_lu_notes.md).  The sentinel is a quiet-NaN payload that
+// arithmetic never produces (a computed NaN is the canonical 0x7ff8000000000000).
+//
+// Rows are handed to warps through a ticket counter in dependency-level order: a warp holding a
+// ticket only ever waits for rows with smaller tickets, which are held by running warps - no
+// residency requirement, no deadlock.
 // ------------------------------------------------------------------------------------------
 #define VJX_SPIN_LIMIT (1u << 24)
+#define VJX_SENTINEL 0x7ff8dead0badbeefULL
 
-__device__ __forceinline__ bool wait_flag(const unsigned* f, unsigned epoch, NRStat* st, int errbit) {
-  unsigned spins = 0;
-  while (ld_relaxed_u32(f) != epoch) {
-    if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); return false; }
-    if (spins > 64) __nanosleep(20);
+__device__ __forceinline__ ull ld_poll_u64(const double* p) {
+  ull v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_pub_f64(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double bits_f64(ull b) { return __longlong_as_double((long long)b); }
+
+// Flat pass, full grid: rows without an L part (peeled singletons, leaves of the elimination forest -
+// 80 % of all rows) are plain copies of A's values and are finished here, pivot reciprocal and y
+// included; the U part / pivot / y of every other row and all of x are set to the sentinel.
+// init[p]: >= 0 slot of A, -1 structural fill (0.0), -2 sentinel, -3 leave (L part of an L row).
+__global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restrict__ csr, const double* __restrict__ b,
+                                                 double scale, const unsigned char* __restrict__ zero_mask, NRStat* st) {
+  const long long nt = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double sent = bits_f64(VJX_SENTINEL);
+  for (long long p = t0; p < lu.nnz; p += nt) {
+    const int c = lu.init[p];
+    if (c >= 0) lu.val[p] = csr[c];
+    else if (c == -1) lu.val[p] = 0.0;
+    else if (c == -2) lu.val[p] = sent;
   }
-  return true;
+  for (long long i = t0; i < lu.n; i += nt) {
+    lu.xp[i] = sent;
+    const int dg = lu.diag[i];
+    if (dg == lu.ptr[i]) {
+      const int s = lu.src[dg];
+      const double d = s >= 0 ? csr[s] : 0.0;
+      if (d == 0.0 || d != d) atomicOr(&st->error, 2);
+      lu.inv_diag[i] = 1.0 / d;
+      const int r = lu.perm_r[i];
+      lu.y[i] = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
+      if (lu.ts) lu.ts[i] = global_ns();
+    } else {
+      lu.inv_diag[i] = sent;
+      lu.y[i] = sent;
+    }
+  }
 }
 
-// Numeric refactorisation, up-looking and k-sequential.  One warp per row, rows handed out in
-// dependency-level order.  The row lives in a shared-memory working vector w (rows longer than
-// VJX_ROWBUF work in place in global memory): for every L entry (i,k) in ascending k the warp forms
-// l = w[k] / U(k,k) and scatters w[pos] -= l * U(k,j) through the precomputed position list, lanes
-// striding over U(k,:).  Rounding is identical to the classic row update.
+// Rows with an L part, up-looking and k-sequential, one warp per row.  The row lives in a
+// shared-memory working vector w (sized at analysis time for the longest such row; rows beyond the
+// cap use a per-warp global scratch): for every L entry (i,k) in ascending k the warp forms
+// l = w[k] / U(k,k), scatters w[pos] -= l * U(k,j) through the precomputed position list (lanes
+// striding over U(k,:)) and lane 0 carries y_i -= l * y_k.  Rounding of the factor is that of the
+// classic row update.
 //
-// The k-steps are taken in batches of VJX_KB: lane b fetches the bounds of row k_b, the whole warp
-// polls CONVERGENTLY until all rows of the batch are published (per-lane divergent spins starve the
-// lane whose flag has arrived, profiles/r1_lu_notes.md), prefetches the U values and scatter
-// positions of the batch into registers, then runs the order-dependent shared-memory updates back to
-// back.  Measured on B200 (gpurun_out/r1_kb_exp3.txt): 371 / 339 / 359 / 457 us per refactorisation
-// for VJX_KB = 1 / 2 / 4 / 8 - the dependency chain of the trailing block (1.6 us per link through
-// global memory) dominates, so small batches win.
-#define VJX_ROWBUF 640
-#ifndef VJX_KB
-#define VJX_KB 2
-#endif
-__global__ void __launch_bounds__(256) k_lu_factor(LUDev lu, const double* __restrict__ csr, NRStat* st) {
-  __shared__ double wbuf[8][VJX_ROWBUF];
-  const unsigned epoch = st->epoch;
+// The L entries are taken 32 at a time: lane b fetches the static description of step b (coalesced)
+// and issues ONE non-blocking load of 1/pivot and y of its row k_b; the steps then run in order, and
+// only a step whose inputs still hold the sentinel polls.  The first 32 U values / positions of step
+// b+1 are requested before step b's update is applied, so a row whose dependencies are long finished
+// streams its k-steps at shared-memory speed, and a row at the head of a dependency chain pays one
+// L2 round trip per link.  All polling is CONVERGENT (whole warp iterates until __all_sync): lanes
+// parked in different spin loops starve the lane whose value has arrived (profiles/r1_lu_notes.md).
+//
+// Publication order: U part, pivot reciprocal and y first (what other rows wait for), the L part
+// (needed by nobody before the next kernel) afterwards.
+#define VJX_FACTOR_WARPS 4
+extern __shared__ double vjx_lu_smem[];
+
+__global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, const double* __restrict__ csr,
+                                                                    const double* __restrict__ b, double scale,
+                                                                    const unsigned char* __restrict__ zero_mask, NRStat* st) {
   const int lane = threadIdx.x & 31;
-  const int n = lu.n;
+  const int warp = threadIdx.x >> 5;
+  const int n_rows = lu.n - lu.n_nol;
+  double* const wsm = vjx_lu_smem + (size_t)warp * lu.rowbuf;
   while (true) {
     unsigned tk = 0;
     if (lane == 0) tk = atomicAdd(&st->ticket_f, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= (unsigned)n) break;
-    const int i = lu.order_f[tk];
+    if (tk >= (unsigned)n_rows) break;
+    const int i = lu.order_f[lu.n_nol + tk];
     const int rb = lu.ptr[i], dg = lu.diag[i], re = lu.ptr[i + 1];
-    double d;
-    if (dg == rb) {
-      // no L part (peeled singletons, leaves): the row is a copy of A's values
-      for (int p = rb + lane; p < re; p += 32) {
-        const int s = lu.src[p];
-        lu.val[p] = s >= 0 ? csr[s] : 0.0;
+    double* w = (re - rb) <= lu.rowbuf ? wsm : lu.scratch + ((size_t)blockIdx.x * VJX_FACTOR_WARPS + warp) * lu.max_lrow;
+    for (int p = rb + lane; p < re; p += 32) {
+      const int s = lu.src[p];
+      w[p - rb] = s >= 0 ? csr[s] : 0.0;
+    }
+    double ysum = 0.0;
+    if (lane == 0) {
+      const int r = lu.perm_r[i];
+      ysum = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
+    }
+    __syncwarp();
+    for (int pb = rb; pb < dg; pb += 32) {
+      const int nb = min(32, dg - pb);
+      int k = 0, ub = 0, ue = 0;
+      long long mb = 0;
+      ull inv_l = 0ULL, yk_l = 0ULL;
+      if (lane < nb) {
+        k = lu.col[pb + lane];
+        ub = lu.kub[pb + lane];
+        mb = lu.upd_ptr[pb + lane];
+        ue = ub + (int)(lu.upd_ptr[pb + lane + 1] - mb);
+        inv_l = ld_poll_u64(lu.inv_diag + k);
+        yk_l = ld_poll_u64(lu.y + k);
       }
-      const int sd = lu.src[dg];
-      d = sd >= 0 ? csr[sd] : 0.0;
-    } else {
-      const bool in_smem = (re - rb) <= VJX_ROWBUF;
-      double* w = in_smem ? wbuf[threadIdx.x >> 5] : lu.val + rb;
-      for (int p = rb + lane; p < re; p += 32) {
-        const int s = lu.src[p];
-        w[p - rb] = s >= 0 ? csr[s] : 0.0;
-      }
-      __syncwarp();
-#ifdef VJX_DEBUG_TS
-      int dbg_slot = 0;
-      const bool dbg = lu.ts && i == n - 1;
-      if (dbg && lane == 0) lu.ts[n + 2 + dbg_slot++] = global_ns();
-#endif
-      for (int pb = rb; pb < dg; pb += VJX_KB) {
-        const int nb = min(VJX_KB, dg - pb);
-        // lane b owns step b of the batch: wait for its row, fetch pivot + bounds + scatter base
-        int ub_l = 0, ue_l = 0;
-        long long mb_l = 0;
-        double inv_l = 0.0;
-        int k = -1;
-        if (lane < nb) {
-          k = lu.col[pb + lane];
-          mb_l = lu.upd_ptr[pb + lane];
-          ub_l = lu.diag[k] + 1;
-          ue_l = lu.ptr[k + 1];
+      // first chunk of step 0
+      int ub_c = __shfl_sync(0xffffffffu, ub, 0), ue_c = __shfl_sync(0xffffffffu, ue, 0);
+      long long mb_c = __shfl_sync(0xffffffffu, mb, 0);
+      ull u_c = 0ULL;
+      int pos_c = 0;
+      if (ub_c + lane < ue_c) { pos_c = lu.upd_pos[mb_c + lane]; u_c = ld_poll_u64(lu.val + ub_c + lane); }
+      for (int bb = 0; bb < nb; ++bb) {
+        // request the first chunk of the next step before this step's dependent work
+        int ub_n = 0, ue_n = 0, pos_n = 0;
+        long long mb_n = 0;
+        ull u_n = 0ULL;
+        if (bb + 1 < nb) {
+          ub_n = __shfl_sync(0xffffffffu, ub, bb + 1);
+          ue_n = __shfl_sync(0xffffffffu, ue, bb + 1);
+          mb_n = __shfl_sync(0xffffffffu, mb, bb + 1);
+          if (ub_n + lane < ue_n) { pos_n = lu.upd_pos[mb_n + lane]; u_n = ld_poll_u64(lu.val + ub_n + lane); }
         }
-        {
-          // convergent poll: the whole warp iterates until every row of the batch is published
-          bool ok = k < 0;
+        ull inv_s = __shfl_sync(0xffffffffu, inv_l, bb), yk_s = __shfl_sync(0xffffffffu, yk_l, bb);
+        if (inv_s == VJX_SENTINEL || yk_s == VJX_SENTINEL) {
+          const int k_s = __shfl_sync(0xffffffffu, k, bb);
           unsigned spins = 0;
           while (true) {
-            if (!ok) ok = ld_relaxed_u32(lu.flag_f + k) == epoch;
-            if (__all_sync(0xffffffffu, ok)) break;
+            if (lane == 0) { inv_s = ld_poll_u64(lu.inv_diag + k_s); yk_s = ld_poll_u64(lu.y + k_s); }
+            inv_s = __shfl_sync(0xffffffffu, inv_s, 0);
+            yk_s = __shfl_sync(0xffffffffu, yk_s, 0);
+            if (inv_s != VJX_SENTINEL && yk_s != VJX_SENTINEL) break;
             if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
           }
         }
-        if (k >= 0) inv_l = __ldcg(lu.inv_diag + k);
-#ifdef VJX_DEBUG_TS
-        if (dbg && lane == 0 && dbg_slot < 4000) lu.ts[n + 2 + dbg_slot++] = global_ns();
-#endif
-        double u0[VJX_KB], u1[VJX_KB];
-        int t0[VJX_KB], t1[VJX_KB];
-#pragma unroll
-        for (int b = 0; b < VJX_KB; ++b) {
-          const int ub = __shfl_sync(0xffffffffu, ub_l, b), ue = __shfl_sync(0xffffffffu, ue_l, b);
-          const long long mb = __shfl_sync(0xffffffffu, mb_l, b);
-          u0[b] = 0.0; u1[b] = 0.0; t0[b] = -1; t1[b] = -1;
-          if (b < nb) {
-            if (ub + lane < ue) { u0[b] = __ldcg(lu.val + ub + lane); t0[b] = lu.upd_pos[mb + lane]; }
-            if (ub + lane + 32 < ue) { u1[b] = __ldcg(lu.val + ub + lane + 32); t1[b] = lu.upd_pos[mb + lane + 32]; }
+        const int kpos = pb + bb - rb;
+        const double l = w[kpos] * bits_f64(inv_s);
+        for (int q0 = ub_c; q0 < ue_c; q0 += 32) {
+          const bool has = q0 + lane < ue_c;
+          if (q0 != ub_c) {
+            u_c = 0ULL;
+            if (has) { pos_c = lu.upd_pos[mb_c + (q0 - ub_c) + lane]; u_c = ld_poll_u64(lu.val + q0 + lane); }
           }
-        }
-#ifdef VJX_DEBUG_TS
-        if (dbg && lane == 0 && dbg_slot < 4000) lu.ts[n + 2 + dbg_slot++] = global_ns() + (u0[0] != 1.2345e300 ? 0 : 1) + (u0[VJX_KB - 1] != 1.2345e300 ? 0 : 1);
-#endif
-#pragma unroll
-        for (int b = 0; b < VJX_KB; ++b) {
-          if (b < nb) {
-            const int ub = __shfl_sync(0xffffffffu, ub_l, b), ue = __shfl_sync(0xffffffffu, ue_l, b);
-            const long long mb = __shfl_sync(0xffffffffu, mb_l, b);
-            const double l = w[pb + b - rb] * __shfl_sync(0xffffffffu, inv_l, b);
-            if (t0[b] >= 0) w[t0[b]] -= l * u0[b];
-            if (t1[b] >= 0) w[t1[b]] -= l * u1[b];
-            for (int q = ub + lane + 64; q < ue; q += 32) w[lu.upd_pos[mb + (q - ub)]] -= l * __ldcg(lu.val + q);
-            __syncwarp();
-            if (lane == 0) w[pb + b - rb] = l;
-            __syncwarp();
+          unsigned spins = 0;
+          while (true) {
+            const bool ok = !has || u_c != VJX_SENTINEL;
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (!ok) u_c = ld_poll_u64(lu.val + q0 + lane);
+            if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
           }
+          if (has) w[pos_c] -= l * bits_f64(u_c);
         }
-#ifdef VJX_DEBUG_TS
-        if (dbg && lane == 0 && dbg_slot < 4000) lu.ts[n + 2 + dbg_slot++] = global_ns();
-#endif
+        __syncwarp();
+        if (lane == 0) {
+          w[kpos] = l;
+          ysum -= l * bits_f64(yk_s);
+        }
+        __syncwarp();
+        ub_c = ub_n; ue_c = ue_n; mb_c = mb_n; u_c = u_n; pos_c = pos_n;
       }
-      __syncwarp();
-      if (in_smem)
-        for (int p = rb + lane; p < re; p += 32) lu.val[p] = w[p - rb];
-      d = w[dg - rb];
     }
-    __syncwarp();
+    const double d = w[dg - rb];
+    for (int p = dg + 1 + lane; p < re; p += 32) st_pub_f64(lu.val + p, w[p - rb]);
     if (lane == 0) {
       if (d == 0.0 || d != d) atomicOr(&st->error, 2);
-      lu.inv_diag[i] = 1.0 / d;
-      st_release_u32(lu.flag_f + i, epoch);
+      st_pub_f64(lu.y + i, ysum);
+      st_pub_f64(lu.inv_diag + i, 1.0 / d);
+      lu.val[dg] = d;
       if (lu.ts) lu.ts[i] = global_ns();
     }
+    for (int p = rb + lane; p < dg; p += 32) lu.val[p] = w[p - rb];
     __syncwarp();
   }
 }
@@ -637,30 +685,12 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Chain tails pass values through shared memory; an entry still holding this quiet-NaN payload has
-// not been produced yet (a computed NaN is the canonical 0x7ff8000000000000).
+// The chain tail of the back solve passes values through shared memory (same sentinel).
 #define VJX_TAIL_MAX 4096
-// The triangular-solve kernels run 1024-thread blocks: the chain tail is walked by ONE block whose
-// warps take the tail rows round-robin, and a row costs a warp ~10 us of (mostly latency) time, so
-// the tail advances at (row time) / (warps per block) per row - 32 warps instead of 8 is a 4x.
+// The back-solve kernel runs 1024-thread blocks: the chain tail is walked by ONE block whose warps
+// take the tail rows round-robin, and a row costs a warp ~10 us of (mostly latency) time, so the tail
+// advances at (row time) / (warps per block) per row - 32 warps instead of 8 is a 4x.
 #define VJX_SOLVE_THREADS 1024
-#ifndef VJX_SMEM_SLEEP
-#define VJX_SMEM_SLEEP 0
-#endif
-#define VJX_SENTINEL 0x7ff8dead0badbeefULL
-
-__device__ __forceinline__ double wait_smem(const double* slot, NRStat* st, int errbit) {
-  const volatile ull* p = reinterpret_cast<const volatile ull*>(slot);
-  unsigned spins = 0;
-  ull bits;
-  while ((bits = *p) == VJX_SENTINEL) {
-    if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); break; }
-#if VJX_SMEM_SLEEP > 0
-    __nanosleep(VJX_SMEM_SLEEP);   // leave the issue slots to the warp that is producing the value
-#endif
-  }
-  return __longlong_as_double((long long)bits);
-}
 
 // Dot product of one row part with already solved unknowns.  `tid` is the thread's index among the
 // STRIDE threads that share the row (lane for a warp, threadIdx.x for a whole block).  Four
@@ -699,102 +729,21 @@ __device__ __forceinline__ double row_dot(const LUDev& lu, int begin, int end, i
   return part;
 }
 
-// Forward solve y = L^-1 P b.  Rows outside the chain tail: one warp per row handed out by ticket in
-// level order, every lane loads its matrix entries first and then waits for exactly the y it needs.
-// Rows of the chain tail [tail_start, n): block 0 alone, its warps taking the rows round-robin in
-// index order and handing y over in shared memory.
-__global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_lsolve(LUDev lu, const double* __restrict__ b, double scale,
-                                                   const unsigned char* __restrict__ zero_mask, NRStat* st) {
-  __shared__ double ytail[VJX_TAIL_MAX];
-  const unsigned epoch = st->epoch;
-  const int lane = threadIdx.x & 31;
-  const int n = lu.n;
-  const int n_bulk = lu.tail_start;
-  const int n_tail = n - lu.tail_start;
-  if (blockIdx.x == 0 && n_tail > 0) {
-    for (int t = threadIdx.x; t < n_tail; t += blockDim.x)
-      reinterpret_cast<ull*>(ytail)[t] = VJX_SENTINEL;
-    __syncthreads();
-    for (int t = threadIdx.x >> 5; t < n_tail; t += (blockDim.x >> 5)) {
-      const int i = n_bulk + t;
-#ifdef VJX_DEBUG_TS
-      long long c_start = clock64(), c_dot = 0, c_sum = 0;
-#endif
-      const int rb = lu.ptr[i], dg = lu.diag[i];
-      double bi = 0.0;
-      if (lane == 0) {
-        const int r = lu.perm_r[i];
-        bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
-      }
-      double part = row_dot<32>(lu, rb, dg, lane, st, 4, [&](int c, double* x) {
-        const int s = c - n_bulk;
-        if (s >= 0) {
-          const ull bits = *reinterpret_cast<const volatile ull*>(ytail + s);
-          *x = __longlong_as_double((long long)bits);
-          return bits != VJX_SENTINEL;
-        }
-        if (ld_relaxed_u32(lu.flag_l + c) != epoch) return false;
-        *x = __ldcg(lu.y + c);
-        return true;
-      });
-#ifdef VJX_DEBUG_TS
-      c_dot = clock64();
-      c_dot = __shfl_sync(0xffffffffu, c_dot, (dg - 1 - rb) & 31);
-#endif
-      if (dg - rb > 1) part = warp_sum(part);
-      else part = __shfl_sync(0xffffffffu, part, 0);
-#ifdef VJX_DEBUG_TS
-      c_sum = clock64();
-#endif
-      if (lane == 0) {
-        const double yi = bi - part;
-        *reinterpret_cast<volatile double*>(ytail + t) = yi;
-#ifdef VJX_DEBUG_TS
-        if (lu.ts) { lu.ts[n + 2 + 4 * t] = (ull)c_start; lu.ts[n + 2 + 4 * t + 1] = (ull)c_dot; lu.ts[n + 2 + 4 * t + 2] = (ull)c_sum; lu.ts[n + 2 + 4 * t + 3] = (ull)clock64(); }
-#endif
-        lu.y[i] = yi;
-        if (lu.ts) lu.ts[i] = global_ns();
-      }
-    }
-    return;
-  }
-  while (true) {
-    unsigned tk = 0;
-    if (lane == 0) tk = atomicAdd(&st->ticket_l, 1u);
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= (unsigned)n_bulk) break;
-    const int i = lu.order_l[tk];
-    const int rb = lu.ptr[i], dg = lu.diag[i];
-    double bi = 0.0;
-    if (lane == 0) {
-      const int r = lu.perm_r[i];
-      bi = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
-    }
-    double part = row_dot<32>(lu, rb, dg, lane, st, 4, [&](int c, double* x) {
-      if (ld_relaxed_u32(lu.flag_l + c) != epoch) return false;
-      *x = __ldcg(lu.y + c);
-      return true;
-    });
-    if (dg - rb > 1) part = warp_sum(part);
-    else part = __shfl_sync(0xffffffffu, part, 0);
-    if (lane == 0) {
-      lu.y[i] = bi - part;
-      st_release_u32(lu.flag_l + i, epoch);
-      if (lu.ts) lu.ts[i] = global_ns();
-    }
-  }
-}
-
-// Back solve x = U^-1 y, scattered through the column permutation.  Here the chain comes first
-// (the trailing block of U): block 0 walks it through shared memory and publishes every x for the
-// wide remainder, which the other blocks solve by ticket.  The last n_long_u blocks each take one
-// very long row (a rail kept as column-singleton pivot: one entry per attached device).
+// Back solve x = U^-1 y, scattered through the column permutation.  The chain comes first (the
+// trailing block of U): block 0 walks rows [tail_start, n) in reverse through shared memory and
+// publishes every x for the wide remainder, which the other blocks solve by ticket in level order,
+// polling x itself.  The last n_long_u blocks each take one very long row (a rail kept as
+// column-singleton pivot: one entry per attached device).
 __global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_usolve(LUDev lu, double* __restrict__ x_out, NRStat* st) {
   __shared__ double xtail[VJX_TAIL_MAX];
-  const unsigned epoch = st->epoch;
   const int lane = threadIdx.x & 31;
   const int n = lu.n;
   const int n_tail = n - lu.tail_start;
+  auto peek_x = [&](int c, double* x) {
+    const ull bits = ld_poll_u64(lu.xp + c);
+    *x = bits_f64(bits);
+    return bits != VJX_SENTINEL;
+  };
   if (blockIdx.x == 0 && n_tail > 0) {
     for (int t = threadIdx.x; t < n_tail; t += blockDim.x)
       reinterpret_cast<ull*>(xtail)[t] = VJX_SENTINEL;
@@ -812,7 +761,7 @@ __global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_usolve(LUDev lu, doubl
       // a tail row's U entries point into the tail
       double part = row_dot<32>(lu, ub, re, lane, st, 8, [&](int c, double* x) {
         const ull bits = *reinterpret_cast<const volatile ull*>(xtail + (n - 1 - c));
-        *x = __longlong_as_double((long long)bits);
+        *x = bits_f64(bits);
         return bits != VJX_SENTINEL;
       });
       if (re - ub > 1) part = warp_sum(part);
@@ -820,9 +769,8 @@ __global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_usolve(LUDev lu, doubl
       if (lane == 0) {
         const double xi = (yi - part) * di;
         *reinterpret_cast<volatile double*>(xtail + t) = xi;
-        lu.xp[i] = xi;
+        st_pub_f64(lu.xp + i, xi);
         x_out[pc] = xi;
-        st_release_u32(lu.flag_u + i, epoch);
         if (lu.ts) lu.ts[i] = global_ns();
       }
     }
@@ -832,17 +780,12 @@ __global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_usolve(LUDev lu, doubl
     double* sh = xtail;
     const int i = lu.long_u[blockIdx.x - (gridDim.x - lu.n_long_u)];
     const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
-    double part = row_dot<VJX_SOLVE_THREADS>(lu, ub, re, threadIdx.x, st, 8, [&](int c, double* x) {
-      if (ld_relaxed_u32(lu.flag_u + c) != epoch) return false;
-      *x = __ldcg(lu.xp + c);
-      return true;
-    });
+    double part = row_dot<VJX_SOLVE_THREADS>(lu, ub, re, threadIdx.x, st, 8, peek_x);
     part = block_sum_256(part, sh);
     if (threadIdx.x == 0) {
       const double xi = (lu.y[i] - part) * lu.inv_diag[i];
-      lu.xp[i] = xi;
+      st_pub_f64(lu.xp + i, xi);
       x_out[lu.perm_c[i]] = xi;
-      st_release_u32(lu.flag_u + i, epoch);
       if (lu.ts) lu.ts[i] = global_ns();
     }
     return;
@@ -861,18 +804,13 @@ __global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_usolve(LUDev lu, doubl
       di = lu.inv_diag[i];
       pc = lu.perm_c[i];
     }
-    double part = row_dot<32>(lu, ub, re, lane, st, 8, [&](int c, double* x) {
-      if (ld_relaxed_u32(lu.flag_u + c) != epoch) return false;
-      *x = __ldcg(lu.xp + c);
-      return true;
-    });
+    double part = row_dot<32>(lu, ub, re, lane, st, 8, peek_x);
     if (re - ub > 1) part = warp_sum(part);
     else part = __shfl_sync(0xffffffffu, part, 0);
     if (lane == 0) {
       const double xi = (yi - part) * di;
-      lu.xp[i] = xi;
+      st_pub_f64(lu.xp + i, xi);
       x_out[pc] = xi;
-      st_release_u32(lu.flag_u + i, epoch);
       if (lu.ts) lu.ts[i] = global_ns();
     }
   }
@@ -1402,15 +1340,16 @@ struct vjx_handle {
   // LU
   bool lu_ready = false;
   VjxSymbolic sym;
-  DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_order_l, lu_order_u, lu_perm_r, lu_perm_c;
+  DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_init, lu_kub, lu_order_u, lu_perm_r, lu_perm_c;
+  DevBuf<double> lu_scratch;
+  int lu_smem_f = 0, lu_grid_load = 0;
   DevBuf<int> lu_order_f, lu_long_u;
   int lu_grid_u = 0;
   DevBuf<long long> lu_upd_ptr;
   DevBuf<int> lu_upd_pos;
-  DevBuf<unsigned> lu_flags;
   DevBuf<double> lu_val, lu_inv, lu_y, lu_xp;
   LUDev lud{};
-  int lu_grid_f = 0, lu_grid_s = 0;
+  int lu_grid_f = 0;
   // transient
   DevBuf<TranScalars> ts;
   DevBuf<double> X, Vpred, Vhist, Vmax, Q_prev, dQdt_prev, Q_prev2, hist_mrc, res_tol_floor, limit_state;
@@ -1851,12 +1790,22 @@ static void launch_residual(vjx_handle* h, const BuildPtrs& b, int check, cudaSt
 
 static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s);
 
+static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr, const double* b, double scale,
+                             const unsigned char* zero_mask, cudaStream_t s) {
+  k_lu_load<<<h->lu_grid_load, 256, 0, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
+  h->launches += 1;
+  if (lud.n > lud.n_nol) {
+    k_lu_rows<<<h->lu_grid_f, 32 * VJX_FACTOR_WARPS, h->lu_smem_f, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
+    h->launches += 1;
+  }
+}
+
+// Refactorise on the fixed pattern with the forward solve folded in, then back solve into x.
 static void launch_lu(vjx_handle* h, const double* csr, const double* b, double scale, const unsigned char* zero_mask,
                       double* x, cudaStream_t s) {
-  k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, csr, h->st.p);
-  k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(h->lud, b, scale, zero_mask, h->st.p);
+  launch_lu_factor(h, h->lud, csr, b, scale, zero_mask, s);
   k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(h->lud, x, h->st.p);
-  h->launches += 3;
+  h->launches += 1;
 }
 
 static UpdateArgs make_update_args(vjx_handle* h, double* X, const double* limit_in, const double* limit_out) {
@@ -1888,11 +1837,11 @@ static int launch_nr_iteration(vjx_handle* h, const BuildPtrs& b, double* X, cud
 
 static int upload_symbolic(vjx_handle* h) {
   VjxSymbolic& S = h->sym;
+  const int n = S.n;
   CK(h->lu_ptr.upload(S.lu_ptr));
   CK(h->lu_col.upload(S.lu_col));
   CK(h->lu_diag.upload(S.lu_diag));
   CK(h->lu_src.upload(S.lu_src));
-  CK(h->lu_order_l.upload(S.order_l));
   CK(h->lu_order_u.upload(S.order_u));
   CK(h->lu_perm_r.upload(S.perm_r));
   CK(h->lu_perm_c.upload(S.perm_c));
@@ -1903,19 +1852,45 @@ static int upload_symbolic(vjx_handle* h) {
     if (up.empty()) up.push_back(0);
     CK(h->lu_upd_pos.upload(up));
   }
+  // k_lu_load program and the per-L-entry start of U(k,:); rows without an L part come first in order_f
+  int n_nol = 0, max_lrow = 0;
+  {
+    std::vector<int> init((size_t)std::max<int64_t>(S.nnz_lu, 1), -3), kub((size_t)std::max<int64_t>(S.nnz_lu, 1), 0);
+    for (int i = 0; i < n; ++i) {
+      const int rb = S.lu_ptr[i], dg = S.lu_diag[i], re = S.lu_ptr[i + 1];
+      if (dg == rb) {
+        ++n_nol;
+        for (int p = rb; p < re; ++p) init[p] = S.lu_src[p] >= 0 ? S.lu_src[p] : -1;
+      } else {
+        max_lrow = std::max(max_lrow, re - rb);
+        for (int p = rb; p < dg; ++p) kub[p] = S.lu_diag[S.lu_col[p]] + 1;
+        for (int p = dg; p < re; ++p) init[p] = -2;
+      }
+    }
+    for (int t = 0; t < n; ++t) {
+      const int i = S.order_f[t];
+      const bool nol = S.lu_diag[i] == S.lu_ptr[i];
+      if (nol != (t < n_nol)) return fail(VJX_ERR_INVALID, "factorisation order does not start with the rows without an L part");
+    }
+    CK(h->lu_init.upload(init));
+    CK(h->lu_kub.upload(kub));
+  }
   CK(h->lu_val.alloc((size_t)S.nnz_lu));
-  CK(h->lu_inv.alloc(S.n));
-  CK(h->lu_y.alloc(S.n));
-  CK(h->lu_xp.alloc(S.n));
-  CK(h->lu_flags.alloc((size_t)3 * S.n));
+  CK(h->lu_inv.alloc(n));
+  CK(h->lu_y.alloc(n));
+  CK(h->lu_xp.alloc(n));
   LUDev& L = h->lud;
-  L.n = S.n;
+  L.n = n;
+  L.nnz = S.nnz_lu;
   L.ptr = h->lu_ptr.p; L.col = h->lu_col.p; L.diag = h->lu_diag.p; L.src = h->lu_src.p;
-  L.order_l = h->lu_order_l.p; L.order_u = h->lu_order_u.p; L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
+  L.init = h->lu_init.p; L.kub = h->lu_kub.p;
+  L.order_u = h->lu_order_u.p; L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
   L.ts = nullptr;
   L.upd_ptr = h->lu_upd_ptr.p; L.upd_pos = h->lu_upd_pos.p;
   CK(h->lu_order_f.upload(S.order_f));
   L.order_f = h->lu_order_f.p;
+  L.n_nol = n_nol;
+  L.max_lrow = max_lrow;
   L.tail_start = S.tail_start;
   {
     std::vector<int> lg(S.long_u);
@@ -1926,23 +1901,34 @@ static int upload_symbolic(vjx_handle* h) {
   L.n_long_u = (int)S.long_u.size();
   L.n_bulk_u = (int)S.order_u.size();
   L.val = h->lu_val.p; L.inv_diag = h->lu_inv.p; L.y = h->lu_y.p; L.xp = h->lu_xp.p;
-  L.flag_f = h->lu_flags.p; L.flag_l = h->lu_flags.p + S.n; L.flag_u = h->lu_flags.p + 2 * (size_t)S.n;
-  // persistent grids: every CTA must be resident (dependency waits), so size from occupancy
-  int occ_f = 1, occ_s = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_lu_factor, 256, 0));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_lu_lsolve, VJX_SOLVE_THREADS, 0));
-  int occ_u = 1;
+  // k_lu_rows: the shared-memory working vector of a warp holds the longest row with an L part, up to
+  // a cap that keeps at least two blocks per SM; longer rows go through a global scratch.
+  const int kRowbufCap = 6144;   // doubles per warp: 4 warps x 48 KB = 192 KB per block at the cap
+  L.rowbuf = std::max(64, std::min(kRowbufCap, (max_lrow + 31) / 32 * 32));
+  if (L.rowbuf > 2048 && max_lrow > L.rowbuf) L.rowbuf = 2048;   // scratch rows exist anyway: keep occupancy
+  h->lu_smem_f = L.rowbuf * VJX_FACTOR_WARPS * (int)sizeof(double);
+  CK(cudaFuncSetAttribute(k_lu_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lu_smem_f));
+  int occ_f = 1, occ_u = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_lu_rows, 32 * VJX_FACTOR_WARPS, h->lu_smem_f));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_lu_usolve, VJX_SOLVE_THREADS, 0));
-  occ_s = std::max(1, std::min(occ_s, occ_u));
-  long long warps_needed = S.n;
+  occ_f = std::max(1, occ_f);
+  occ_u = std::max(1, occ_u);
+  const long long n_lrows = n - n_nol;
+  h->lu_grid_f = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_f,
+                                                                  (n_lrows + VJX_FACTOR_WARPS - 1) / VJX_FACTOR_WARPS));
+  L.scratch = nullptr;
+  if (max_lrow > L.rowbuf) {
+    CK(h->lu_scratch.alloc((size_t)h->lu_grid_f * VJX_FACTOR_WARPS * (size_t)max_lrow));
+    L.scratch = h->lu_scratch.p;
+  }
+  h->lu_grid_load = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 8, (S.nnz_lu + 255) / 256));
+  // back solve: one block per SM slot, minus room for the long-row blocks; block 0 is dedicated to the
+  // chain tail, the other blocks take the tickets
   const int wps = VJX_SOLVE_THREADS / 32;
-  h->lu_grid_f = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * std::min(occ_f, 4), (warps_needed + 7) / 8));
-  // one block per SM slot, minus room for the long-row blocks, so that every block is resident
-  h->lu_grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_s - (long long)S.long_u.size(),
-                                                                  (warps_needed + wps - 1) / wps));
-  // block 0 of the solve kernels is dedicated to the chain tail; the other blocks take the tickets
-  if (S.tail_start < S.n && h->lu_grid_s < 2) h->lu_grid_s = 2;
-  h->lu_grid_u = h->lu_grid_s + (int)S.long_u.size();
+  int grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_u - (long long)S.long_u.size(),
+                                                                 ((long long)n + wps - 1) / wps));
+  if (S.tail_start < n && grid_s < 2) grid_s = 2;
+  h->lu_grid_u = grid_s + (int)S.long_u.size();
   h->lu_ready = true;
   return VJX_OK;
 }
@@ -2437,7 +2423,7 @@ __global__ void k_stamp_now(ull* out) { *out = global_ns(); }
 // dependency chain spends its time; never called by the product path.
 extern "C" int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* level_out, vjx_stream stream) {
   if (!h || !h->X.p || !h->lu_ready) return fail(VJX_ERR_INVALID, "run a transient first");
-  if (phase < 3 || phase > 5) return fail(VJX_ERR_INVALID, "phase must be 3, 4 or 5");
+  if (phase != 3 && phase != 5) return fail(VJX_ERR_INVALID, "phase must be 3 (factor + forward solve) or 5 (back solve)");
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const int n = h->sym.n;
@@ -2445,38 +2431,15 @@ extern "C" int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* le
   CK(ts.alloc((size_t)n + 1 + 4100));
   LUDev lud = h->lud;
   k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
-  if (phase >= 4) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p);
-  if (phase >= 5) k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+  if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, s);
   lud.ts = ts.p;
+  CK(cudaMemsetAsync(ts.p, 0, sizeof(ull) * ((size_t)n + 1), s));
   k_stamp_now<<<1, 1, 0, s>>>(ts.p + n);
-  if (phase == 3) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(lud, h->csr.p, h->st.p);
-  if (phase == 4) k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+  if (phase == 3) launch_lu_factor(h, lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, s);
   if (phase == 5) k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(lud, h->delta.p, h->st.p);
   std::vector<ull> hts((size_t)n + 1);
   CK(cudaStreamSynchronize(s));
   CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
-#ifdef VJX_DEBUG_TS
-  if (phase == 4) {
-    const int nt = n - h->sym.tail_start;
-    std::vector<ull> dbg(4100);
-    CK(cudaMemcpy(dbg.data(), ts.p + n + 1, sizeof(ull) * 4100, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "lsolve tail rows (SM cycles relative to previous row's publish): t, start, dot done, summed, published, Llen\n");
-    for (int t = std::max(1, nt - 30); t < nt && 4 * t + 4 < 4099; ++t) {
-      long long base = (long long)dbg[1 + 4 * (t - 1) + 3];
-      fprintf(stderr, "  %4d %8lld %8lld %8lld %8lld  %d\n", t, (long long)dbg[1 + 4 * t] - base, (long long)dbg[1 + 4 * t + 1] - base,
-              (long long)dbg[1 + 4 * t + 2] - base, (long long)dbg[1 + 4 * t + 3] - base,
-              h->sym.lu_diag[h->sym.tail_start + t] - h->sym.lu_ptr[h->sym.tail_start + t]);
-    }
-  }
-  if (phase == 3) {
-    std::vector<ull> dbg(4100);
-    CK(cudaMemcpy(dbg.data(), ts.p + n + 1, sizeof(ull) * 4100, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "last-row batch trace (us since kernel start): start, then per batch [flags, loaded, applied]\n");
-    for (int k = 1; k < 4000 && dbg[k]; ++k)
-      fprintf(stderr, "%s%.2f", ((k - 2) % 3 == 0 && k > 1) ? "\n  " : " ", ((long long)dbg[k] - (long long)hts[n]) / 1e3);
-    fprintf(stderr, "\n");
-  }
-#endif
   for (int i = 0; i < n; ++i) {
     ns_out[i] = (double)((long long)hts[i] - (long long)hts[n]);
     if (level_out) level_out[i] = phase == 5 ? h->sym.level_u[i] : h->sym.level_l[i];
@@ -2504,8 +2467,7 @@ extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg
     if (phase == 3 || phase == 4 || phase == 5) {
       // each LU phase needs a fresh epoch and the preceding phases' results
       k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
-      if (phase >= 4) k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p);
-      if (phase >= 5) k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p);
+      if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, s);
     }
     CK(cudaEventRecord(e0, s));
     l0 = h->launches;
@@ -2513,8 +2475,8 @@ extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg
       case 0: { int rc = launch_eval(h, b, s); if (rc) return rc; break; }
       case 1: launch_stamp(h, h->csr.p, 1, s); break;
       case 2: launch_residual(h, b, 0, s); break;
-      case 3: k_lu_factor<<<h->lu_grid_f, 256, 0, s>>>(h->lud, h->csr.p, h->st.p); h->launches++; break;
-      case 4: k_lu_lsolve<<<h->lu_grid_s, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->f.p, -1.0, h->noi_row_mask.p, h->st.p); h->launches++; break;
+      case 3: launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, s); break;
+      case 4: break;   // the forward solve is part of the factorisation kernels (phase 3)
       case 5: k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->delta.p, h->st.p); h->launches++; break;
       case 6: k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua); h->launches++; break;
       default: return fail(VJX_ERR_INVALID, "unknown phase");
