@@ -87,7 +87,6 @@ struct LUDev {
   const int* perm_c;
   const int* order_f;          // all rows by L-dependency level; the first n_nol have no L part
   int n_nol;                   // rows without an L part (finished by k_lu_load)
-  int rowbuf;                  // shared-memory working vector per warp of k_lu_rows (doubles)
   int max_lrow;                // longest row with an L part
   double* scratch;             // per-warp global working vectors, only when max_lrow > rowbuf
   int tail_start;              // rows [tail_start, n): chain tail of the back solve, one thread block
@@ -570,23 +569,26 @@ __global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restr
 // Publication order: U part, pivot reciprocal and y first (what other rows wait for), the L part
 // (needed by nobody before the next kernel) afterwards.
 #define VJX_FACTOR_WARPS 4
+#ifndef VJX_UG
+#define VJX_UG 4   // chunks of 32 U entries requested together per k-step
+#endif
 extern __shared__ double vjx_lu_smem[];
 
 __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, const double* __restrict__ csr,
                                                                     const double* __restrict__ b, double scale,
-                                                                    const unsigned char* __restrict__ zero_mask, NRStat* st) {
+                                                                    const unsigned char* __restrict__ zero_mask, NRStat* st,
+                                                                    unsigned* ticket, int t_begin, int t_end, int rowbuf) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int n_rows = lu.n - lu.n_nol;
-  double* const wsm = vjx_lu_smem + (size_t)warp * lu.rowbuf;
+  double* const wsm = vjx_lu_smem + (size_t)warp * rowbuf;
   while (true) {
     unsigned tk = 0;
-    if (lane == 0) tk = atomicAdd(&st->ticket_f, 1u);
+    if (lane == 0) tk = atomicAdd(ticket, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= (unsigned)n_rows) break;
-    const int i = lu.order_f[lu.n_nol + tk];
+    if (tk >= (unsigned)(t_end - t_begin)) break;
+    const int i = lu.order_f[t_begin + tk];
     const int rb = lu.ptr[i], dg = lu.diag[i], re = lu.ptr[i + 1];
-    double* w = (re - rb) <= lu.rowbuf ? wsm : lu.scratch + ((size_t)blockIdx.x * VJX_FACTOR_WARPS + warp) * lu.max_lrow;
+    double* w = (re - rb) <= rowbuf ? wsm : lu.scratch + ((size_t)blockIdx.x * VJX_FACTOR_WARPS + warp) * lu.max_lrow;
     for (int p = rb + lane; p < re; p += 32) {
       const int s = lu.src[p];
       w[p - rb] = s >= 0 ? csr[s] : 0.0;
@@ -610,22 +612,34 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
         inv_l = ld_poll_u64(lu.inv_diag + k);
         yk_l = ld_poll_u64(lu.y + k);
       }
-      // first chunk of step 0
+      // first group (VJX_UG chunks of 32 U entries) of step 0
       int ub_c = __shfl_sync(0xffffffffu, ub, 0), ue_c = __shfl_sync(0xffffffffu, ue, 0);
       long long mb_c = __shfl_sync(0xffffffffu, mb, 0);
-      ull u_c = 0ULL;
-      int pos_c = 0;
-      if (ub_c + lane < ue_c) { pos_c = lu.upd_pos[mb_c + lane]; u_c = ld_poll_u64(lu.val + ub_c + lane); }
+      ull u_c[VJX_UG];
+      int pos_c[VJX_UG];
+#pragma unroll
+      for (int g = 0; g < VJX_UG; ++g) {
+        u_c[g] = 0ULL; pos_c[g] = 0;
+        const int q = ub_c + g * 32 + lane;
+        if (q < ue_c) { pos_c[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_c[g] = ld_poll_u64(lu.val + q); }
+      }
       for (int bb = 0; bb < nb; ++bb) {
-        // request the first chunk of the next step before this step's dependent work
-        int ub_n = 0, ue_n = 0, pos_n = 0;
+        // request the first group of the next step before this step's dependent work
+        int ub_n = 0, ue_n = 0;
         long long mb_n = 0;
-        ull u_n = 0ULL;
+        ull u_n[VJX_UG];
+        int pos_n[VJX_UG];
+#pragma unroll
+        for (int g = 0; g < VJX_UG; ++g) { u_n[g] = 0ULL; pos_n[g] = 0; }
         if (bb + 1 < nb) {
           ub_n = __shfl_sync(0xffffffffu, ub, bb + 1);
           ue_n = __shfl_sync(0xffffffffu, ue, bb + 1);
           mb_n = __shfl_sync(0xffffffffu, mb, bb + 1);
-          if (ub_n + lane < ue_n) { pos_n = lu.upd_pos[mb_n + lane]; u_n = ld_poll_u64(lu.val + ub_n + lane); }
+#pragma unroll
+          for (int g = 0; g < VJX_UG; ++g) {
+            const int q = ub_n + g * 32 + lane;
+            if (q < ue_n) { pos_n[g] = lu.upd_pos[mb_n + (q - ub_n)]; u_n[g] = ld_poll_u64(lu.val + q); }
+          }
         }
         ull inv_s = __shfl_sync(0xffffffffu, inv_l, bb), yk_s = __shfl_sync(0xffffffffu, yk_l, bb);
         if (inv_s == VJX_SENTINEL || yk_s == VJX_SENTINEL) {
@@ -641,20 +655,29 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
         }
         const int kpos = pb + bb - rb;
         const double l = w[kpos] * bits_f64(inv_s);
-        for (int q0 = ub_c; q0 < ue_c; q0 += 32) {
-          const bool has = q0 + lane < ue_c;
+        for (int q0 = ub_c; q0 < ue_c; q0 += 32 * VJX_UG) {
           if (q0 != ub_c) {
-            u_c = 0ULL;
-            if (has) { pos_c = lu.upd_pos[mb_c + (q0 - ub_c) + lane]; u_c = ld_poll_u64(lu.val + q0 + lane); }
+#pragma unroll
+            for (int g = 0; g < VJX_UG; ++g) {
+              u_c[g] = 0ULL;
+              const int q = q0 + g * 32 + lane;
+              if (q < ue_c) { pos_c[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_c[g] = ld_poll_u64(lu.val + q); }
+            }
           }
           unsigned spins = 0;
           while (true) {
-            const bool ok = !has || u_c != VJX_SENTINEL;
+            bool ok = true;
+#pragma unroll
+            for (int g = 0; g < VJX_UG; ++g) {
+              const int q = q0 + g * 32 + lane;
+              if (q < ue_c && u_c[g] == VJX_SENTINEL) { u_c[g] = ld_poll_u64(lu.val + q); ok = false; }
+            }
             if (__all_sync(0xffffffffu, ok)) break;
-            if (!ok) u_c = ld_poll_u64(lu.val + q0 + lane);
             if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
           }
-          if (has) w[pos_c] -= l * bits_f64(u_c);
+#pragma unroll
+          for (int g = 0; g < VJX_UG; ++g)
+            if (q0 + g * 32 + lane < ue_c) w[pos_c[g]] -= l * bits_f64(u_c[g]);
         }
         __syncwarp();
         if (lane == 0) {
@@ -662,7 +685,9 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
           ysum -= l * bits_f64(yk_s);
         }
         __syncwarp();
-        ub_c = ub_n; ue_c = ue_n; mb_c = mb_n; u_c = u_n; pos_c = pos_n;
+        ub_c = ub_n; ue_c = ue_n; mb_c = mb_n;
+#pragma unroll
+        for (int g = 0; g < VJX_UG; ++g) { u_c[g] = u_n[g]; pos_c[g] = pos_n[g]; }
       }
     }
     const double d = w[dg - rb];
@@ -1342,7 +1367,10 @@ struct vjx_handle {
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_init, lu_kub, lu_order_u, lu_perm_r, lu_perm_c;
   DevBuf<double> lu_scratch;
-  int lu_smem_f = 0, lu_grid_load = 0;
+  int lu_grid_load = 0;
+  // k_lu_rows runs as one or two launches over consecutive ranges of order_f (wide low levels with a
+  // small working vector and many warps per SM, then the narrow high levels with long rows)
+  int lu_nseg = 0, lu_seg_t0[2] = {0, 0}, lu_seg_t1[2] = {0, 0}, lu_seg_rowbuf[2] = {0, 0}, lu_seg_grid[2] = {0, 0};
   DevBuf<int> lu_order_f, lu_long_u;
   int lu_grid_u = 0;
   DevBuf<long long> lu_upd_ptr;
@@ -1794,8 +1822,10 @@ static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr,
                              const unsigned char* zero_mask, cudaStream_t s) {
   k_lu_load<<<h->lu_grid_load, 256, 0, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
   h->launches += 1;
-  if (lud.n > lud.n_nol) {
-    k_lu_rows<<<h->lu_grid_f, 32 * VJX_FACTOR_WARPS, h->lu_smem_f, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
+  for (int g = 0; g < h->lu_nseg; ++g) {
+    k_lu_rows<<<h->lu_seg_grid[g], 32 * VJX_FACTOR_WARPS, h->lu_seg_rowbuf[g] * VJX_FACTOR_WARPS * sizeof(double), s>>>(
+        lud, csr, b, scale, zero_mask, h->st.p, g == 0 ? &h->st.p->ticket_f : &h->st.p->ticket_l, h->lu_seg_t0[g],
+        h->lu_seg_t1[g], h->lu_seg_rowbuf[g]);
     h->launches += 1;
   }
 }
@@ -1901,26 +1931,59 @@ static int upload_symbolic(vjx_handle* h) {
   L.n_long_u = (int)S.long_u.size();
   L.n_bulk_u = (int)S.order_u.size();
   L.val = h->lu_val.p; L.inv_diag = h->lu_inv.p; L.y = h->lu_y.p; L.xp = h->lu_xp.p;
-  // k_lu_rows: the shared-memory working vector of a warp holds the longest row with an L part, up to
-  // a cap that keeps at least two blocks per SM; longer rows go through a global scratch.
-  const int kRowbufCap = 6144;   // doubles per warp: 4 warps x 48 KB = 192 KB per block at the cap
-  L.rowbuf = std::max(64, std::min(kRowbufCap, (max_lrow + 31) / 32 * 32));
-  if (L.rowbuf > 2048 && max_lrow > L.rowbuf) L.rowbuf = 2048;   // scratch rows exist anyway: keep occupancy
-  h->lu_smem_f = L.rowbuf * VJX_FACTOR_WARPS * (int)sizeof(double);
-  CK(cudaFuncSetAttribute(k_lu_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lu_smem_f));
-  int occ_f = 1, occ_u = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_lu_rows, 32 * VJX_FACTOR_WARPS, h->lu_smem_f));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_lu_usolve, VJX_SOLVE_THREADS, 0));
-  occ_f = std::max(1, occ_f);
-  occ_u = std::max(1, occ_u);
-  const long long n_lrows = n - n_nol;
-  h->lu_grid_f = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_f,
-                                                                  (n_lrows + VJX_FACTOR_WARPS - 1) / VJX_FACTOR_WARPS));
-  L.scratch = nullptr;
-  if (max_lrow > L.rowbuf) {
-    CK(h->lu_scratch.alloc((size_t)h->lu_grid_f * VJX_FACTOR_WARPS * (size_t)max_lrow));
-    L.scratch = h->lu_scratch.p;
+  // k_lu_rows: the shared-memory working vector of a warp holds the longest row of its range, up to a
+  // cap; longer rows go through a global scratch.  When the long rows would cost occupancy (> 1024
+  // entries), the wide low levels get their own launch with a small vector and many warps per SM.
+  {
+    const int kRowbufCap = 6144;   // doubles per warp: 4 warps x 48 KB = 192 KB per block at the cap
+    auto rowlen = [&](int t) { const int i = S.order_f[t]; return S.lu_ptr[i + 1] - S.lu_ptr[i]; };
+    int n_cut = n;
+    if (max_lrow > 1024) {
+      std::vector<int> cl(S.n_levels_l, 0);
+      for (int i = 0; i < n; ++i) cl[S.level_l[i]]++;
+      int lcut = S.n_levels_l;
+      while (lcut > 1 && cl[lcut - 1] <= 128) --lcut;
+      n_cut = n_nol;
+      while (n_cut < n && S.level_l[S.order_f[n_cut]] < lcut) ++n_cut;
+      if (n_cut - n_nol < 2048 || n_cut == n) n_cut = n;
+    }
+    h->lu_nseg = 0;
+    int bounds[3] = {n_nol, n_cut, n};
+    int max_grid = 1;
+    for (int sgi = 0; sgi < 2; ++sgi) {
+      const int t0 = bounds[sgi], t1 = bounds[sgi + 1];
+      if (t1 <= t0) continue;
+      std::vector<int> lens;
+      lens.reserve(t1 - t0);
+      for (int t = t0; t < t1; ++t) lens.push_back(rowlen(t));
+      std::sort(lens.begin(), lens.end());
+      int want = lens.back();
+      // a handful of outliers in a wide range should not set the vector for everyone: they use the scratch
+      if (t1 - t0 >= 4096) want = std::max(lens[(size_t)((lens.size() - 1) * 0.999)], std::min(want, 512));
+      const int rowbuf = std::max(64, std::min(kRowbufCap, (want + 31) / 32 * 32));
+      const int smem = rowbuf * VJX_FACTOR_WARPS * (int)sizeof(double);
+      int occ = 1;
+      CK(cudaFuncSetAttribute(k_lu_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kRowbufCap * VJX_FACTOR_WARPS * (int)sizeof(double)));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lu_rows, 32 * VJX_FACTOR_WARPS, smem));
+      occ = std::max(1, occ);
+      const int s_i = h->lu_nseg++;
+      h->lu_seg_t0[s_i] = t0;
+      h->lu_seg_t1[s_i] = t1;
+      h->lu_seg_rowbuf[s_i] = rowbuf;
+      h->lu_seg_grid[s_i] = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ,
+                                                     ((long long)(t1 - t0) + VJX_FACTOR_WARPS - 1) / VJX_FACTOR_WARPS));
+      max_grid = std::max(max_grid, h->lu_seg_grid[s_i]);
+    }
+    L.scratch = nullptr;
+    if (max_lrow > 0) {
+      CK(h->lu_scratch.alloc((size_t)max_grid * VJX_FACTOR_WARPS * (size_t)max_lrow));
+      L.scratch = h->lu_scratch.p;
+    }
   }
+  int occ_u = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_lu_usolve, VJX_SOLVE_THREADS, 0));
+  occ_u = std::max(1, occ_u);
   h->lu_grid_load = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 8, (S.nnz_lu + 255) / 256));
   // back solve: one block per SM slot, minus room for the long-row blocks; block 0 is dedicated to the
   // chain tail, the other blocks take the tickets
