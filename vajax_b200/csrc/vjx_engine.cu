@@ -89,6 +89,13 @@ struct LUDev {
   int n_nol;                   // rows without an L part (finished by k_lu_load)
   int max_lrow;                // longest row with an L part
   double* scratch;             // per-warp global working vectors, only when max_lrow > rowbuf
+  // Dense trailing block: rows [dense_start, n) stop their row updates at column dense_start and hand
+  // the rest (+ their partial y in column n_dense) to k_lu_dense_tail as a dense n_dense x (n_dense+1)
+  // row-major matrix.
+  int dense_start, n_dense;
+  int dbg;                     // timing experiments only (VJX_DT_DBG), 0 in production
+  const int* dense_lstop;      // per dense row: first position of the row whose column is >= dense_start
+  double* dense;
   int tail_start;              // rows [tail_start, n): chain tail of the back solve, one thread block
   const int* long_u;           // rows with a very long U part: one thread block each (last blocks of the grid)
   int n_long_u, n_bulk_u;      // order_u holds n_bulk_u rows
@@ -533,6 +540,7 @@ __global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restr
     else if (c == -1) lu.val[p] = 0.0;
     else if (c == -2) lu.val[p] = sent;
   }
+  for (long long p = t0; p < (long long)lu.n_dense * (lu.n_dense + 1); p += nt) lu.dense[p] = 0.0;
   for (long long i = t0; i < lu.n; i += nt) {
     lu.xp[i] = sent;
     const int dg = lu.diag[i];
@@ -599,8 +607,10 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
       ysum = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
     }
     __syncwarp();
-    for (int pb = rb; pb < dg; pb += 32) {
-      const int nb = min(32, dg - pb);
+    const bool dense_row = i >= lu.dense_start;
+    const int lend = dense_row ? lu.dense_lstop[i - lu.dense_start] : dg;
+    for (int pb = rb; pb < lend; pb += 32) {
+      const int nb = min(32, lend - pb);
       int k = 0, ub = 0, ue = 0;
       long long mb = 0;
       ull inv_l = 0ULL, yk_l = 0ULL;
@@ -677,18 +687,27 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
           }
 #pragma unroll
           for (int g = 0; g < VJX_UG; ++g)
-            if (q0 + g * 32 + lane < ue_c) w[pos_c[g]] -= l * bits_f64(u_c[g]);
+            if (q0 + g * 32 + lane < ue_c) w[pos_c[g]] = __fma_rn(-l, bits_f64(u_c[g]), w[pos_c[g]]);
         }
         __syncwarp();
         if (lane == 0) {
           w[kpos] = l;
-          ysum -= l * bits_f64(yk_s);
+          ysum = __fma_rn(-l, bits_f64(yk_s), ysum);
         }
         __syncwarp();
         ub_c = ub_n; ue_c = ue_n; mb_c = mb_n;
 #pragma unroll
         for (int g = 0; g < VJX_UG; ++g) { u_c[g] = u_n[g]; pos_c[g] = pos_n[g]; }
       }
+    }
+    if (dense_row) {
+      // the part of the row inside the dense trailing block goes to k_lu_dense_tail, nobody waits for it
+      double* srow = lu.dense + (size_t)(i - lu.dense_start) * (lu.n_dense + 1);
+      for (int p = lend + lane; p < re; p += 32) srow[lu.col[p] - lu.dense_start] = w[p - rb];
+      if (lane == 0) srow[lu.n_dense] = ysum;
+      for (int p = rb + lane; p < lend; p += 32) lu.val[p] = w[p - rb];
+      __syncwarp();
+      continue;
     }
     const double d = w[dg - rb];
     for (int p = dg + 1 + lane; p < re; p += 32) st_pub_f64(lu.val + p, w[p - rb]);
@@ -703,6 +722,179 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
     __syncwarp();
   }
 }
+
+// Dense trailing block.  The last rows of the elimination order form a near-dense block whose rows
+// depend on each other one after the other (118 single-row levels at c6288 size): walked row by row
+// through global memory every link costs an L2 round trip (~1.2 us).  Here ONE thread block holds the
+// whole block in REGISTERS (10 x 5 doubles per thread, 512 threads: 159 rows + the y column), warp w
+// owning rows w, w+16, ... and lane l owning columns l, l+32, ..., and runs the right-looking
+// elimination with one __syncthreads per pivot: the pivot row and the pivot column travel through a
+// double-buffered shared-memory line.  Every entry receives its updates in ascending pivot order, so
+// the values are those of the row algorithm (both use fused multiply-add).  y rides along as column n_dense.  The block is
+// then spilled to shared memory once and the back substitution of these rows runs on it
+// (column-oriented, one barrier per unknown), publishing x for the rest of the back solve.
+#define VJX_DT_THREADS 512
+#define VJX_DT_R 10
+#define VJX_DT_C 5
+#define VJX_DT_MAX 159
+#define VJX_DT_LDS 161
+#define VJX_DT_SMEM (160 * VJX_DT_LDS * 8)
+#define VJX_DT_UPDATE_ROW(A2, BC)                                                                  \
+  {                                                                                                \
+    const int i_ = wi + 16 * (A2);                                                                 \
+    const double nl_ = i_ < T ? -(lc[i_] * inv) : 0.0;                                             \
+    if (act0) r[A2][BC] = __fma_rn(nl_, u[BC], r[A2][BC]);                                         \
+    _Pragma("unroll") for (int b = (BC) + 1; b < VJX_DT_C; ++b) r[A2][b] = __fma_rn(nl_, u[b], r[A2][b]); \
+  }
+#define VJX_DT_PUBLISH_ROW(A2, BC, LP)                                                             \
+  {                                                                                                \
+    _Pragma("unroll") for (int b = (BC); b < VJX_DT_C; ++b) urn[lane + 32 * b] = r[A2][b];         \
+    if (lane == (LP)) {                                                                            \
+      const double piv = r[A2][BC];                                                                \
+      if (piv == 0.0 || piv != piv) bad = true;                                                    \
+      urn[160] = 1.0 / piv;                                                                        \
+    }                                                                                              \
+  }
+template <int A>
+__device__ __forceinline__ void vjx_dt_panel(double (&r)[VJX_DT_R][VJX_DT_C], double* urow, double* lcol, const int T,
+                                             const int wi, const int lane, bool& bad, const int dbg) {
+  {
+    constexpr int bcol = A >> 1;
+    for (int w = 0; w < 16; ++w) {
+      const int k = 16 * A + w;
+      if (k >= T) return;
+      const double* const ur = urow + (k & 1) * 192;
+      const double* const lc = lcol + (k & 1) * 160;
+      double* const urn = urow + ((k + 1) & 1) * 192;
+      double* const lcn = lcol + ((k + 1) & 1) * 160;
+      const int lpiv = 16 * (A & 1) + w;
+      __syncthreads();
+      if (dbg == 1) continue;
+      const double inv = ur[160];
+      double u[VJX_DT_C];
+#pragma unroll
+      for (int b = bcol; b < VJX_DT_C; ++b) u[b] = ur[lane + 32 * b];
+      const bool act0 = lane > lpiv;   // inside the pivot's column block only the columns right of it
+      const bool has_next = k + 1 < T;
+      if (w < 15) {
+        // next pivot: row 16 A + w + 1 = register row A of warp w + 1, same column block
+        if (wi == w + 1) {
+          VJX_DT_UPDATE_ROW(A, bcol)
+          if (has_next) VJX_DT_PUBLISH_ROW(A, bcol, lpiv + 1)
+        } else if (wi > w + 1) {
+          VJX_DT_UPDATE_ROW(A, bcol)
+        }
+#pragma unroll
+        for (int a2 = A + 1; a2 < VJX_DT_R; ++a2) VJX_DT_UPDATE_ROW(a2, bcol)
+        if (has_next && lane == lpiv + 1) {
+#pragma unroll
+          for (int a2 = A; a2 < VJX_DT_R; ++a2) lcn[wi + 16 * a2] = r[a2][bcol];
+        }
+      } else if constexpr (A + 1 < VJX_DT_R) {
+        // last pivot of the panel: the next one is register row A + 1 of warp 0
+        constexpr int An = A + 1;
+        constexpr int bn = An >> 1;
+        if (wi == 0) {
+          VJX_DT_UPDATE_ROW(An, bcol)
+          if (has_next) VJX_DT_PUBLISH_ROW(An, bn, 16 * (An & 1))
+#pragma unroll
+          for (int a2 = An + 1; a2 < VJX_DT_R; ++a2) VJX_DT_UPDATE_ROW(a2, bcol)
+        } else {
+#pragma unroll
+          for (int a2 = An; a2 < VJX_DT_R; ++a2) VJX_DT_UPDATE_ROW(a2, bcol)
+        }
+        if (has_next && lane == 16 * (An & 1)) {
+#pragma unroll
+          for (int a2 = An; a2 < VJX_DT_R; ++a2) lcn[wi + 16 * a2] = r[a2][bn];
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(VJX_DT_THREADS, 1) k_lu_dense_tail(LUDev lu, double* __restrict__ x_out, NRStat* st) {
+  extern __shared__ double vjx_dt_smem[];
+  const int T = lu.n_dense, ldg = T + 1;
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double r[VJX_DT_R][VJX_DT_C];
+#pragma unroll
+  for (int a = 0; a < VJX_DT_R; ++a)
+#pragma unroll
+    for (int b = 0; b < VJX_DT_C; ++b) {
+      const int i = wi + 16 * a, j = lane + 32 * b;
+      r[a][b] = (i < T && j <= T) ? lu.dense[(size_t)i * ldg + j] : 0.0;
+    }
+  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 1] = global_ns();
+  double* const urow = vjx_dt_smem;         // [2][192] pivot row, slot 160 = 1 / pivot
+  double* const lcol = vjx_dt_smem + 384;   // [2][160] pivot column
+  bool bad = false;
+  __syncthreads();
+  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 2] = global_ns();
+  // The register tile can only be indexed with compile-time constants, so the pivots are walked in
+  // panels of 16 (one per register row A, fully unrolled): inside panel A pivot k = 16 A + w belongs to
+  // warp w, register row A, column block A / 2, lane 16 (A & 1) + w - all but w known at compile time.
+  // Finished register rows (< A) and column blocks (< A / 2) drop out of the unrolled code.
+  //
+  // Look-ahead: in step k the owner of row k+1 updates that row FIRST, takes the reciprocal of the next
+  // pivot and publishes the row into the other buffer while the remaining warps are still busy with
+  // their step-k updates, so the division is off the critical path; every warp publishes its entries
+  // of column k+1 after its own updates.  One barrier per pivot.  Row updates are branch-free
+  // (a structural zero of L multiplies through as -0) so that independent rows overlap in the pipes.
+  {
+    double* const urn = urow;
+    if (wi == 0) VJX_DT_PUBLISH_ROW(0, 0, 0)
+    if (lane == 0) {
+#pragma unroll
+      for (int a2 = 0; a2 < VJX_DT_R; ++a2) lcol[wi + 16 * a2] = r[a2][0];
+    }
+  }
+  vjx_dt_panel<0>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<1>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<2>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<3>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<4>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<5>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<6>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<7>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<8>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<9>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&st->error, 2);
+  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 3] = global_ns();
+  double* const S = vjx_dt_smem;
+#pragma unroll
+  for (int a = 0; a < VJX_DT_R; ++a)
+#pragma unroll
+    for (int b = 0; b < VJX_DT_C; ++b) {
+      const int i = wi + 16 * a, j = lane + 32 * b;
+      if (i < T && j <= T) S[i * VJX_DT_LDS + j] = r[a][b];
+    }
+  __syncthreads();
+  const int tid = threadIdx.x;
+  if (tid < T) {
+    const double inv = 1.0 / S[tid * VJX_DT_LDS + tid];
+    S[tid * VJX_DT_LDS + tid] = inv;
+    lu.inv_diag[lu.dense_start + tid] = inv;
+    lu.y[lu.dense_start + tid] = S[tid * VJX_DT_LDS + T];
+  }
+  __syncthreads();
+  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 4] = global_ns();
+  double xmine = 0.0;
+  for (int k = T - 1; k >= 0; --k) {
+    const double xk = S[k * VJX_DT_LDS + T] * S[k * VJX_DT_LDS + k];
+    if (tid < k) S[tid * VJX_DT_LDS + T] = __fma_rn(-S[tid * VJX_DT_LDS + k], xk, S[tid * VJX_DT_LDS + T]);
+    if (tid == k) xmine = xk;
+    __syncthreads();
+  }
+  if (tid < T) {
+    const int i = lu.dense_start + tid;
+    st_pub_f64(lu.xp + i, xmine);
+    x_out[lu.perm_c[i]] = xmine;
+    if (lu.ts) lu.ts[i] = global_ns();
+  }
+  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 5] = global_ns();
+}
+#undef VJX_DT_UPDATE_ROW
+#undef VJX_DT_PUBLISH_ROW
 
 // Deterministic warp sum: fixed butterfly order.
 __device__ __forceinline__ double warp_sum(double v) {
@@ -770,10 +962,14 @@ __global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_usolve(LUDev lu, doubl
     return bits != VJX_SENTINEL;
   };
   if (blockIdx.x == 0 && n_tail > 0) {
-    for (int t = threadIdx.x; t < n_tail; t += blockDim.x)
-      reinterpret_cast<ull*>(xtail)[t] = VJX_SENTINEL;
+    // the dense trailing block is already solved (k_lu_dense_tail): its x is preloaded
+    const int n_done = min(lu.n_dense, n_tail);
+    for (int t = threadIdx.x; t < n_tail; t += blockDim.x) {
+      if (t < n_done) xtail[t] = lu.xp[n - 1 - t];
+      else reinterpret_cast<ull*>(xtail)[t] = VJX_SENTINEL;
+    }
     __syncthreads();
-    for (int t = threadIdx.x >> 5; t < n_tail; t += (blockDim.x >> 5)) {
+    for (int t = n_done + (threadIdx.x >> 5); t < n_tail; t += (blockDim.x >> 5)) {
       const int i = n - 1 - t;
       const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
       double yi = 0.0, di = 0.0;
@@ -1366,7 +1562,8 @@ struct vjx_handle {
   bool lu_ready = false;
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_init, lu_kub, lu_order_u, lu_perm_r, lu_perm_c;
-  DevBuf<double> lu_scratch;
+  DevBuf<double> lu_scratch, lu_dense;
+  DevBuf<int> lu_dense_lstop;
   int lu_grid_load = 0;
   // k_lu_rows runs as one or two launches over consecutive ranges of order_f (wide low levels with a
   // small working vector and many warps per SM, then the narrow high levels with long rows)
@@ -1819,7 +2016,7 @@ static void launch_residual(vjx_handle* h, const BuildPtrs& b, int check, cudaSt
 static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s);
 
 static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr, const double* b, double scale,
-                             const unsigned char* zero_mask, cudaStream_t s) {
+                             const unsigned char* zero_mask, double* x, cudaStream_t s) {
   k_lu_load<<<h->lu_grid_load, 256, 0, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
   h->launches += 1;
   for (int g = 0; g < h->lu_nseg; ++g) {
@@ -1828,12 +2025,16 @@ static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr,
         h->lu_seg_t1[g], h->lu_seg_rowbuf[g]);
     h->launches += 1;
   }
+  if (lud.n_dense > 0) {
+    k_lu_dense_tail<<<1, VJX_DT_THREADS, VJX_DT_SMEM, s>>>(lud, x, h->st.p);
+    h->launches += 1;
+  }
 }
 
 // Refactorise on the fixed pattern with the forward solve folded in, then back solve into x.
 static void launch_lu(vjx_handle* h, const double* csr, const double* b, double scale, const unsigned char* zero_mask,
                       double* x, cudaStream_t s) {
-  launch_lu_factor(h, h->lud, csr, b, scale, zero_mask, s);
+  launch_lu_factor(h, h->lud, csr, b, scale, zero_mask, x, s);
   k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(h->lud, x, h->st.p);
   h->launches += 1;
 }
@@ -1872,7 +2073,6 @@ static int upload_symbolic(vjx_handle* h) {
   CK(h->lu_col.upload(S.lu_col));
   CK(h->lu_diag.upload(S.lu_diag));
   CK(h->lu_src.upload(S.lu_src));
-  CK(h->lu_order_u.upload(S.order_u));
   CK(h->lu_perm_r.upload(S.perm_r));
   CK(h->lu_perm_c.upload(S.perm_c));
   std::vector<long long> pp(S.upd_ptr.begin(), S.upd_ptr.end());
@@ -1914,22 +2114,54 @@ static int upload_symbolic(vjx_handle* h) {
   L.nnz = S.nnz_lu;
   L.ptr = h->lu_ptr.p; L.col = h->lu_col.p; L.diag = h->lu_diag.p; L.src = h->lu_src.p;
   L.init = h->lu_init.p; L.kub = h->lu_kub.p;
-  L.order_u = h->lu_order_u.p; L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
+  L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
   L.ts = nullptr;
   L.upd_ptr = h->lu_upd_ptr.p; L.upd_pos = h->lu_upd_pos.p;
   CK(h->lu_order_f.upload(S.order_f));
   L.order_f = h->lu_order_f.p;
   L.n_nol = n_nol;
   L.max_lrow = max_lrow;
-  L.tail_start = S.tail_start;
+  // dense trailing block: the longest suffix of rows that all have an L part, up to VJX_DT_MAX rows
+  int n_dense = 0;
+  const int dt_cap = getenv("VJX_DT_ROWS") ? std::min(VJX_DT_MAX, atoi(getenv("VJX_DT_ROWS"))) : VJX_DT_MAX;
+  while (n_dense < dt_cap && n_dense < n && S.lu_diag[n - 1 - n_dense] > S.lu_ptr[n - 1 - n_dense]) ++n_dense;
+  if (n_dense < 16 || getenv("VJX_NO_DENSE_TAIL")) n_dense = 0;
+  const int ds = n - n_dense;
   {
-    std::vector<int> lg(S.long_u);
+    std::vector<int> lstop((size_t)std::max(n_dense, 1), 0);
+    for (int t = 0; t < n_dense; ++t) {
+      const int i = ds + t;
+      int p = S.lu_ptr[i];
+      while (p < S.lu_diag[i] && S.lu_col[p] < ds) ++p;
+      lstop[t] = p;
+    }
+    CK(h->lu_dense_lstop.upload(lstop));
+    CK(h->lu_dense.alloc((size_t)std::max(n_dense, 1) * (n_dense + 1)));
+  }
+  L.dense_start = ds;
+  L.dbg = getenv("VJX_DT_DBG") ? atoi(getenv("VJX_DT_DBG")) : 0;
+  L.n_dense = n_dense;
+  L.dense_lstop = h->lu_dense_lstop.p;
+  L.dense = h->lu_dense.p;
+  if (n_dense > 0) CK(cudaFuncSetAttribute(k_lu_dense_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, VJX_DT_SMEM));
+  // back solve: rows of the dense block are solved by k_lu_dense_tail; the chain tail walked by block 0
+  // of k_lu_usolve is what is left of [tail_start, n) in front of it
+  L.tail_start = std::min(S.tail_start, ds);
+  std::vector<int> bulk_u, lg;
+  for (int i : S.order_u) if (i < L.tail_start) bulk_u.push_back(i);
+  for (int i : S.long_u) if (i < L.tail_start) lg.push_back(i);
+  const int n_long_u = (int)lg.size();
+  {
+    if (bulk_u.empty()) bulk_u.push_back(0);
     if (lg.empty()) lg.push_back(0);
+    L.n_bulk_u = 0;
+    for (int i : S.order_u) if (i < L.tail_start) L.n_bulk_u++;
+    CK(h->lu_order_u.upload(bulk_u));
     CK(h->lu_long_u.upload(lg));
   }
+  L.order_u = h->lu_order_u.p;
   L.long_u = h->lu_long_u.p;
-  L.n_long_u = (int)S.long_u.size();
-  L.n_bulk_u = (int)S.order_u.size();
+  L.n_long_u = n_long_u;
   L.val = h->lu_val.p; L.inv_diag = h->lu_inv.p; L.y = h->lu_y.p; L.xp = h->lu_xp.p;
   // k_lu_rows: the shared-memory working vector of a warp holds the longest row of its range, up to a
   // cap; longer rows go through a global scratch.  When the long rows would cost occupancy (> 1024
@@ -1988,10 +2220,9 @@ static int upload_symbolic(vjx_handle* h) {
   // back solve: one block per SM slot, minus room for the long-row blocks; block 0 is dedicated to the
   // chain tail, the other blocks take the tickets
   const int wps = VJX_SOLVE_THREADS / 32;
-  int grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_u - (long long)S.long_u.size(),
-                                                                 ((long long)n + wps - 1) / wps));
-  if (S.tail_start < n && grid_s < 2) grid_s = 2;
-  h->lu_grid_u = grid_s + (int)S.long_u.size();
+  int grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_u - n_long_u, ((long long)n + wps - 1) / wps));
+  if (L.tail_start < n && grid_s < 2) grid_s = 2;
+  h->lu_grid_u = grid_s + n_long_u;
   h->lu_ready = true;
   return VJX_OK;
 }
@@ -2494,15 +2725,20 @@ extern "C" int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* le
   CK(ts.alloc((size_t)n + 1 + 4100));
   LUDev lud = h->lud;
   k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
-  if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, s);
+  if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
   lud.ts = ts.p;
-  CK(cudaMemsetAsync(ts.p, 0, sizeof(ull) * ((size_t)n + 1), s));
+  CK(cudaMemsetAsync(ts.p, 0, sizeof(ull) * ((size_t)n + 8), s));
   k_stamp_now<<<1, 1, 0, s>>>(ts.p + n);
-  if (phase == 3) launch_lu_factor(h, lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, s);
+  if (phase == 3) launch_lu_factor(h, lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
   if (phase == 5) k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(lud, h->delta.p, h->st.p);
-  std::vector<ull> hts((size_t)n + 1);
+  std::vector<ull> hts((size_t)n + 8);
   CK(cudaStreamSynchronize(s));
-  CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 8), cudaMemcpyDeviceToHost));
+  if (phase == 3 && h->lud.n_dense > 0 && getenv("VJX_DT_TRACE")) {
+    auto us = [&](int q) { return ((long long)hts[n + q] - (long long)hts[n]) / 1e3; };
+    fprintf(stderr, "dense trailing block (%d rows), us since factorisation start: begin %.1f, loaded %.1f, eliminated %.1f, "
+            "spilled %.1f, solved %.1f\n", h->lud.n_dense, us(1), us(2), us(3), us(4), us(5));
+  }
   for (int i = 0; i < n; ++i) {
     ns_out[i] = (double)((long long)hts[i] - (long long)hts[n]);
     if (level_out) level_out[i] = phase == 5 ? h->sym.level_u[i] : h->sym.level_l[i];
@@ -2530,7 +2766,7 @@ extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg
     if (phase == 3 || phase == 4 || phase == 5) {
       // each LU phase needs a fresh epoch and the preceding phases' results
       k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
-      if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, s);
+      if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
     }
     CK(cudaEventRecord(e0, s));
     l0 = h->launches;
@@ -2538,7 +2774,7 @@ extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg
       case 0: { int rc = launch_eval(h, b, s); if (rc) return rc; break; }
       case 1: launch_stamp(h, h->csr.p, 1, s); break;
       case 2: launch_residual(h, b, 0, s); break;
-      case 3: launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, s); break;
+      case 3: launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s); break;
       case 4: break;   // the forward solve is part of the factorisation kernels (phase 3)
       case 5: k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(h->lud, h->delta.p, h->st.p); h->launches++; break;
       case 6: k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua); h->launches++; break;
