@@ -147,20 +147,21 @@ def phase_bytes(eng, lu):
         "device_eval": ev,
         "jacobian_stamp": jc * (8 + 4) + nse * 8 + n * (8 + 4),
         "residual": 4 * rc * (8 + 4) + rc * (8 + 4) + 5 * n * 8,
-        "lu_factor": 8 * (nse + 2 * nnz),
-        "lu_lsolve": 8 * ((nnz - n) // 2 + n) + 3 * 8 * n,
+        # refactorisation (read A, read + write L+U) with the forward solve folded in (b, y, 1/pivot)
+        "lu_factor_fwd": 8 * (nse + 2 * nnz) + 3 * 8 * n,
         "lu_usolve": 8 * ((nnz - n) // 2 + n) + 3 * 8 * n,
         "nr_update": 14 * n * 8,
     }
 
 
-PHASES = ["device_eval", "jacobian_stamp", "residual", "lu_factor", "lu_lsolve", "lu_usolve", "nr_update"]
+# (name, vjx_time_phase id); id 4 was the separate forward solve, now part of id 3
+PHASES = [("device_eval", 0), ("jacobian_stamp", 1), ("residual", 2), ("lu_factor_fwd", 3), ("lu_usolve", 5), ("nr_update", 6)]
 
 
-def launches_per(eng):
+def launches_per(eng, n_lu):
     nm = len(eng.models)
     isrc = 1 if eng.n_is > 0 else 0
-    per_iter = 1 + isrc + nm + 1 + 1 + 3 + 2
+    per_iter = 1 + isrc + nm + 1 + 1 + n_lu + 2
     per_attempt = 2 + (isrc + nm + 1 + 1 + 1 + 1 + 1 + 1)
     return per_iter, per_attempt
 
@@ -276,8 +277,6 @@ def run_b200(args, rank, world, local_rank):
         return
     g_steps, g_res_steps, g_e2e_steps = int(cnts[0]), int(cnts[1]), int(cnts[2])
     ms_per_step = vals[0] / max(g_steps, 1)
-    per_iter, per_attempt = launches_per(eng)
-    gpu_launches = int(cnts[4] * per_iter + cnts[3] * per_attempt)
     # ---- roofline of the dominant kernel (rank 0, engine 0), timed alone
     lu = eng.lu_stats()
     pb = phase_bytes(eng, lu)
@@ -285,17 +284,21 @@ def run_b200(args, rank, world, local_rank):
     iters_per_step = cnts[4] / max(g_steps, 1)
     att_per_step = cnts[3] / max(g_steps, 1)
     phase = {}
-    for i, nm in enumerate(PHASES):
-        ms, nl = eng.time_phase(i, 20)
+    for nm, pid in PHASES:
+        ms, nl = eng.time_phase(pid, 20)
         calls = {"device_eval": iters_per_step + att_per_step, "residual": iters_per_step + att_per_step}.get(nm, iters_per_step)
         phase[nm] = {"ms": ms, "launches": nl, "calls_per_step": calls, "ms_per_step": ms * calls,
                      "alg_bytes": pb[nm], "gbs": pb[nm] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0}
+    per_iter, per_attempt = launches_per(eng, phase["lu_factor_fwd"]["launches"] + phase["lu_usolve"]["launches"])
+    gpu_launches = int(cnts[4] * per_iter + cnts[3] * per_attempt)
     dom = max(phase, key=lambda k: phase[k]["ms_per_step"])
     pd = phase[dom]
     roof = {"kernel": dom, "bound": "hbm", "achieved": pd["gbs"], "peak": peak, "unit": "GB/s",
             "frac": pd["gbs"] / peak, "traffic": None, "peak_source": peak_kind,
             "launch_ms": pd["ms"], "share_of_step": pd["ms_per_step"] / max(ms_per_step, 1e-12),
-            "note": "timed alone with CUDA events, L2-warm (working set < L2 at this size); latency-bound"}
+            "kernels": "k_lu_load + k_lu_rows + k_lu_dense_tail" if dom == "lu_factor_fwd" else dom,
+            "note": "timed alone with CUDA events, L2-warm (working set < L2 at this size); bound by the dependency "
+                    "chain of the elimination (latency), not by bytes: see profiles/r1_lu_notes.md"}
     out = {
         "metric": METRIC, "value": ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
@@ -310,6 +313,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": vals[2] * 1e3 / max(g_e2e_steps, 1), "unit": UNIT,
                 "h2d_bytes_per_step": cnts[6] / max(g_e2e_steps, 1), "d2h_bytes_per_step": cnts[7] / max(g_e2e_steps, 1),
                 "gather_s": gather_s},
+        "sweep_steps_per_s": 1e3 / ms_per_step if ms_per_step > 0 else None,
         "gpu_launches": gpu_launches,
         "clocks": clocks,
         "roofline": roof,
@@ -318,9 +322,50 @@ def run_b200(args, rank, world, local_rank):
         "reported_reference": {"c6288_jax_gpu_T4_ms_per_step": 19.81, "c6288_jax_cpu_ms_per_step": 88.06,
                                "note": "reference README numbers on its real c6288 netlist + PSP103; not the same circuit/model"},
     }
+    if world == 1 and args.mul64_steps > 0 and args.workload == "c6288":
+        for e in engines:
+            e.close()
+        engines.clear()
+        out["mul64"] = mul64_record(args, local_rank, peak)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
     print(json.dumps(out))
+
+
+def mul64_record(args, local_rank, peak):
+    """Second half of BASELINE.json's metric: ms per accepted step of the mul64 transient on one B200
+    (266k MOSFETs, 666k unknowns; the reference times 15 steps, README.md:80)."""
+    from vajax_b200.analysis.engine import B200Engine
+    from vajax_b200.benchmarks.circuits import mul64_circuit
+
+    t0 = time.perf_counter()
+    e = B200Engine(mul64_circuit(64), get_bundles(), device=local_rank, use_device_graph=True).prepare()
+    prep = time.perf_counter() - t0
+    W, K = 3, args.mul64_steps
+    e.tran_begin(max_steps=1 + W)
+    e.tran_run()
+    e.tran_begin(max_steps=1 + W + K)
+    e.tran_run(step_limit=1 + W)
+    sc0 = e.tran_scalars()
+    e.tran_run(step_limit=1 + W + K)
+    ms = e.tran_run_ms()[0]
+    sc = e.tran_scalars()
+    steps = sc["step_idx"] - sc0["step_idx"]
+    lu = e.lu_stats()
+    pb = phase_bytes(e, lu)
+    ph = {}
+    for nm, pid in PHASES:
+        t, nl = e.time_phase(pid, 5)
+        ph[nm] = {"ms": round(t, 4), "launches": nl, "alg_bytes": pb[nm], "gbs": round(pb[nm] / (t * 1e-3) / 1e9, 2) if t > 0 else 0.0,
+                  "frac_of_hbm_peak": round(pb[nm] / (t * 1e-3) / 1e9 / peak, 5) if t > 0 else 0.0}
+    rec = {"metric": "ms/transient step (mul64) on B200", "value": ms / max(steps, 1), "unit": UNIT, "steps_timed": steps,
+           "warmup_steps": W, "nr_iterations": sc["total_nr"] - sc0["total_nr"], "rejected": sc["rejected"] - sc0["rejected"],
+           "n_unknowns": e.n_aug, "csr_nnz": e.nse, "prepare_s": round(prep, 2), "phases": ph, "lu": lu,
+           "timing": "one uninterrupted device-side loop (CUDA graph with conditional nodes), CUDA events on the launch stream; "
+                     "the working set (about 0.6 GB) is larger than L2",
+           "error_flags": sc["error_flags"]}
+    e.close()
+    return rec
 
 
 def cpu_baseline(args, sample_steps: int, threads_note: str = "") -> dict:
@@ -370,6 +415,7 @@ def main():
                     help="PVT corners (whole-circuit replicas) per GPU; 8 per GPU = the 64-point sweep at 8 GPUs; "
                          "corner 0 is the nominal circuit (value_nominal)")
     ap.add_argument("--cpu-steps", type=int, default=25)
+    ap.add_argument("--mul64-steps", type=int, default=15, help="also time this many mul64 steps at N=1 (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="host-polled NR/step loops (for ncu launch lists)")
     args = ap.parse_args()

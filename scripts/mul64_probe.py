@@ -38,7 +38,7 @@ for s in range(1, 1 + K):
     if a == 0 or sc["error_flags"]:
         break
 print("lu:", json.dumps(e.lu_stats()), flush=True)
-names = ["device_eval", "jacobian_stamp", "residual", "lu_factor", "lu_lsolve", "lu_usolve", "nr_update"]
+names = ["device_eval", "jacobian_stamp", "residual", "lu_factor_fwd", "(fused)", "lu_usolve", "nr_update"]
 for i, nm in enumerate(names):
     ms, nl = e.time_phase(i, 3)
     print(f"phase {nm:15s} {ms:9.3f} ms ({nl} launches)", flush=True)

@@ -6,8 +6,9 @@
 //   k_isrc                       K4     current-source contributions
 //   k_stamp_jacobian             K3,K5,K8  segmented sum over slot-sorted contributions -> CSR values
 //   k_residual                   K4,K6,K7  row-sorted vector sums, residual assembly, convergence
-//   k_lu_factor                  K9     dependency-driven (sync-free) row-wise refactorisation
-//   k_lu_lsolve / k_lu_usolve    K9     dependency-driven triangular solves
+//   k_lu_load / k_lu_rows /      K9     dependency-driven (sync-free) row-wise refactorisation with the forward
+//   k_lu_dense_tail                     solve folded in; dense trailing block in the registers of one CTA
+//   k_lu_usolve                  K9     dependency-driven back solve
 //   k_delta_reduce / k_nr_update K7,K10 delta convergence, step limiting, X update, NOI clamp
 //   k_pre_step .. k_step_commit  K11,K12 integration coefficients, sources, predictor, LTE,
 //                                       accept/reject, history, outputs - all on the device
