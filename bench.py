@@ -54,6 +54,26 @@ def load_peaks():
     return HBM_FALLBACK_GBS, "fallback"
 
 
+def load_extra():
+    """Numbers measured on this pool's B200s by this repo's own probes (fp64 DFMA peak, ncu DRAM traffic)."""
+    p = os.path.join(ROOT, "profiles", "r1_measured_extra.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
+def eval_flops(eng):
+    """Static fp64 operation count of the emitted model kernels x instances (cuda_emitter counts arithmetic,
+    divisions and transcendental calls of the whole MIR; the executed path is shorter)."""
+    tot = {"arith": 0, "div": 0, "transc": 0}
+    for m in eng.models.values():
+        f = m["meta"].get("flops_static", {})
+        for k in tot:
+            tot[k] += int(f.get(k, 0)) * m["n_dev"]
+    return tot
+
+
 def make_circuit(workload: str, nbits: int, corner: int = 0):
     from vajax_b200.benchmarks import circuits
 
@@ -185,7 +205,9 @@ def run_b200(args, rank, world, local_rank):
         gid = c * world + rank  # block-cyclic: corner i -> GPU i mod world
         corner_ids.append(gid)
         circ, desc = make_circuit(args.workload, args.nbits, corner=gid)
-        engines.append(B200Engine(circ, bundles, device=local_rank, use_device_graph=not args.no_graph).prepare())
+        # every engine on its own stream: the sweep leg below runs the corners of a rank concurrently
+        engines.append(B200Engine(circ, bundles, device=local_rank, use_device_graph=not args.no_graph,
+                                  stream="own").prepare())
     eng = engines[0]
     rows = 1 + K
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -238,6 +260,30 @@ def run_b200(args, rank, world, local_rank):
         res_ms += e.tran_run_ms()[0]
         res_steps += e.tran_scalars()["step_idx"] - 1
     barrier()
+    # ---- sweep: the corners of this rank run CONCURRENTLY (one stream + host thread each), no L2 flush:
+    # a c6288-sized circuit is latency-bound and leaves most of the GPU idle
+    sweep_ms, sweep_steps = 0.0, 0
+    if n_corners > 1 and not args.no_graph:
+        for e in engines:
+            e.tran_begin(max_steps=rows)
+        barrier()
+        ev_s, ev_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_s.record()
+        ths = [threading.Thread(target=e.tran_run, kwargs=dict(step_limit=rows)) for e in engines]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        torch.cuda.synchronize()
+        ev_e.record()
+        torch.cuda.synchronize()
+        sweep_ms = ev_s.elapsed_time(ev_e)
+        for e in engines:
+            sc = e.tran_scalars()
+            sweep_steps += sc["step_idx"] - 1
+            if sc["error_flags"]:
+                raise SystemExit(f"bench.py: device error flags {sc['error_flags']} in the concurrent sweep")
+        barrier()
     clocks = sampler.stop()
     # ---- e2e through the public API with host buffers (H2D of the initial state, D2H of the waveforms)
     barrier()
@@ -265,8 +311,9 @@ def run_b200(args, rank, world, local_rank):
         gather_s = time.perf_counter() - tg
         e2e_local += gather_s
     # ---- reduce over ranks: MAX time, SUM steps
-    vals = torch.tensor([total_ms, res_ms, e2e_local, wall_flushed], dtype=torch.float64, device=dev)
-    cnts = torch.tensor([steps_done, res_steps, e2e_steps, attempts, nr_total, rejected, h2d, d2h], dtype=torch.float64, device=dev)
+    vals = torch.tensor([total_ms, res_ms, e2e_local, wall_flushed, sweep_ms], dtype=torch.float64, device=dev)
+    cnts = torch.tensor([steps_done, res_steps, e2e_steps, attempts, nr_total, rejected, h2d, d2h, sweep_steps],
+                        dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
 
@@ -291,10 +338,20 @@ def run_b200(args, rank, world, local_rank):
                      "alg_bytes": pb[nm], "gbs": pb[nm] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0}
     per_iter, per_attempt = launches_per(eng, phase["lu_factor_fwd"]["launches"] + phase["lu_usolve"]["launches"])
     gpu_launches = int(cnts[4] * per_iter + cnts[3] * per_attempt)
+    extra = load_extra()
+    ef = eval_flops(eng)
+    ev_ms = phase["device_eval"]["ms"]
+    if ev_ms > 0:
+        # transcendental calls (exp/log/sqrt/pow) counted as 20 fp64 operations each, divisions as 8
+        fl = ef["arith"] + 8 * ef["div"] + 20 * ef["transc"]
+        phase["device_eval"].update({"flops_static": fl, "tflops": fl / (ev_ms * 1e-3) / 1e12,
+                                     "fp64_peak_tflops": extra.get("fp64_tflops"),
+                                     "frac_of_fp64_peak": (fl / (ev_ms * 1e-3) / 1e12) / extra["fp64_tflops"] if extra.get("fp64_tflops") else None})
     dom = max(phase, key=lambda k: phase[k]["ms_per_step"])
     pd = phase[dom]
     roof = {"kernel": dom, "bound": "hbm", "achieved": pd["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": pd["gbs"] / peak, "traffic": None, "peak_source": peak_kind,
+            "frac": pd["gbs"] / peak,
+            "traffic": extra.get("traffic_bytes_per_launch", {}).get(args.workload, {}).get(dom), "peak_source": peak_kind,
             "launch_ms": pd["ms"], "share_of_step": pd["ms_per_step"] / max(ms_per_step, 1e-12),
             "kernels": "k_lu_load + k_lu_rows + k_lu_dense_tail" if dom == "lu_factor_fwd" else dom,
             "note": "timed alone with CUDA events, L2-warm (working set < L2 at this size); bound by the dependency "
@@ -314,6 +371,11 @@ def run_b200(args, rank, world, local_rank):
                 "h2d_bytes_per_step": cnts[6] / max(g_e2e_steps, 1), "d2h_bytes_per_step": cnts[7] / max(g_e2e_steps, 1),
                 "gather_s": gather_s},
         "sweep_steps_per_s": 1e3 / ms_per_step if ms_per_step > 0 else None,
+        "sweep_concurrent": {"steps_per_s": cnts[8] / (vals[4] * 1e-3) if vals[4] > 0 else None,
+                             "ms_per_step": vals[4] / cnts[8] if cnts[8] > 0 else None, "corners_in_flight_per_gpu": n_corners,
+                             "steps": int(cnts[8]),
+                             "note": "same corners and steps as `value`, but the corners of a GPU run concurrently on "
+                                     "separate streams (run_corners(concurrent=...)); CUDA events, max over ranks"},
         "gpu_launches": gpu_launches,
         "clocks": clocks,
         "roofline": roof,

@@ -88,3 +88,16 @@ def test_two_rank_corner_sweep_matches_single_process(bundles):
         assert n == r.stats["n_steps"] and np.array_equal(t, r.times) and np.array_equal(V, r.voltages), name
     # the corners really differ (temperature / vdd change the waveforms)
     assert not np.array_equal(single.results[0].voltages, single.results[4].voltages)
+
+
+def test_concurrent_corners_match_sequential(bundles):
+    """run_corners(concurrent=k) only changes how a rank schedules its corners (threads + streams)."""
+    from vajax_b200.analysis import corners as cz
+    from vajax_b200.benchmarks.circuits import diode_clipper_circuit
+
+    circ = diode_clipper_circuit(stop=1e-4)
+    a = cz.run_corners(circ, bundles, _corners(), engine_factory=_OracleAsEngine)
+    b = cz.run_corners(circ, bundles, _corners(), engine_factory=_OracleAsEngine, concurrent=3)
+    assert [r.corner.name for r in a.results] == [r.corner.name for r in b.results]
+    for ra, rb in zip(a.results, b.results):
+        assert np.array_equal(ra.times, rb.times) and np.array_equal(ra.voltages, rb.voltages)

@@ -102,3 +102,19 @@ def test_mul4_settles_to_the_product(bundles):
     assert all(v < 0.2 or v > 1.0 for v in bits), bits
     assert got == 225, (got, bits)
     e.close()
+
+
+def test_concurrent_corner_sweep_is_bit_identical(bundles):
+    """Whole-circuit replicas on separate streams / host threads of ONE GPU (run_corners(concurrent=4)):
+    same waveforms, bit for bit, as the sequential sweep - the LU's ticket / sentinel protocol does not
+    depend on which other kernels share the SMs."""
+    from vajax_b200.analysis import corners as cz
+
+    circ = circuits.multiplier_circuit(4, stop=4e-10, step=2e-12)
+    cs = cz.sweep_corners(64)[:6]
+    a = cz.run_corners(circ, bundles, cs, use_device_graph=True)
+    b = cz.run_corners(circ, bundles, cs, use_device_graph=True, concurrent=4)
+    assert a.all_converged and b.all_converged
+    for ra, rb in zip(a.results, b.results):
+        assert ra.corner.name == rb.corner.name
+        assert np.array_equal(ra.times, rb.times) and np.array_equal(ra.voltages, rb.voltages)

@@ -134,7 +134,10 @@ class _Plugin:
 
 class B200Engine:
     def __init__(self, circuit: dict, bundles: Dict[str, dict], use_device_limiting: bool = False,
-                 device: int = 0, use_device_graph: bool = False, pivot_tol: float = 1e-3):
+                 device: int = 0, use_device_graph: bool = False, pivot_tol: float = 1e-3, stream=None):
+        """``stream``: None = the default CUDA stream; "own" = a private non-blocking stream, so that several
+        engines (corners of a sweep) can run their device-resident loops concurrently on one GPU; or a
+        ``torch.cuda.Stream``."""
         self.circuit = circuit
         self.devices = circuit["devices"]
         self.num_nodes = int(circuit["num_nodes"])
@@ -144,6 +147,8 @@ class B200Engine:
         self.device = device
         self.use_device_graph = use_device_graph
         self.pivot_tol = pivot_tol
+        self._stream_req = stream
+        self._stream = None
         self.analysis_params = dict(circuit.get("analysis", {}))
         self.options = SimulationOptions()
         for k in ("nr_damping", "tran_itl", "reltol", "abstol", "vntol", "gmin", "temp", "icmode"):
@@ -582,6 +587,25 @@ class B200Engine:
         self._prepared = True
         return self
 
+    # ---- stream plumbing ---------------------------------------------------------------
+    def _sarg(self):
+        """Stream argument of the C-ABI calls.  With a private stream, work torch queued on its current
+        stream (allocations zero-filled, uploads) is finished first: the two streams are not ordered."""
+        if self._stream_req is None:
+            return None
+        torch = self._torch()
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=self.device) if isinstance(self._stream_req, str) else self._stream_req
+        torch.cuda.current_stream(self.device).synchronize()
+        return C.c_void_p(self._stream.cuda_stream)
+
+    def _sync(self):
+        torch = self._torch()
+        if self._stream is not None:
+            self._stream.synchronize()
+        else:
+            torch.cuda.synchronize()
+
     def close(self):
         if self.handle:
             vlib.load().vjx_destroy(self.handle)
@@ -670,8 +694,8 @@ class B200Engine:
             self.handle, self._p(args[0]), self._p(args[1]) if self.n_vs else None, self._p(args[2]) if self.n_is else None,
             self._p(args[3]), float(integ_c0), float(gmin), float(gshunt), float(integ_c1), float(integ_d1),
             self._p(dq), float(integ_c2), self._p(q2), self._p(li), int(nr_iteration),
-            self._p(csr), self._p(f), self._p(Q), self._p(Ivs), self._p(lim), self._p(mrc), None))
-        torch.cuda.synchronize()
+            self._p(csr), self._p(f), self._p(Q), self._p(Ivs), self._p(lim), self._p(mrc), self._sarg()))
+        self._sync()
         return (csr[:self.nse].cpu().numpy(), f[:self.n_aug].cpu().numpy(), Q[:self.n_unknowns].cpu().numpy(),
                 Ivs[:self.n_vs].cpu().numpy(), lim[:self.total_limit_states].cpu().numpy(), mrc[:self.n_unknowns].cpu().numpy())
 
@@ -681,8 +705,8 @@ class B200Engine:
         torch = self._torch()
         c, bb = self._dev(csr_data), self._dev(b)
         x = torch.zeros(self.n_aug, dtype=torch.float64, device=c.device)
-        vlib.check(vlib.load().vjx_lu_solve(self.handle, self._p(c), self._p(bb), self._p(x), None))
-        torch.cuda.synchronize()
+        vlib.check(vlib.load().vjx_lu_solve(self.handle, self._p(c), self._p(bb), self._p(x), self._sarg()))
+        self._sync()
         return x.cpu().numpy()
 
     def lu_stats(self) -> dict:
@@ -712,8 +736,8 @@ class B200Engine:
             float(integ_c2), self._p(a[5]), self._p(a[6]), self._p(a[7]),
             -1 if max_iterations is None else int(max_iterations),
             self._p(X_out), C.byref(it), C.byref(cv), C.byref(mf), self._p(Q), self._p(dQdt), self._p(Ivs),
-            self._p(lim), self._p(mrc), None))
-        torch.cuda.synchronize()
+            self._p(lim), self._p(mrc), self._sarg()))
+        self._sync()
         outs = (X_out[:nx], it.value, bool(cv.value), mf.value, Q[:self.n_unknowns], dQdt[:self.n_unknowns],
                 Ivs[:self.n_vs], lim[:self.total_limit_states], mrc[:self.n_unknowns])
         if return_device:
@@ -779,8 +803,8 @@ class B200Engine:
             X0, Q_init = X_dc, Q_dc
         dX0, dQ, dI, dM = self._dev(X0), self._dev(Q_init), self._dev(I_dc if nvs else np.zeros(1)), self._dev(dc_mrc)
         vlib.check(lib.vjx_tran_begin(self.handle, self._p(dX0), self._p(dQ), self._p(dI), self._p(dM), t_stop, dt,
-                                      float(max_dt), int(max_steps), None))
-        torch.cuda.synchronize()
+                                      float(max_dt), int(max_steps), self._sarg()))
+        self._sync()
         self.timings["tran_setup"] = time.perf_counter() - t_setup
         self._tran = dict(t_stop=t_stop, max_steps=int(max_steps),
                           h2d_bytes=8 * (dX0.numel() + dQ.numel() + dI.numel() + dM.numel()))
@@ -791,9 +815,9 @@ class B200Engine:
         initial condition) or ``max_attempts`` attempts; returns the attempts made."""
         lib = vlib.load()
         if step_limit is not None:
-            vlib.check(lib.vjx_tran_set_step_limit(self.handle, int(step_limit), None))
+            vlib.check(lib.vjx_tran_set_step_limit(self.handle, int(step_limit), self._sarg()))
         att = C.c_int(0)
-        vlib.check(lib.vjx_tran_run(self.handle, int(max_attempts), C.byref(att), None))
+        vlib.check(lib.vjx_tran_run(self.handle, int(max_attempts), C.byref(att), self._sarg()))
         return att.value
 
     def tran_run_ms(self) -> Tuple[float, float]:
@@ -804,7 +828,7 @@ class B200Engine:
 
     def tran_scalars(self) -> dict:
         sc = np.zeros(12)
-        vlib.check(vlib.load().vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), None))
+        vlib.check(vlib.load().vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), self._sarg()))
         keys = ["t", "dt", "step_idx", "total_nr", "rejected", "min_dt_used", "max_dt_used", "history_count", "warmup",
                 "consecutive_rejects", "attempts", "error_flags"]
         return {k: (float(v) if k in ("t", "dt", "min_dt_used", "max_dt_used") else int(v)) for k, v in zip(keys, sc)}
@@ -819,7 +843,7 @@ class B200Engine:
         I_out = np.zeros((max_steps, max(nvs, 1)))
         if rows > 0:
             vlib.check(vlib.load().vjx_tran_read(self.handle, 0, rows, times.ctypes.data_as(C.c_void_p),
-                                                 V_out.ctypes.data_as(C.c_void_p), I_out.ctypes.data_as(C.c_void_p), None))
+                                                 V_out.ctypes.data_as(C.c_void_p), I_out.ctypes.data_as(C.c_void_p), self._sarg()))
         self._tran["d2h_bytes"] = 8 * rows * (1 + self.n_external + max(nvs, 1))
         return times, V_out, I_out
 
@@ -831,7 +855,7 @@ class B200Engine:
         nvs = self.n_vs
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_start = time.perf_counter()
-        ev0.record()
+        ev0.record(self._stream) if self._stream is not None else ev0.record()
         while True:
             att = self.tran_run(None, chunk_attempts)
             if att == 0 or chunk_attempts <= 0:
@@ -839,8 +863,8 @@ class B200Engine:
             sc = self.tran_scalars()
             if not (sc["t"] < t_stop) or sc["step_idx"] >= max_steps:
                 break
-        ev1.record()
-        torch.cuda.synchronize()
+        ev1.record(self._stream) if self._stream is not None else ev1.record()
+        self._sync()
         wall = time.perf_counter() - t_start
         sc = self.tran_scalars()
         n_steps = sc["step_idx"]
@@ -870,11 +894,11 @@ class B200Engine:
         """Per-attempt records (step, t_next, dt, nr_iters, accept, lte_reject, nr_failed, lte_norm)."""
         sc = np.zeros(12)
         lib = vlib.load()
-        vlib.check(lib.vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), None))
+        vlib.check(lib.vjx_tran_scalars(self.handle, sc.ctypes.data_as(C.c_void_p), self._sarg()))
         n = int(sc[10]) if count is None else count
         out = np.zeros((max(n, 1), 8))
         if n > 0:
-            vlib.check(lib.vjx_tran_records(self.handle, 0, n, out.ctypes.data_as(C.c_void_p), None))
+            vlib.check(lib.vjx_tran_records(self.handle, 0, n, out.ctypes.data_as(C.c_void_p), self._sarg()))
         return out[:n]
 
     def tran_state(self):
@@ -882,12 +906,12 @@ class B200Engine:
         Q = np.zeros(max(self.n_unknowns, 1))
         dQ = np.zeros(max(self.n_unknowns, 1))
         vlib.check(vlib.load().vjx_tran_state(self.handle, X.ctypes.data_as(C.c_void_p), Q.ctypes.data_as(C.c_void_p),
-                                              dQ.ctypes.data_as(C.c_void_p), None))
+                                              dQ.ctypes.data_as(C.c_void_p), self._sarg()))
         return X, Q[:self.n_unknowns], dQ[:self.n_unknowns]
 
     def time_phase(self, phase: int, reps: int = 20) -> Tuple[float, int]:
         ms, nl = C.c_double(0.0), C.c_int(0)
-        vlib.check(vlib.load().vjx_time_phase(self.handle, phase, reps, C.byref(ms), C.byref(nl), None))
+        vlib.check(vlib.load().vjx_time_phase(self.handle, phase, reps, C.byref(ms), C.byref(nl), self._sarg()))
         return ms.value, nl.value
 
     def launch_count(self) -> int:
