@@ -201,8 +201,9 @@ def run_b200(args, rank, world, local_rank):
     engines = []
     desc = ""
     corner_ids = []
-    for c in range(n_corners):
-        gid = c * world + rank  # block-cyclic: corner i -> GPU i mod world
+    from vajax_b200.analysis.corners import shard
+
+    for gid in shard(n_corners * world, rank, world):  # rotated block-cyclic (corners.shard)
         corner_ids.append(gid)
         circ, desc = make_circuit(args.workload, args.nbits, corner=gid)
         # every engine on its own stream: the sweep leg below runs the corners of a rank concurrently
@@ -391,7 +392,7 @@ def run_b200(args, rank, world, local_rank):
         out["mul64"] = mul64_record(args, local_rank, peak)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
-    print(json.dumps(out))
+    _emit(json.dumps(out))
 
 
 def mul64_record(args, local_rank, peak):
@@ -462,10 +463,14 @@ def run_reference(args, rank, world):
            "config": {"workload": desc, "circuit": args.workload},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
 
 
 def main():
+    # the JSON line must be the only thing on stdout: libraries (NCCL's version banner) write there too
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    globals()["_emit"] = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

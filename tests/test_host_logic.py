@@ -210,4 +210,9 @@ def test_apply_corner_is_pure_and_signed():
     assert m2["params"]["kp"] == kp0 * 1.15 and m2["params"]["vto"] == vto0 - 0.05
     assert v2["params"]["dc"] == dc0 * 0.9 and c["temperature_k"] == 233.15
     assert mos["params"]["kp"] == kp0 and vdd["params"]["dc"] == dc0  # input untouched
-    assert cz.shard(10, 1, 4) == [1, 5, 9] and sum(len(cz.shard(64, r, 8)) for r in range(8)) == 64
+    assert cz.shard(10, 1, 4) == [1, 4] and cz.shard(10, 0, 4) == [0, 7] and cz.shard(10, 2, 4) == [2, 5, 8]
+    parts = [cz.shard(64, r, 8) for r in range(8)]
+    assert sorted(i for p in parts for i in p) == list(range(64)) and all(len(p) == 8 for p in parts)
+    # Latin square: a rank sees every position-in-block (vdd x temperature parity) exactly once
+    assert all(sorted(i % 8 for i in p) == list(range(8)) for p in parts)
+    assert cz.shard(7, 0, 1) == list(range(7))

@@ -200,8 +200,15 @@ def monte_carlo_corners(n: int = 64, seed: int = 64) -> List[CornerConfig]:
 
 
 def shard(n_items: int, rank: int, world_size: int) -> List[int]:
-    """Static block-cyclic assignment: item i -> rank i mod world_size."""
-    return [i for i in range(n_items) if i % world_size == rank]
+    """Static assignment of sweep items to ranks: item i -> rank (i + i // world_size) mod world_size.
+
+    Every rank gets one item of each consecutive block of ``world_size`` (as plain block-cyclic
+    ``i mod world_size`` would), but the position inside the block rotates from block to block.  Sweep
+    tables are nested loops (process x temperature x vdd), so ``i mod world_size`` hands a rank the same
+    vdd / temperature in every block and the ranks' loads differ systematically (a low-vdd corner needs
+    more NR iterations per step); the rotation is a Latin square over (block, position) and evens that out
+    without any run-time exchange.  Counts per rank are those of block-cyclic."""
+    return [i for i in range(n_items) if (i + i // world_size) % world_size == rank]
 
 
 def run_corners(circuit: dict, bundles: Dict[str, dict], corners: Sequence[CornerConfig], *, rank: int = 0,
