@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-T=s6j
-./scripts/fp64_peak > gpurun_out/r1_${T}_fp64_peak.txt 2>&1; cat gpurun_out/r1_${T}_fp64_peak.txt
-python -m pytest tests -m gpu -x -q 2>&1 | tail -n 5
-python bench.py --mul64-steps 0 --no-cpu-baseline > gpurun_out/r1_${T}_bench.json 2> gpurun_out/r1_${T}_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/r1_${T}_bench.err
-python -c "
-import json; d=json.load(open('gpurun_out/r1_${T}_bench.json')); print(d['value'], d['value_l2_resident'], d['sweep_concurrent'], d['e2e'])"
+T=s6l
+python -m pytest tests -m gpu -x -q 2>&1 | tail -n 3
+VJX_DT_TRACE=1 python scripts/lu_timeline.py 16 > gpurun_out/r1_${T}_timeline16.txt 2>&1; grep "==\|dense" gpurun_out/r1_${T}_timeline16.txt | tail -n 3
+python scripts/lu_timeline.py 64 > gpurun_out/r1_${T}_timeline64.txt 2>&1; grep "==" gpurun_out/r1_${T}_timeline64.txt
+python scripts/mul64_probe.py 64 6 2>&1 | grep "phase lu\|steady\|residual"

@@ -118,3 +118,26 @@ def test_concurrent_corner_sweep_is_bit_identical(bundles):
     for ra, rb in zip(a.results, b.results):
         assert ra.corner.name == rb.corner.name
         assert np.array_equal(ra.times, rb.times) and np.array_equal(ra.voltages, rb.voltages)
+
+
+def test_live_engines_keep_their_own_model_constants(bundles):
+    """Two circuit handles alive at the same time (corners with different temperature / process values)
+    must not share the model plugin's __constant__ bank: the waveforms of a corner do not depend on
+    which other engines exist (regression: constants were uploaded at create into one shared bank)."""
+    from vajax_b200.analysis import corners as cz
+    from vajax_b200.analysis.engine import B200Engine
+
+    circ = circuits.multiplier_circuit(4, stop=2e-10, step=2e-12)
+    cs = cz.sweep_corners(64)
+    ca, cb = cz.apply_corner(circ, cs[5]), cz.apply_corner(circ, cs[40])
+    alone = B200Engine(ca, bundles, use_device_graph=True)
+    t0, V0, s0 = alone.run_transient()
+    alone.close()
+    a = B200Engine(ca, bundles, use_device_graph=True).prepare()
+    b = B200Engine(cb, bundles, use_device_graph=True).prepare()   # created later: used to overwrite a's constants
+    t1, V1, s1 = a.run_transient()
+    t2, V2, s2 = b.run_transient()
+    a.close()
+    b.close()
+    assert s1["n_steps"] == s0["n_steps"] and np.array_equal(t0, t1) and np.array_equal(V0, V1)
+    assert not np.array_equal(V1, V2)   # the two corners really differ

@@ -213,9 +213,11 @@ class B200Engine:
         cache = torch.zeros((max(cs, 1), n), dtype=torch.float64, device=dev)
         col = torch.zeros((max(nc, 1), n), dtype=torch.float32, device=dev)
         args = vlib.VjxInitArgs(n, packed.data_ptr(), d_off.data_ptr(), d_str.data_ptr(), cache.data_ptr(), col.data_ptr())
-        torch.cuda.synchronize(dev)
+        # stream-level, not device-wide, synchronisation: another host thread may be capturing a CUDA graph
+        # for its own engine, and a device-wide sync is illegal while any capture is open
+        torch.cuda.current_stream(dev).synchronize()
         rc = plug.dll.vjx_model_init(C.byref(args), C.c_void_p(0))
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()
         if rc != 0:
             raise vlib.VjxError(f"init kernel launch failed for {mt}: cuda error {rc}")
         return cache[:cs].t().contiguous(), col[:nc].t().contiguous()
@@ -604,7 +606,7 @@ class B200Engine:
         if self._stream is not None:
             self._stream.synchronize()
         else:
-            torch.cuda.synchronize()
+            torch.cuda.current_stream(self.device).synchronize()
 
     def close(self):
         if self.handle:

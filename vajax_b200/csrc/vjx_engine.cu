@@ -18,10 +18,13 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -30,6 +33,8 @@
 #include "vjx_symbolic.h"
 
 static thread_local std::string g_err;
+static void* plugin_open(const char* path, std::string& key);
+static void plugin_close(void* dl, const std::string& key);
 static int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -569,20 +574,25 @@ __global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restr
 //
 // The L entries are taken 32 at a time: lane b fetches the static description of step b (coalesced)
 // and issues ONE non-blocking load of 1/pivot and y of its row k_b; the steps then run in order, and
-// only a step whose inputs still hold the sentinel polls.  The first 32 U values / positions of step
-// b+1 are requested before step b's update is applied, so a row whose dependencies are long finished
-// streams its k-steps at shared-memory speed, and a row at the head of a dependency chain pays one
-// L2 round trip per link.  All polling is CONVERGENT (whole warp iterates until __all_sync): lanes
+// only a step whose inputs still hold the sentinel polls.  The first 32 U values / positions of the
+// next VJX_PF steps are kept in flight in a register ring (with a look-ahead of one step every k-step
+// waited a full L2 latency for its own prefetch: 0.35 us per step), so a row whose dependencies are
+// long finished streams its k-steps at shared-memory speed, and a row at the head of a dependency
+// chain pays one L2 round trip per link.  All polling is CONVERGENT (whole warp iterates until __all_sync): lanes
 // parked in different spin loops starve the lane whose value has arrived (profiles/r1_lu_notes.md).
 //
 // Publication order: U part, pivot reciprocal and y first (what other rows wait for), the L part
 // (needed by nobody before the next kernel) afterwards.
 #define VJX_FACTOR_WARPS 4
 #ifndef VJX_UG
-#define VJX_UG 4   // chunks of 32 U entries requested together per k-step
+#define VJX_UG 4   // chunks of 32 U entries requested together per k-step (beyond the first)
+#endif
+#ifndef VJX_PF
+#define VJX_PF 4   // k-steps whose first chunk is in flight
 #endif
 extern __shared__ double vjx_lu_smem[];
 
+template <int UG>
 __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, const double* __restrict__ csr,
                                                                     const double* __restrict__ b, double scale,
                                                                     const unsigned char* __restrict__ zero_mask, NRStat* st,
@@ -623,82 +633,96 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
         inv_l = ld_poll_u64(lu.inv_diag + k);
         yk_l = ld_poll_u64(lu.y + k);
       }
-      // first group (VJX_UG chunks of 32 U entries) of step 0
-      int ub_c = __shfl_sync(0xffffffffu, ub, 0), ue_c = __shfl_sync(0xffffffffu, ue, 0);
-      long long mb_c = __shfl_sync(0xffffffffu, mb, 0);
-      ull u_c[VJX_UG];
-      int pos_c[VJX_UG];
+      // ring of VJX_PF steps in flight: the first 32 U values / positions of steps bb .. bb+VJX_PF-1
+      ull u_r[VJX_PF];
+      int pos_r[VJX_PF];
 #pragma unroll
-      for (int g = 0; g < VJX_UG; ++g) {
-        u_c[g] = 0ULL; pos_c[g] = 0;
-        const int q = ub_c + g * 32 + lane;
-        if (q < ue_c) { pos_c[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_c[g] = ld_poll_u64(lu.val + q); }
+      for (int j = 0; j < VJX_PF; ++j) {
+        u_r[j] = 0ULL; pos_r[j] = 0;
+        if (j < nb) {
+          const int ub_j = __shfl_sync(0xffffffffu, ub, j), ue_j = __shfl_sync(0xffffffffu, ue, j);
+          const long long mb_j = __shfl_sync(0xffffffffu, mb, j);
+          if (ub_j + lane < ue_j) { pos_r[j] = lu.upd_pos[mb_j + lane]; u_r[j] = ld_poll_u64(lu.val + ub_j + lane); }
+        }
       }
-      for (int bb = 0; bb < nb; ++bb) {
-        // request the first group of the next step before this step's dependent work
-        int ub_n = 0, ue_n = 0;
-        long long mb_n = 0;
-        ull u_n[VJX_UG];
-        int pos_n[VJX_UG];
+      for (int bb0 = 0; bb0 < nb; bb0 += VJX_PF) {
 #pragma unroll
-        for (int g = 0; g < VJX_UG; ++g) { u_n[g] = 0ULL; pos_n[g] = 0; }
-        if (bb + 1 < nb) {
-          ub_n = __shfl_sync(0xffffffffu, ub, bb + 1);
-          ue_n = __shfl_sync(0xffffffffu, ue, bb + 1);
-          mb_n = __shfl_sync(0xffffffffu, mb, bb + 1);
-#pragma unroll
-          for (int g = 0; g < VJX_UG; ++g) {
-            const int q = ub_n + g * 32 + lane;
-            if (q < ue_n) { pos_n[g] = lu.upd_pos[mb_n + (q - ub_n)]; u_n[g] = ld_poll_u64(lu.val + q); }
-          }
-        }
-        ull inv_s = __shfl_sync(0xffffffffu, inv_l, bb), yk_s = __shfl_sync(0xffffffffu, yk_l, bb);
-        if (inv_s == VJX_SENTINEL || yk_s == VJX_SENTINEL) {
-          const int k_s = __shfl_sync(0xffffffffu, k, bb);
-          unsigned spins = 0;
-          while (true) {
-            if (lane == 0) { inv_s = ld_poll_u64(lu.inv_diag + k_s); yk_s = ld_poll_u64(lu.y + k_s); }
-            inv_s = __shfl_sync(0xffffffffu, inv_s, 0);
-            yk_s = __shfl_sync(0xffffffffu, yk_s, 0);
-            if (inv_s != VJX_SENTINEL && yk_s != VJX_SENTINEL) break;
-            if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
-          }
-        }
-        const int kpos = pb + bb - rb;
-        const double l = w[kpos] * bits_f64(inv_s);
-        for (int q0 = ub_c; q0 < ue_c; q0 += 32 * VJX_UG) {
-          if (q0 != ub_c) {
-#pragma unroll
-            for (int g = 0; g < VJX_UG; ++g) {
-              u_c[g] = 0ULL;
-              const int q = q0 + g * 32 + lane;
-              if (q < ue_c) { pos_c[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_c[g] = ld_poll_u64(lu.val + q); }
+        for (int j = 0; j < VJX_PF; ++j) {
+          const int bb = bb0 + j;
+          if (bb < nb) {   // warp-uniform
+            const int ub_c = __shfl_sync(0xffffffffu, ub, bb), ue_c = __shfl_sync(0xffffffffu, ue, bb);
+            const long long mb_c = __shfl_sync(0xffffffffu, mb, bb);
+            ull inv_s = __shfl_sync(0xffffffffu, inv_l, bb), yk_s = __shfl_sync(0xffffffffu, yk_l, bb);
+            if (inv_s == VJX_SENTINEL || yk_s == VJX_SENTINEL) {
+              // row k is not finished yet: poll its pivot / y and, in the same round trip, its first 32 U
+              // values, so that the step can start as soon as the row appears
+              const int k_s = __shfl_sync(0xffffffffu, k, bb);
+              const bool has0 = ub_c + lane < ue_c;
+              unsigned spins = 0;
+              while (true) {
+                if (lane == 0) { inv_s = ld_poll_u64(lu.inv_diag + k_s); yk_s = ld_poll_u64(lu.y + k_s); }
+                if (has0) u_r[j] = ld_poll_u64(lu.val + ub_c + lane);
+                inv_s = __shfl_sync(0xffffffffu, inv_s, 0);
+                yk_s = __shfl_sync(0xffffffffu, yk_s, 0);
+                if (inv_s != VJX_SENTINEL && yk_s != VJX_SENTINEL) break;
+                if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+              }
             }
-          }
-          unsigned spins = 0;
-          while (true) {
-            bool ok = true;
-#pragma unroll
-            for (int g = 0; g < VJX_UG; ++g) {
-              const int q = q0 + g * 32 + lane;
-              if (q < ue_c && u_c[g] == VJX_SENTINEL) { u_c[g] = ld_poll_u64(lu.val + q); ok = false; }
+            const int kpos = pb + bb - rb;
+            const double l = w[kpos] * bits_f64(inv_s);
+            // first chunk: from the ring (re-polled only while it still holds the sentinel)
+            {
+              const bool has = ub_c + lane < ue_c;
+              ull u0 = u_r[j];
+              unsigned spins = 0;
+              while (true) {
+                const bool ok = !has || u0 != VJX_SENTINEL;
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (!ok) u0 = ld_poll_u64(lu.val + ub_c + lane);
+                if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+              }
+              if (has) w[pos_r[j]] = __fma_rn(-l, bits_f64(u0), w[pos_r[j]]);
             }
-            if (__all_sync(0xffffffffu, ok)) break;
-            if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+            // refill this ring slot with step bb + VJX_PF before the long tail of this step
+            u_r[j] = 0ULL;
+            if (bb + VJX_PF < nb) {
+              const int ub_n = __shfl_sync(0xffffffffu, ub, bb + VJX_PF), ue_n = __shfl_sync(0xffffffffu, ue, bb + VJX_PF);
+              const long long mb_n = __shfl_sync(0xffffffffu, mb, bb + VJX_PF);
+              if (ub_n + lane < ue_n) { pos_r[j] = lu.upd_pos[mb_n + lane]; u_r[j] = ld_poll_u64(lu.val + ub_n + lane); }
+            }
+            // rest of U(k,:), UG chunks of 32 requested together
+            for (int q0 = ub_c + 32; q0 < ue_c; q0 += 32 * UG) {
+              ull u_c[UG];
+              int pos_c[UG];
+#pragma unroll
+              for (int g = 0; g < UG; ++g) {
+                u_c[g] = 0ULL; pos_c[g] = 0;
+                const int q = q0 + g * 32 + lane;
+                if (q < ue_c) { pos_c[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_c[g] = ld_poll_u64(lu.val + q); }
+              }
+              unsigned spins = 0;
+              while (true) {
+                bool ok = true;
+#pragma unroll
+                for (int g = 0; g < UG; ++g) {
+                  const int q = q0 + g * 32 + lane;
+                  if (q < ue_c && u_c[g] == VJX_SENTINEL) { u_c[g] = ld_poll_u64(lu.val + q); ok = false; }
+                }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+              }
+#pragma unroll
+              for (int g = 0; g < UG; ++g)
+                if (q0 + g * 32 + lane < ue_c) w[pos_c[g]] = __fma_rn(-l, bits_f64(u_c[g]), w[pos_c[g]]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+              w[kpos] = l;
+              ysum = __fma_rn(-l, bits_f64(yk_s), ysum);
+            }
+            __syncwarp();
           }
-#pragma unroll
-          for (int g = 0; g < VJX_UG; ++g)
-            if (q0 + g * 32 + lane < ue_c) w[pos_c[g]] = __fma_rn(-l, bits_f64(u_c[g]), w[pos_c[g]]);
         }
-        __syncwarp();
-        if (lane == 0) {
-          w[kpos] = l;
-          ysum = __fma_rn(-l, bits_f64(yk_s), ysum);
-        }
-        __syncwarp();
-        ub_c = ub_n; ue_c = ue_n; mb_c = mb_n;
-#pragma unroll
-        for (int g = 0; g < VJX_UG; ++g) { u_c[g] = u_n[g]; pos_c[g] = pos_n[g]; }
       }
     }
     if (dense_row) {
@@ -706,6 +730,7 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
       double* srow = lu.dense + (size_t)(i - lu.dense_start) * (lu.n_dense + 1);
       for (int p = lend + lane; p < re; p += 32) srow[lu.col[p] - lu.dense_start] = w[p - rb];
       if (lane == 0) srow[lu.n_dense] = ysum;
+      if (lu.ts && lane == 0) lu.ts[lu.n + 8 + (i - lu.dense_start)] = global_ns();
       for (int p = rb + lane; p < lend; p += 32) lu.val[p] = w[p - rb];
       __syncwarp();
       continue;
@@ -1531,6 +1556,7 @@ struct ModelState {
   void* dl = nullptr;
   vjx_model_eval_fn eval = nullptr;
   vjx_model_set_const_fn set_const = nullptr;
+  std::string plugin_key;   // non-empty: this handle holds the in-tree instance of the plugin
   int n_dev = 0, n_volt = 0, n_dev_params = 0, n_dev_cache = 0, R = 0, J = 0, n_lim = 0;
   int n_shared = 0, n_shared_cache = 0, n_simparams = 0;
   int limit_offset = 0;
@@ -1563,6 +1589,7 @@ struct vjx_handle {
   bool lu_ready = false;
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_init, lu_kub, lu_order_u, lu_perm_r, lu_perm_c;
+  cudaStream_t last_stream = 0;   // most recent stream an entry point was called with (vjx_destroy waits for it)
   DevBuf<double> lu_scratch, lu_dense;
   DevBuf<int> lu_dense_lstop;
   int lu_grid_load = 0;
@@ -1599,7 +1626,7 @@ struct vjx_handle {
 vjx_handle::~vjx_handle() {
   for (auto* m : models) {
     if (m) {
-      if (m->dl) dlclose(m->dl);
+      if (m->dl) plugin_close(m->dl, m->plugin_key);
       delete m;
     }
   }
@@ -1612,6 +1639,12 @@ vjx_handle::~vjx_handle() {
   if (ev1) cudaEventDestroy(ev1);
   if (own_stream) cudaStreamDestroy(own_stream);
   if (pinned) cudaFreeHost(pinned);
+}
+
+static inline cudaStream_t use_stream(vjx_handle* h, vjx_stream stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h) h->last_stream = s;
+  return s;
 }
 
 static inline int grid_for(const vjx_handle* h, long long n, int block = 256) {
@@ -1628,6 +1661,58 @@ static int csr_find(const std::vector<int>& indptr, const std::vector<int>& indi
   return (int)(it - indices.begin());
 }
 
+// A model plugin keeps the parameters shared by all instances in ITS OWN __constant__ bank, so two live
+// circuit handles (corners of a sweep: different temperature / process values) must not share one loaded
+// instance of the plugin.  The first handle that asks for a path gets the in-tree file itself; while it
+// is in use, every further handle loads a private copy (a temporary file, unlinked once mapped), which
+// the CUDA runtime registers as a separate module with its own constants.
+static std::mutex g_plugin_mu;
+static std::set<std::string> g_plugin_in_use;
+
+static void* plugin_open(const char* path, std::string& key) {
+  key.clear();
+  {
+    std::lock_guard<std::mutex> lk(g_plugin_mu);
+    if (g_plugin_in_use.insert(path).second) key = path;
+  }
+  if (!key.empty()) {
+    void* dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!dl) {
+      std::lock_guard<std::mutex> lk(g_plugin_mu);
+      g_plugin_in_use.erase(key);
+      key.clear();
+    }
+    return dl;
+  }
+  const char* td = getenv("TMPDIR");
+  std::string tmpl = std::string(td && *td ? td : "/tmp") + "/vjx_plugin_XXXXXX.so";
+  std::vector<char> name(tmpl.begin(), tmpl.end());
+  name.push_back(0);
+  int fd = mkstemps(name.data(), 3);
+  if (fd < 0) return nullptr;
+  FILE* in = fopen(path, "rb");
+  bool ok = in != nullptr;
+  if (ok) {
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof(buf), in)) > 0)
+      if (write(fd, buf, got) != (ssize_t)got) { ok = false; break; }
+    fclose(in);
+  }
+  close(fd);
+  void* dl = ok ? dlopen(name.data(), RTLD_NOW | RTLD_LOCAL) : nullptr;
+  unlink(name.data());
+  return dl;
+}
+
+static void plugin_close(void* dl, const std::string& key) {
+  dlclose(dl);
+  if (!key.empty()) {
+    std::lock_guard<std::mutex> lk(g_plugin_mu);
+    g_plugin_in_use.erase(key);
+  }
+}
+
 extern "C" const char* vjx_last_error(void) { return g_err.c_str(); }
 extern "C" int vjx_version(void) { return 100; }
 extern "C" int vjx_device_count(void) {
@@ -1640,7 +1725,10 @@ extern "C" void vjx_clear_cache(void) {}
 extern "C" void vjx_destroy(vjx_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaDeviceSynchronize();
+  // not cudaDeviceSynchronize: another host thread may be capturing a graph for its own handle
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  cudaStreamSynchronize(h->last_stream);
+  cudaStreamSynchronize(0);
   delete h;
 }
 
@@ -1858,8 +1946,8 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
   for (int m = 0; m < d->n_models; ++m) {
     const vjx_model_desc& md = d->models[m];
     ModelState* ms = h->models[m];
-    ms->dl = dlopen(md.plugin_path, RTLD_NOW | RTLD_LOCAL);
-    if (!ms->dl) return fail(VJX_ERR_PLUGIN, std::string("cannot load model plugin: ") + dlerror());
+    ms->dl = plugin_open(md.plugin_path, ms->plugin_key);
+    if (!ms->dl) return fail(VJX_ERR_PLUGIN, std::string("cannot load model plugin: ") + (dlerror() ? dlerror() : md.plugin_path));
     ms->eval = (vjx_model_eval_fn)dlsym(ms->dl, "vjx_model_eval");
     ms->set_const = (vjx_model_set_const_fn)dlsym(ms->dl, "vjx_model_set_const");
     if (!ms->eval || !ms->set_const) return fail(VJX_ERR_PLUGIN, "model plugin lacks vjx_model_eval/vjx_model_set_const");
@@ -1919,7 +2007,7 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
   CK(h->ts.alloc(1));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CK(cudaHostAlloc(&h->pinned, 4096, cudaHostAllocDefault));
-  CK(cudaDeviceSynchronize());
+  CK(cudaStreamSynchronize(0));   // allocations are zero-filled on the legacy stream (not a device-wide sync: see vjx_destroy)
   *out = h.release();
   return VJX_OK;
 }
@@ -2021,7 +2109,8 @@ static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr,
   k_lu_load<<<h->lu_grid_load, 256, 0, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
   h->launches += 1;
   for (int g = 0; g < h->lu_nseg; ++g) {
-    k_lu_rows<<<h->lu_seg_grid[g], 32 * VJX_FACTOR_WARPS, h->lu_seg_rowbuf[g] * VJX_FACTOR_WARPS * sizeof(double), s>>>(
+    auto kfn = k_lu_rows<VJX_UG>;
+    kfn<<<h->lu_seg_grid[g], 32 * VJX_FACTOR_WARPS, h->lu_seg_rowbuf[g] * VJX_FACTOR_WARPS * sizeof(double), s>>>(
         lud, csr, b, scale, zero_mask, h->st.p, g == 0 ? &h->st.p->ticket_f : &h->st.p->ticket_l, h->lu_seg_t0[g],
         h->lu_seg_t1[g], h->lu_seg_rowbuf[g]);
     h->launches += 1;
@@ -2122,11 +2211,8 @@ static int upload_symbolic(vjx_handle* h) {
   L.order_f = h->lu_order_f.p;
   L.n_nol = n_nol;
   L.max_lrow = max_lrow;
-  // dense trailing block: the longest suffix of rows that all have an L part, up to VJX_DT_MAX rows
-  int n_dense = 0;
-  const int dt_cap = getenv("VJX_DT_ROWS") ? std::min(VJX_DT_MAX, atoi(getenv("VJX_DT_ROWS"))) : VJX_DT_MAX;
-  while (n_dense < dt_cap && n_dense < n && S.lu_diag[n - 1 - n_dense] > S.lu_ptr[n - 1 - n_dense]) ++n_dense;
-  if (n_dense < 16 || getenv("VJX_NO_DENSE_TAIL")) n_dense = 0;
+  // dense trailing block: chosen by the symbolic analysis (which also orders the L parts around it)
+  const int n_dense = S.n_dense;
   const int ds = n - n_dense;
   {
     std::vector<int> lstop((size_t)std::max(n_dense, 1), 0);
@@ -2135,6 +2221,8 @@ static int upload_symbolic(vjx_handle* h) {
       int p = S.lu_ptr[i];
       while (p < S.lu_diag[i] && S.lu_col[p] < ds) ++p;
       lstop[t] = p;
+      for (int q = p; q < S.lu_diag[i]; ++q)
+        if (S.lu_col[q] < ds) return fail(VJX_ERR_INVALID, "L part of a dense-block row is not ordered bulk-first");
     }
     CK(h->lu_dense_lstop.upload(lstop));
     CK(h->lu_dense.alloc((size_t)std::max(n_dense, 1) * (n_dense + 1)));
@@ -2196,9 +2284,12 @@ static int upload_symbolic(vjx_handle* h) {
       const int rowbuf = std::max(64, std::min(kRowbufCap, (want + 31) / 32 * 32));
       const int smem = rowbuf * VJX_FACTOR_WARPS * (int)sizeof(double);
       int occ = 1;
-      CK(cudaFuncSetAttribute(k_lu_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      // (requesting 8 chunks of U at a time for the long rows costs registers and was slower: mul64
+      // 2.11 vs 1.76 ms, gpurun s6v)
+      auto kfn = k_lu_rows<VJX_UG>;
+      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kRowbufCap * VJX_FACTOR_WARPS * (int)sizeof(double)));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lu_rows, 32 * VJX_FACTOR_WARPS, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 32 * VJX_FACTOR_WARPS, smem));
       occ = std::max(1, occ);
       const int s_i = h->lu_nseg++;
       h->lu_seg_t0[s_i] = t0;
@@ -2235,7 +2326,10 @@ static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s) {
   CK(cudaMemcpy(vals.data(), csr_dev, sizeof(double) * h->nse, cudaMemcpyDeviceToHost));
   std::string err;
   double tol = h->o.pivot_tol > 0 ? h->o.pivot_tol : 1e-3;
-  int rc = vjx_symbolic_analyze(h->n_aug, h->h_indptr.data(), h->h_indices.data(), vals.data(), tol, true, h->sym, err);
+  int dense_cap = VJX_DT_MAX;
+  if (getenv("VJX_DT_ROWS")) dense_cap = std::min(VJX_DT_MAX, atoi(getenv("VJX_DT_ROWS")));
+  if (getenv("VJX_NO_DENSE_TAIL")) dense_cap = 0;
+  int rc = vjx_symbolic_analyze(h->n_aug, h->h_indptr.data(), h->h_indices.data(), vals.data(), tol, true, h->sym, err, dense_cap);
   if (rc != 0) return fail(VJX_ERR_SINGULAR, "LU analysis failed: " + err);
   return upload_symbolic(h);
 }
@@ -2275,7 +2369,7 @@ static int check_device_error(vjx_handle* h, cudaStream_t s) {
 extern "C" int vjx_lu_solve(vjx_handle* h, const double* csr_data_dev, const double* b_dev, double* x_dev, vjx_stream stream) {
   if (!h || !csr_data_dev || !b_dev || !x_dev) return fail(VJX_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   int rc = ensure_lu(h, csr_data_dev, s);
   if (rc) return rc;
   k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
@@ -2292,7 +2386,7 @@ extern "C" int vjx_build_system(vjx_handle* h, const double* X, const double* vs
                                 double* limit_out, double* maxres_out, vjx_stream stream) {
   if (!h || !X) return fail(VJX_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   k_set_ctl<<<1, 1, 0, s>>>(h->ctl.p, c0, c1, d1, c2, gmin, gshunt, (double)nr_iteration, h->o.gmin);
   h->launches++;
   BuildPtrs b{};
@@ -2353,7 +2447,7 @@ extern "C" int vjx_nr_solve(vjx_handle* h, const double* X_init, const double* v
                             double* limit_out, double* maxres_out, vjx_stream stream) {
   if (!h || !X_init || !X_out) return fail(VJX_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   const int nx = h->n_total + h->n_vs;
   if (max_iterations < 0) max_iterations = h->o.tran_itl;
   k_set_ctl<<<1, 1, 0, s>>>(h->ctl.p, c0, c1, d1, c2, gmin, gshunt, 0.0, h->o.gmin);
@@ -2427,7 +2521,7 @@ extern "C" int vjx_tran_begin(vjx_handle* h, const double* X0, const double* Q_i
                               vjx_stream stream) {
   if (!h || !X0) return fail(VJX_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   const int nt = h->n_total, nu = std::max(h->n_unknowns, 1), nx = h->n_total + h->n_vs, nvs1 = std::max(h->n_vs, 1);
   h->H = h->o.max_order + 2;
   if (h->H > 4 || h->H < 3) return fail(VJX_ERR_INVALID, "max_order must be 1 or 2");
@@ -2563,7 +2657,7 @@ static int build_tran_graph(vjx_handle* h, int attempts_limit, cudaStream_t s) {
 extern "C" int vjx_tran_run(vjx_handle* h, int max_attempts, int* attempts, vjx_stream stream) {
   if (!h || !h->X.p) return fail(VJX_ERR_INVALID, "vjx_tran_begin not called");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   TranScalars* hts = (TranScalars*)((char*)h->pinned + 512);
   CK(cudaMemcpyAsync(hts, h->ts.p, sizeof(TranScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -2656,7 +2750,7 @@ extern "C" int vjx_tran_set_step_limit(vjx_handle* h, int step_limit, vjx_stream
 extern "C" int vjx_tran_scalars(vjx_handle* h, double* out, vjx_stream stream) {
   if (!h || !h->ts.p) return fail(VJX_ERR_INVALID, "null handle");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   TranScalars* hts = (TranScalars*)((char*)h->pinned + 512);
   NRStat* hs = (NRStat*)h->pinned;
   CK(cudaMemcpyAsync(hts, h->ts.p, sizeof(TranScalars), cudaMemcpyDeviceToHost, s));
@@ -2672,7 +2766,7 @@ extern "C" int vjx_tran_read(vjx_handle* h, int row0, int rows, double* times, d
   if (!h || !h->X.p) return fail(VJX_ERR_INVALID, "no transient state");
   if (row0 < 0 || rows < 0 || row0 + rows > h->max_steps) return fail(VJX_ERR_INVALID, "row range");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   const int nvs1 = std::max(h->n_vs, 1);
   if (times) CK(cudaMemcpyAsync(times, h->times_out.p + row0, sizeof(double) * rows, cudaMemcpyDeviceToHost, s));
   if (V_out) CK(cudaMemcpyAsync(V_out, h->V_out.p + (size_t)row0 * h->n_ext, sizeof(double) * (size_t)rows * h->n_ext, cudaMemcpyDeviceToHost, s));
@@ -2693,7 +2787,7 @@ extern "C" int vjx_tran_records(vjx_handle* h, int first, int count, double* out
 extern "C" int vjx_tran_state(vjx_handle* h, double* X, double* Q_prev, double* dQdt_prev, vjx_stream stream) {
   if (!h || !h->X.p) return fail(VJX_ERR_INVALID, "no transient state");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   if (X) CK(cudaMemcpyAsync(X, h->X.p, sizeof(double) * (h->n_total + h->n_vs), cudaMemcpyDeviceToHost, s));
   if (Q_prev) CK(cudaMemcpyAsync(Q_prev, h->Q_prev.p, sizeof(double) * h->n_unknowns, cudaMemcpyDeviceToHost, s));
   if (dQdt_prev) CK(cudaMemcpyAsync(dQdt_prev, h->dQdt_prev.p, sizeof(double) * h->n_unknowns, cudaMemcpyDeviceToHost, s));
@@ -2720,7 +2814,7 @@ extern "C" int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* le
   if (!h || !h->X.p || !h->lu_ready) return fail(VJX_ERR_INVALID, "run a transient first");
   if (phase != 3 && phase != 5) return fail(VJX_ERR_INVALID, "phase must be 3 (factor + forward solve) or 5 (back solve)");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   const int n = h->sym.n;
   DevBuf<ull> ts;
   CK(ts.alloc((size_t)n + 1 + 4100));
@@ -2728,17 +2822,24 @@ extern "C" int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* le
   k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
   if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
   lud.ts = ts.p;
-  CK(cudaMemsetAsync(ts.p, 0, sizeof(ull) * ((size_t)n + 8), s));
+  CK(cudaMemsetAsync(ts.p, 0, sizeof(ull) * ((size_t)n + 8 + VJX_DT_MAX), s));
   k_stamp_now<<<1, 1, 0, s>>>(ts.p + n);
   if (phase == 3) launch_lu_factor(h, lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
   if (phase == 5) k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(lud, h->delta.p, h->st.p);
-  std::vector<ull> hts((size_t)n + 8);
+  std::vector<ull> hts((size_t)n + 8 + VJX_DT_MAX);
   CK(cudaStreamSynchronize(s));
-  CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 8), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 8 + VJX_DT_MAX), cudaMemcpyDeviceToHost));
   if (phase == 3 && h->lud.n_dense > 0 && getenv("VJX_DT_TRACE")) {
     auto us = [&](int q) { return ((long long)hts[n + q] - (long long)hts[n]) / 1e3; };
     fprintf(stderr, "dense trailing block (%d rows), us since factorisation start: begin %.1f, loaded %.1f, eliminated %.1f, "
             "spilled %.1f, solved %.1f\n", h->lud.n_dense, us(1), us(2), us(3), us(4), us(5));
+    fprintf(stderr, "row updates of the dense-block rows done at (us): row(offset) Lbulk Ldense -> t\n");
+    for (int t = 0; t < h->lud.n_dense; t += 6) {
+      const int i = n - h->lud.n_dense + t;
+      int lb = 0;
+      for (int p = h->sym.lu_ptr[i]; p < h->sym.lu_diag[i]; ++p) lb += h->sym.lu_col[p] < n - h->lud.n_dense;
+      fprintf(stderr, "  %3d %3d %3d -> %.1f\n", t, lb, h->sym.lu_diag[i] - h->sym.lu_ptr[i] - lb, us(8 + t));
+    }
   }
   for (int i = 0; i < n; ++i) {
     ns_out[i] = (double)((long long)hts[i] - (long long)hts[n]);
@@ -2753,7 +2854,7 @@ extern "C" long long vjx_launch_count(vjx_handle* h) { return h ? h->launches : 
 extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg, int* launches, vjx_stream stream) {
   if (!h || !h->X.p || !h->lu_ready) return fail(VJX_ERR_INVALID, "run a transient first");
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = use_stream(h, stream);
   BuildPtrs b{};
   tran_build_ptrs(h, b);
   cudaEvent_t e0, e1;

@@ -231,7 +231,7 @@ Peel peel_singletons(int n, const int* indptr, const int* indices, const double*
 }  // namespace
 
 int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const double* values,
-                         double pivot_tol, bool build_update_stream, VjxSymbolic& S, std::string& err) {
+                         double pivot_tol, bool build_update_stream, VjxSymbolic& S, std::string& err, int dense_cap) {
   S = VjxSymbolic();
   S.n = n;
   if (n <= 0) { err = "empty matrix"; return -1; }
@@ -472,6 +472,45 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
     }
     S.order_l.swap(bl);
     S.order_u.swap(bu);
+  }
+  // --- dense trailing block and execution order of the L parts (see vjx_symbolic.h)
+  {
+    int nd = 0;
+    while (nd < dense_cap && nd < n && S.lu_diag[n - 1 - nd] > S.lu_ptr[n - 1 - nd]) ++nd;
+    if (nd < 16) nd = 0;
+    S.n_dense = nd;
+    const int ds = n - nd;
+    // depth[k]: dependency depth of row k counting both what it waits for (L(k,j) != 0: row j finished)
+    // and what must be applied before it inside any row that holds both (U(j,k) != 0)
+    std::vector<int> depth(n, 0);
+    for (int k = 0; k < n; ++k) {
+      int d = depth[k];   // pushed from rows j < k with U(j,k) != 0
+      for (int pp = S.lu_ptr[k]; pp < S.lu_diag[k]; ++pp) d = std::max(d, depth[S.lu_col[pp]] + 1);
+      depth[k] = d;
+      for (int pp = S.lu_diag[k] + 1; pp < S.lu_ptr[k + 1]; ++pp) {
+        int& t = depth[S.lu_col[pp]];
+        t = std::max(t, d + 1);
+      }
+    }
+    std::vector<int> idx, col2, src2;
+    for (int i = 0; i < n; ++i) {
+      const int rb = S.lu_ptr[i], dg = S.lu_diag[i];
+      if (dg - rb < 2) continue;
+      idx.resize(dg - rb);
+      std::iota(idx.begin(), idx.end(), rb);
+      std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+        const int ka = S.lu_col[a], kb = S.lu_col[b];
+        const bool da = ka >= ds, db = kb >= ds;
+        if (da != db) return db;
+        if (depth[ka] != depth[kb]) return depth[ka] < depth[kb];
+        return ka < kb;
+      });
+      col2.resize(dg - rb);
+      src2.resize(dg - rb);
+      for (int t = 0; t < dg - rb; ++t) { col2[t] = S.lu_col[idx[t]]; src2[t] = S.lu_src[idx[t]]; }
+      std::copy(col2.begin(), col2.end(), S.lu_col.begin() + rb);
+      std::copy(src2.begin(), src2.end(), S.lu_src.begin() + rb);
+    }
   }
   // --- flops and the scatter program
   double fl = 0.0;

@@ -48,6 +48,13 @@ struct VjxSymbolic {
   // Rows whose U part is longer than kLongRow (a rail row kept as a column-singleton pivot has one
   // entry per attached device) are left out of order_u and solved by a whole thread block each.
   std::vector<int> long_u;
+  // Dense trailing block: rows [n - n_dense, n) hand their part right of column n - n_dense to a dense
+  // kernel.  The L part of every row is stored in EXECUTION order, not column order: sorted by an
+  // estimate of when row k is finished (its dependency depth), columns of the dense block last.  Any
+  // order that applies step k' before step k whenever U(k',k) != 0 is valid; taking the steps whose
+  // rows finish early first keeps a row from idling at one late dependency with hundreds of ready
+  // steps queued behind it.
+  int n_dense = 0;
   int n_singletons = 0;           // pivots peeled as row / column singletons (no fill, no updates)
   int n_core = 0;                 // unknowns left for AMD + Gilbert-Peierls
   double flops = 0.0;             // 2 * sum_k nnz(L(:,k)) * nnz(U(k,:)) + nnz(L)
@@ -55,8 +62,11 @@ struct VjxSymbolic {
 };
 
 // Returns 0 on success; <0 and fills err otherwise.
+// dense_cap: upper bound on the rows of the dense trailing block (0 = none); out.n_dense is the longest
+// suffix of rows that all have an L part, up to that cap.
 int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const double* values,
-                         double pivot_tol, bool build_update_stream, VjxSymbolic& out, std::string& err);
+                         double pivot_tol, bool build_update_stream, VjxSymbolic& out, std::string& err,
+                         int dense_cap = 0);
 
 // Approximate minimum degree ordering on the pattern of A + A^T. perm[k] = k-th pivot.
 void vjx_amd_order(int n, const int* indptr, const int* indices, std::vector<int>& perm);
