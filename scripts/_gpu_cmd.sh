@@ -1,6 +1,15 @@
 mkdir -p gpurun_out
-T=s6l
-python -m pytest tests -m gpu -x -q 2>&1 | tail -n 3
-VJX_DT_TRACE=1 python scripts/lu_timeline.py 16 > gpurun_out/r1_${T}_timeline16.txt 2>&1; grep "==\|dense" gpurun_out/r1_${T}_timeline16.txt | tail -n 3
-python scripts/lu_timeline.py 64 > gpurun_out/r1_${T}_timeline64.txt 2>&1; grep "==" gpurun_out/r1_${T}_timeline64.txt
-python scripts/mul64_probe.py 64 6 2>&1 | grep "phase lu\|steady\|residual"
+for b in 128 64 32; do echo block=$b; VJX_EVAL_BLOCK=$b python - <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+from vajax_b200.analysis.engine import B200Engine
+from vajax_b200.benchmarks import circuits
+from vajax_b200.models.fixtures import get_bundle
+bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
+e = B200Engine(circuits.multiplier_circuit(16), bundles, use_device_graph=True).prepare()
+e.run_transient(max_steps=12)
+print("eval ms", e.time_phase(0, 50))
+e.tran_begin(max_steps=101); e.tran_run(step_limit=101); print("ms/step", e.tran_run_ms()[0]/100)
+e.close()
+PY
+done

@@ -765,12 +765,12 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
 #define VJX_DT_MAX 159
 #define VJX_DT_LDS 161
 #define VJX_DT_SMEM (160 * VJX_DT_LDS * 8)
+// (rows beyond T hold zeros in r and publish zeros into the pivot column, so they need no guard: -0 * u
+// leaves them zero; lanes left of the pivot inside its column block see u = 0 instead of a predicate)
 #define VJX_DT_UPDATE_ROW(A2, BC)                                                                  \
   {                                                                                                \
-    const int i_ = wi + 16 * (A2);                                                                 \
-    const double nl_ = i_ < T ? -(lc[i_] * inv) : 0.0;                                             \
-    if (act0) r[A2][BC] = __fma_rn(nl_, u[BC], r[A2][BC]);                                         \
-    _Pragma("unroll") for (int b = (BC) + 1; b < VJX_DT_C; ++b) r[A2][b] = __fma_rn(nl_, u[b], r[A2][b]); \
+    const double nl_ = -(lcw[16 * (A2)] * inv);                                                    \
+    _Pragma("unroll") for (int b = (BC); b < VJX_DT_C; ++b) r[A2][b] = __fma_rn(nl_, u[b], r[A2][b]); \
   }
 #define VJX_DT_PUBLISH_ROW(A2, BC, LP)                                                             \
   {                                                                                                \
@@ -797,10 +797,11 @@ __device__ __forceinline__ void vjx_dt_panel(double (&r)[VJX_DT_R][VJX_DT_C], do
       __syncthreads();
       if (dbg == 1) continue;
       const double inv = ur[160];
+      const double* const lcw = lc + wi;
       double u[VJX_DT_C];
 #pragma unroll
       for (int b = bcol; b < VJX_DT_C; ++b) u[b] = ur[lane + 32 * b];
-      const bool act0 = lane > lpiv;   // inside the pivot's column block only the columns right of it
+      if (lane <= lpiv) u[bcol] = 0.0;   // inside the pivot's column block only the columns right of it change
       const bool has_next = k + 1 < T;
       if (w < 15) {
         // next pivot: row 16 A + w + 1 = register row A of warp w + 1, same column block
