@@ -1,15 +1,9 @@
 mkdir -p gpurun_out
-for b in 128 64 32; do echo block=$b; VJX_EVAL_BLOCK=$b python - <<'PY'
-import sys, os
-sys.path.insert(0, os.getcwd())
-from vajax_b200.analysis.engine import B200Engine
-from vajax_b200.benchmarks import circuits
-from vajax_b200.models.fixtures import get_bundle
-bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
-e = B200Engine(circuits.multiplier_circuit(16), bundles, use_device_graph=True).prepare()
-e.run_transient(max_steps=12)
-print("eval ms", e.time_phase(0, 50))
-e.tran_begin(max_steps=101); e.tran_run(step_limit=101); print("ms/step", e.tran_run_ms()[0]/100)
-e.close()
-PY
+T=s6y
+python bench.py > gpurun_out/r1_${T}_bench.json 2> gpurun_out/r1_${T}_bench.err; echo "bench rc=$?"; tail -c 300 gpurun_out/r1_${T}_bench.err
+python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/r1_${T}_ref.json 2>/dev/null; echo "ref rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r1_${T}_launches.csv python bench.py --no-graph --steps 3 --warmup 3 --corners 1 --mul64-steps 0 --no-cpu-baseline > gpurun_out/r1_${T}_ncu_bench.log 2>&1
+for k in k_lu_rows k_lu_usolve k_lu_dense k_lu_load; do
+ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -f -o gpurun_out/r1_${T}_$k python scripts/run_steps.py 16 4 > /dev/null 2>&1
 done
+ls gpurun_out | grep $T
