@@ -141,3 +141,62 @@ def test_live_engines_keep_their_own_model_constants(bundles):
     b.close()
     assert s1["n_steps"] == s0["n_steps"] and np.array_equal(t0, t1) and np.array_equal(V0, V1)
     assert not np.array_equal(V1, V2)   # the two corners really differ
+
+
+def test_c6288_first_steps_match_the_oracle(c6288, bundles):
+    """BASELINE.json's full c6288 size against the CPU oracle on the first accepted steps (the oracle
+    needs ~0.15 s per step here): same accepted-step sequence (step, nr_iters, accept/reject), t and dt to
+    the accuracy of the solves (1e-9 relative, north_star), waveforms within 1e-6 RMS relative."""
+    from oracle.engine import OracleEngine
+
+    K = 9
+    o = OracleEngine(circuits.multiplier_circuit(16), bundles)
+    rec = []
+    to, Vo, so = o.run_transient(max_steps=K, record=rec)
+    tg, Vg, sg = c6288.run_transient(max_steps=K)
+    assert sg["error_flags"] == 0 and sg["n_steps"] == so["n_steps"] == K
+    assert sg["total_nr_iterations"] == so["total_nr_iterations"] and sg["rejected_steps"] == so["rejected_steps"]
+    gr = c6288.step_records()
+    assert len(gr) == len(rec)
+    for a, b in zip(gr, rec):
+        assert int(a[0]) == b["step"] and int(a[3]) == b["nr_iters"] and bool(a[4]) == b["accept"]
+        assert abs(a[1] - b["t_next"]) <= 1e-9 * abs(b["t_next"]) and abs(a[2] - b["dt"]) <= 1e-9 * b["dt"]
+    span = max(np.max(Vo[:K]) - np.min(Vo[:K]), 1e-12)
+    rms = np.sqrt(np.mean((Vg[:K] - Vo[:K]) ** 2)) / span
+    assert rms < 1e-6, rms
+    assert np.max(np.abs(Vg[:K] - Vo[:K])) < 1e-7
+
+
+@pytest.mark.timeout(600)
+def test_mul64_scale_properties(bundles):
+    """BASELINE.json's largest configuration (mul64: 266,408 MOSFETs, 666,408 unknowns): the analysis sizes
+    the reference documents, a few transient steps without device error flags, and the size-independent
+    linear-solve properties (residual of A x = b on the current Jacobian, run-to-run bit identity)."""
+    import scipy.sparse as sp
+
+    from vajax_b200.analysis.engine import B200Engine
+
+    e = B200Engine(circuits.mul64_circuit(64), bundles, use_device_graph=True).prepare()
+    assert e.n_aug == 666408 and sum(1 for d in e.devices if d["model"] == "psp103") == 266408
+    t, V, st = e.run_transient(max_steps=4, read_outputs=False)
+    assert st["error_flags"] == 0 and st["n_steps"] == 4
+    lu = e.lu_stats()
+    assert lu["n"] == e.n_aug and lu["n_singletons"] + lu["n_core"] == e.n_aug
+    sc = e.tran_scalars()
+    X, Q, dQ = e.tran_state()
+    vs, isv = e.eval_sources(sc["t"])
+    nu = e.n_unknowns
+    c0 = 2.0 / sc["dt"]
+    csr = e.build_system(X, vs, isv, Q, c0, 1e-12, 0.0, -c0, -1.0, dQ, 0.0, None, None, 1)[0].copy()
+    rows = np.repeat(np.arange(e.n_aug), np.diff(e.csr_indptr))
+    noi = np.zeros(e.n_aug, bool)
+    noi[e.noi_indices - 1] = True
+    csr[noi[rows] | ((rows < nu) & noi[e.csr_indices])] = 0.0
+    csr[noi[rows] & (rows == e.csr_indices)] = 1.0
+    A = sp.csr_matrix((csr, e.csr_indices, e.csr_indptr), shape=(e.n_aug, e.n_aug))
+    rhs = np.random.default_rng(3).normal(size=e.n_aug)
+    x = e.lu_solve(csr, rhs)
+    r = A @ x - rhs
+    assert np.max(np.abs(r)) <= 1e-9 * max(1.0, np.max(np.abs(A @ np.abs(x))))
+    assert np.array_equal(x, e.lu_solve(csr, rhs))
+    e.close()
