@@ -690,7 +690,8 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
               const long long mb_n = __shfl_sync(0xffffffffu, mb, bb + VJX_PF);
               if (ub_n + lane < ue_n) { pos_r[j] = lu.upd_pos[mb_n + lane]; u_r[j] = ld_poll_u64(lu.val + ub_n + lane); }
             }
-            // rest of U(k,:), UG chunks of 32 requested together
+            // rest of U(k,:), UG chunks of 32 requested together (keeping the next request in flight while
+            // this one is applied costs 6 registers too many: occupancy or spills, slower on both circuits)
             for (int q0 = ub_c + 32; q0 < ue_c; q0 += 32 * UG) {
               ull u_c[UG];
               int pos_c[UG];
@@ -947,27 +948,36 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int STRIDE, typename Peek>
 __device__ __forceinline__ double row_dot(const LUDev& lu, int begin, int end, int tid, NRStat* st, int errbit, Peek peek) {
   double part = 0.0;
-  for (int base = begin; base < end; base += 4 * STRIDE) {
+  // highest columns first: in the back solve they are the unknowns that become available first, so a long
+  // row consumes its early dependencies while it waits and is left with one batch when the last one arrives
+  const int n_batches = (end - begin + 4 * STRIDE - 1) / (4 * STRIDE);
+  for (int bi = n_batches - 1; bi >= 0; --bi) {
+    const int base = begin + bi * 4 * STRIDE;
     int c[4];
-    double v[4];
+    double v[4], x[4];
+    bool ok[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int p = base + tid + u * STRIDE;
       c[u] = p < end ? lu.col[p] : -1;
       v[u] = p < end ? lu.val[p] : 0.0;
     }
+    // request all four unknowns of the batch at once; only those still missing are polled again
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (base + u * STRIDE >= end) break;   // uniform: no thread has an entry in this slot
-      bool ok = c[u] < 0;
-      double x = 0.0;
+      x[u] = 0.0;
+      ok[u] = c[u] < 0 || peek(c[u], &x[u]);
+    }
+#pragma unroll
+    for (int u = 3; u >= 0; --u) {
+      if (base + u * STRIDE >= end) continue;   // uniform: no thread has an entry in this slot
       unsigned spins = 0;
       while (true) {
-        if (!ok) ok = peek(c[u], &x);
-        if (__all_sync(0xffffffffu, ok)) break;
+        if (__all_sync(0xffffffffu, ok[u])) break;
+        if (!ok[u]) ok[u] = peek(c[u], &x[u]);
         if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, errbit); break; }
       }
-      if (c[u] >= 0) part += v[u] * x;
+      if (c[u] >= 0) part += v[u] * x[u];
     }
   }
   return part;
