@@ -64,8 +64,8 @@ struct NRStat {
   ull max_dv_bits;   // max |delta V|
   ull lim_delta_bits;
   ull lim_ref_bits;
-  unsigned epoch;    // LU flag epoch
-  unsigned ticket_f, ticket_l, ticket_u;
+  unsigned epoch;    // count of NR iterations started (diagnostics)
+  unsigned ticket_f, ticket_l, ticket_u;   // row tickets: k_lu_rows launch 1 / launch 2, k_lu_usolve
 };
 
 struct TranScalars {
@@ -99,7 +99,6 @@ struct LUDev {
   // the rest (+ their partial y in column n_dense) to k_lu_dense_tail as a dense n_dense x (n_dense+1)
   // row-major matrix.
   int dense_start, n_dense;
-  int dbg;                     // timing experiments only (VJX_DT_DBG), 0 in production
   const int* dense_lstop;      // per dense row: first position of the row whose column is >= dense_start
   double* dense;
   int tail_start;              // rows [tail_start, n): chain tail of the back solve, one thread block
@@ -114,21 +113,6 @@ struct LUDev {
   double* xp;
 };
 
-// Dependency flags are polled with a RELAXED gpu-scope load.  ld.acquire.gpu compiles to
-// LDG.STRONG.GPU + CCTL.IVALL on sm_100a, i.e. every poll wipes the SM's whole L1, and with hundreds
-// of warps spinning nothing static (row pointers, columns, scatter lists) ever stays cached.  The
-// ordering that matters is kept without it: the producer publishes with st.release.gpu (MEMBAR +
-// store), the consumer's data loads are issued only after the poll has returned the new epoch
-// (control dependency; the asm carries a memory clobber for the compiler) and they read through
-// ld.global.cg, which never hits a stale L1 line.
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ double nan0(double v) { return (v != v) ? 0.0 : v; }
 __device__ __forceinline__ ull global_ns() {
   ull t;
@@ -784,7 +768,7 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
   }
 template <int A>
 __device__ __forceinline__ void vjx_dt_panel(double (&r)[VJX_DT_R][VJX_DT_C], double* urow, double* lcol, const int T,
-                                             const int wi, const int lane, bool& bad, const int dbg) {
+                                             const int wi, const int lane, bool& bad) {
   {
     constexpr int bcol = A >> 1;
     for (int w = 0; w < 16; ++w) {
@@ -796,7 +780,6 @@ __device__ __forceinline__ void vjx_dt_panel(double (&r)[VJX_DT_R][VJX_DT_C], do
       double* const lcn = lcol + ((k + 1) & 1) * 160;
       const int lpiv = 16 * (A & 1) + w;
       __syncthreads();
-      if (dbg == 1) continue;
       const double inv = ur[160];
       const double* const lcw = lc + wi;
       double u[VJX_DT_C];
@@ -876,16 +859,16 @@ __global__ void __launch_bounds__(VJX_DT_THREADS, 1) k_lu_dense_tail(LUDev lu, d
       for (int a2 = 0; a2 < VJX_DT_R; ++a2) lcol[wi + 16 * a2] = r[a2][0];
     }
   }
-  vjx_dt_panel<0>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<1>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<2>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<3>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<4>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<5>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<6>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<7>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<8>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
-  vjx_dt_panel<9>(r, urow, lcol, T, wi, lane, bad, lu.dbg);
+  vjx_dt_panel<0>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<1>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<2>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<3>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<4>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<5>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<6>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<7>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<8>(r, urow, lcol, T, wi, lane, bad);
+  vjx_dt_panel<9>(r, urow, lcol, T, wi, lane, bad);
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&st->error, 2);
   if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 3] = global_ns();
   double* const S = vjx_dt_smem;
@@ -1087,8 +1070,8 @@ __global__ void k_nr_begin(NRStat* st, double* ctl, int max_iter, int reset_iter
   st->cont = 1;
 }
 
-// Runs at the head of every NR iteration: clears the per-iteration reductions and opens a new
-// LU epoch (flags from earlier factorizations become stale without being cleared).
+// Runs at the head of every NR iteration: clears the per-iteration reductions and resets the LU row
+// tickets.
 __global__ void k_iter_begin(NRStat* st) {
   st->bad_res = 0;
   st->bad_delta = 0;
@@ -2239,7 +2222,6 @@ static int upload_symbolic(vjx_handle* h) {
     CK(h->lu_dense.alloc((size_t)std::max(n_dense, 1) * (n_dense + 1)));
   }
   L.dense_start = ds;
-  L.dbg = getenv("VJX_DT_DBG") ? atoi(getenv("VJX_DT_DBG")) : 0;
   L.n_dense = n_dense;
   L.dense_lstop = h->lu_dense_lstop.p;
   L.dense = h->lu_dense.p;
@@ -2877,7 +2859,7 @@ extern "C" int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg
   for (int r = 0; r < reps + 1; ++r) {
     long long l0 = h->launches;
     if (phase == 3 || phase == 4 || phase == 5) {
-      // each LU phase needs a fresh epoch and the preceding phases' results
+      // each LU phase needs fresh tickets and the preceding phases' results
       k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
       if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
     }
