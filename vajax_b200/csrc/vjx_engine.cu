@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restr
 #endif
 extern __shared__ double vjx_lu_smem[];
 
-template <int UG>
+template <int UG, bool PIPE>
 __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, const double* __restrict__ csr,
                                                                     const double* __restrict__ b, double scale,
                                                                     const unsigned char* __restrict__ zero_mask, NRStat* st,
@@ -674,31 +674,78 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
               const long long mb_n = __shfl_sync(0xffffffffu, mb, bb + VJX_PF);
               if (ub_n + lane < ue_n) { pos_r[j] = lu.upd_pos[mb_n + lane]; u_r[j] = ld_poll_u64(lu.val + ub_n + lane); }
             }
-            // rest of U(k,:), UG chunks of 32 requested together (keeping the next request in flight while
-            // this one is applied costs 6 registers too many: occupancy or spills, slower on both circuits)
-            for (int q0 = ub_c + 32; q0 < ue_c; q0 += 32 * UG) {
-              ull u_c[UG];
-              int pos_c[UG];
-#pragma unroll
-              for (int g = 0; g < UG; ++g) {
-                u_c[g] = 0ULL; pos_c[g] = 0;
-                const int q = q0 + g * 32 + lane;
-                if (q < ue_c) { pos_c[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_c[g] = ld_poll_u64(lu.val + q); }
-              }
-              unsigned spins = 0;
-              while (true) {
-                bool ok = true;
+            if constexpr (PIPE) {
+              // long rows (their launch is limited by shared memory, registers are free): the next request of
+              // UG chunks is in flight while the current one is validated and applied, so a 300-entry U row
+              // costs about one L2 round trip instead of three
+              if (ub_c + 32 < ue_c) {
+                ull u_a[UG], u_b[UG];
+                int pos_a[UG], pos_b[UG];
+                int q0 = ub_c + 32;
 #pragma unroll
                 for (int g = 0; g < UG; ++g) {
+                  u_a[g] = 0ULL; pos_a[g] = 0;
                   const int q = q0 + g * 32 + lane;
-                  if (q < ue_c && u_c[g] == VJX_SENTINEL) { u_c[g] = ld_poll_u64(lu.val + q); ok = false; }
+                  if (q < ue_c) { pos_a[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_a[g] = ld_poll_u64(lu.val + q); }
                 }
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
-              }
+                while (true) {
+                  const int q1 = q0 + 32 * UG;
+                  const bool more = q1 < ue_c;
+                  if (more) {
 #pragma unroll
-              for (int g = 0; g < UG; ++g)
-                if (q0 + g * 32 + lane < ue_c) w[pos_c[g]] = __fma_rn(-l, bits_f64(u_c[g]), w[pos_c[g]]);
+                    for (int g = 0; g < UG; ++g) {
+                      u_b[g] = 0ULL; pos_b[g] = 0;
+                      const int q = q1 + g * 32 + lane;
+                      if (q < ue_c) { pos_b[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_b[g] = ld_poll_u64(lu.val + q); }
+                    }
+                  }
+                  unsigned spins = 0;
+                  while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int g = 0; g < UG; ++g) {
+                      const int q = q0 + g * 32 + lane;
+                      if (q < ue_c && u_a[g] == VJX_SENTINEL) { u_a[g] = ld_poll_u64(lu.val + q); ok = false; }
+                    }
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+                  }
+#pragma unroll
+                  for (int g = 0; g < UG; ++g)
+                    if (q0 + g * 32 + lane < ue_c) w[pos_a[g]] = __fma_rn(-l, bits_f64(u_a[g]), w[pos_a[g]]);
+                  if (!more) break;
+#pragma unroll
+                  for (int g = 0; g < UG; ++g) { u_a[g] = u_b[g]; pos_a[g] = pos_b[g]; }
+                  q0 = q1;
+                }
+              }
+            } else {
+              // rest of U(k,:), UG chunks of 32 requested together (keeping the next request in flight
+              // costs 6 registers: one block per SM less in the wide launch, which is bound by occupancy)
+              for (int q0 = ub_c + 32; q0 < ue_c; q0 += 32 * UG) {
+                ull u_c[UG];
+                int pos_c[UG];
+  #pragma unroll
+                for (int g = 0; g < UG; ++g) {
+                  u_c[g] = 0ULL; pos_c[g] = 0;
+                  const int q = q0 + g * 32 + lane;
+                  if (q < ue_c) { pos_c[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_c[g] = ld_poll_u64(lu.val + q); }
+                }
+                unsigned spins = 0;
+                while (true) {
+                  bool ok = true;
+  #pragma unroll
+                  for (int g = 0; g < UG; ++g) {
+                    const int q = q0 + g * 32 + lane;
+                    if (q < ue_c && u_c[g] == VJX_SENTINEL) { u_c[g] = ld_poll_u64(lu.val + q); ok = false; }
+                  }
+                  if (__all_sync(0xffffffffu, ok)) break;
+                  if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+                }
+  #pragma unroll
+                for (int g = 0; g < UG; ++g)
+                  if (q0 + g * 32 + lane < ue_c) w[pos_c[g]] = __fma_rn(-l, bits_f64(u_c[g]), w[pos_c[g]]);
+              }
             }
             __syncwarp();
             if (lane == 0) {
@@ -2103,7 +2150,7 @@ static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr,
   k_lu_load<<<h->lu_grid_load, 256, 0, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
   h->launches += 1;
   for (int g = 0; g < h->lu_nseg; ++g) {
-    auto kfn = k_lu_rows<VJX_UG>;
+    auto kfn = h->lu_seg_rowbuf[g] > 1024 ? k_lu_rows<VJX_UG, true> : k_lu_rows<VJX_UG, false>;
     kfn<<<h->lu_seg_grid[g], 32 * VJX_FACTOR_WARPS, h->lu_seg_rowbuf[g] * VJX_FACTOR_WARPS * sizeof(double), s>>>(
         lud, csr, b, scale, zero_mask, h->st.p, g == 0 ? &h->st.p->ticket_f : &h->st.p->ticket_l, h->lu_seg_t0[g],
         h->lu_seg_t1[g], h->lu_seg_rowbuf[g]);
@@ -2279,7 +2326,7 @@ static int upload_symbolic(vjx_handle* h) {
       int occ = 1;
       // (requesting 8 chunks of U at a time for the long rows costs registers and was slower: mul64
       // 2.11 vs 1.76 ms, gpurun s6v)
-      auto kfn = k_lu_rows<VJX_UG>;
+      auto kfn = rowbuf > 1024 ? k_lu_rows<VJX_UG, true> : k_lu_rows<VJX_UG, false>;
       CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kRowbufCap * VJX_FACTOR_WARPS * (int)sizeof(double)));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 32 * VJX_FACTOR_WARPS, smem));
