@@ -2324,8 +2324,7 @@ static int upload_symbolic(vjx_handle* h) {
       const int rowbuf = std::max(64, std::min(kRowbufCap, (want + 31) / 32 * 32));
       const int smem = rowbuf * VJX_FACTOR_WARPS * (int)sizeof(double);
       int occ = 1;
-      // (requesting 8 chunks of U at a time for the long rows costs registers and was slower: mul64
-      // 2.11 vs 1.76 ms, gpurun s6v)
+      // (request size for the long rows, pipelined: 2 / 4 / 8 chunks -> mul64 1.78 / 1.54 / 1.98 ms)
       auto kfn = rowbuf > 1024 ? k_lu_rows<VJX_UG, true> : k_lu_rows<VJX_UG, false>;
       CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kRowbufCap * VJX_FACTOR_WARPS * (int)sizeof(double)));
