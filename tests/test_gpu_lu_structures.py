@@ -1,0 +1,131 @@
+"""Sparse LU (seam S1) on matrix structures chosen to hit every path of the numeric kernels: rows without an
+L part only, chains, arrow / bordered matrices, dense trailing blocks just below / at / above the sizes the
+dense kernel takes (16 and 159 rows), long rows (> 1024 entries: block-per-row back solve, > 640: large
+working vectors), random patterns.  Oracle: SciPy SuperLU on the same matrix; properties: scaled residual,
+run-to-run bit identity, refactorisation with new values on the pattern analysed first."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve_and_check(A, rng, reps=2, tol=1e-9):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from vajax_b200.analysis.matrix_sequence import SparseLUSolver
+
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    n = A.shape[0]
+    s = SparseLUSolver(A.indptr, A.indices)
+    try:
+        data = A.data.copy()
+        for rep in range(reps):
+            if rep:   # same pattern, new values (what every NR iteration does)
+                data = A.data * rng.uniform(0.7, 1.3, size=A.nnz)
+            M = sp.csr_matrix((data, A.indices, A.indptr), shape=(n, n))
+            b = rng.normal(size=n)
+            x = s.solve(data, b)
+            r = M @ x - b
+            scale = max(1.0, float(np.max(abs(M) @ np.abs(x) + np.abs(b))))
+            assert np.max(np.abs(r)) <= tol * scale, (n, rep, np.max(np.abs(r)), scale)
+            ref = spl.splu(sp.csc_matrix(M)).solve(b)
+            assert np.max(np.abs(x - ref)) <= 1e-7 * max(1.0, np.max(np.abs(ref)))
+            assert np.array_equal(x, s.solve(data, b))   # deterministic
+        return s.stats()
+    finally:
+        s.close()
+
+
+def _dominant(P, rng):
+    """Random values on pattern P with a dominant diagonal (the solver keeps the diagonal pivot)."""
+    import scipy.sparse as sp
+
+    P = sp.csr_matrix(P)
+    P.data = rng.uniform(-1.0, 1.0, size=P.nnz)
+    P = P + sp.diags(np.asarray(abs(P).sum(axis=1)).ravel() + 1.0)
+    return sp.csr_matrix(P)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 300])
+def test_diagonal_and_triangular(n):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(n)
+    _solve_and_check(sp.diags(rng.uniform(1, 2, n)), rng)                       # no L part anywhere
+    if n > 1:
+        U = sp.triu(sp.random(n, n, density=min(1.0, 6.0 / n), random_state=n)) + sp.eye(n) * 3
+        _solve_and_check(U, rng)                                                # back solve only
+        _solve_and_check(sp.csr_matrix(U.T), rng)                               # forward solve only
+
+
+@pytest.mark.parametrize("n", [5, 40, 200, 2000])
+def test_tridiagonal_chain(n):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(n + 1)
+    T = sp.diags([rng.uniform(-1, 1, n - 1), rng.uniform(3, 4, n), rng.uniform(-1, 1, n - 1)], [-1, 0, 1])
+    _solve_and_check(T, rng)
+
+
+@pytest.mark.parametrize("border", [1, 8, 15, 16, 17, 40, 158, 159, 160, 161, 220])
+def test_bordered_matrix_dense_trailing_block(border):
+    """A sparse leading part bordered by `border` dense rows and columns: after elimination the trailing
+    block is dense, of exactly the size that decides whether / how the dense kernel takes it."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(border)
+    n0 = 400
+    lead = sp.random(n0, n0, density=0.01, random_state=border)
+    B = sp.random(n0, border, density=0.3, random_state=border + 1)
+    C = sp.random(border, n0, density=0.3, random_state=border + 2)
+    D = sp.csr_matrix(np.ones((border, border)))
+    P = sp.bmat([[lead, B], [C, D]], format="csr")
+    st = _solve_and_check(_dominant(P, rng), rng)
+    assert st["n"] == n0 + border
+
+
+@pytest.mark.parametrize("n,dens", [(50, 0.2), (300, 0.02), (1500, 0.004), (6000, 0.0008)])
+def test_random_patterns(n, dens):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(n)
+    P = sp.random(n, n, density=dens, random_state=n) + sp.eye(n)
+    _solve_and_check(_dominant(P, rng), rng)
+
+
+def test_arrow_matrix_with_long_rows():
+    """One row and one column of 3,000 entries (a supply rail): the long-row paths of the load pass and of the
+    back solve, and a pivot the singleton peeling cannot take."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(7)
+    n = 3000
+    P = sp.lil_matrix((n, n))
+    P.setdiag(1.0)
+    P[0, :] = 1.0
+    P[:, 0] = 1.0
+    for i in range(1, n - 1):
+        P[i, i + 1] = 1.0
+    _solve_and_check(_dominant(P.tocsr(), rng), rng)
+
+
+def test_dense_matrix_of_moderate_size():
+    rng = np.random.default_rng(11)
+    n = 260   # rows longer than the dense block can take: the regular rows feed a 159-row dense tail
+    A = rng.uniform(-1, 1, (n, n)) + np.eye(n) * n
+    _solve_and_check(A, rng)
+
+
+def test_unsymmetric_values_need_off_diagonal_pivots():
+    """Threshold pivoting away from the diagonal (pivot_tol 1e-3): a zero diagonal entry in the pattern."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(13)
+    n = 120
+    P = sp.random(n, n, density=0.05, random_state=5) + sp.eye(n)
+    A = _dominant(P, rng).tolil()
+    for i in range(0, n - 1, 7):   # swap the roles of rows i, i+1: tiny diagonals, large off-diagonals
+        A[i, i], A[i, i + 1], A[i + 1, i], A[i + 1, i + 1] = 1e-9, 5.0, 4.0, 1e-9
+    _solve_and_check(A.tocsr(), rng, reps=1, tol=1e-8)
