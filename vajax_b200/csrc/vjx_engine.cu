@@ -637,36 +637,15 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
             const int ub_c = __shfl_sync(0xffffffffu, ub, bb), ue_c = __shfl_sync(0xffffffffu, ue, bb);
             const long long mb_c = __shfl_sync(0xffffffffu, mb, bb);
             ull inv_s = __shfl_sync(0xffffffffu, inv_l, bb), yk_s = __shfl_sync(0xffffffffu, yk_l, bb);
-            // first request of the rest of U(k,:) (PIPE only); the polling loop below keeps it fresh
-            ull u_a[PIPE ? UG : 1];
-            int pos_a[PIPE ? UG : 1];
-            bool a_loaded = false;
             if (inv_s == VJX_SENTINEL || yk_s == VJX_SENTINEL) {
               // row k is not finished yet: poll its pivot / y and, in the same round trip, its first 32 U
-              // values (long-row launch: the next UG chunks as well), so that the step can start as soon
-              // as the row appears
+              // values, so that the step can start as soon as the row appears
               const int k_s = __shfl_sync(0xffffffffu, k, bb);
               const bool has0 = ub_c + lane < ue_c;
-              if constexpr (PIPE) {
-#pragma unroll
-                for (int g = 0; g < UG; ++g) {
-                  u_a[g] = 0ULL; pos_a[g] = 0;
-                  const int q = ub_c + 32 + g * 32 + lane;
-                  if (q < ue_c) pos_a[g] = lu.upd_pos[mb_c + (q - ub_c)];
-                }
-                a_loaded = true;
-              }
               unsigned spins = 0;
               while (true) {
                 if (lane == 0) { inv_s = ld_poll_u64(lu.inv_diag + k_s); yk_s = ld_poll_u64(lu.y + k_s); }
                 if (has0) u_r[j] = ld_poll_u64(lu.val + ub_c + lane);
-                if constexpr (PIPE) {
-#pragma unroll
-                  for (int g = 0; g < UG; ++g) {
-                    const int q = ub_c + 32 + g * 32 + lane;
-                    if (q < ue_c) u_a[g] = ld_poll_u64(lu.val + q);
-                  }
-                }
                 inv_s = __shfl_sync(0xffffffffu, inv_s, 0);
                 yk_s = __shfl_sync(0xffffffffu, yk_s, 0);
                 if (inv_s != VJX_SENTINEL && yk_s != VJX_SENTINEL) break;
@@ -700,16 +679,14 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
               // UG chunks is in flight while the current one is validated and applied, so a 300-entry U row
               // costs about one L2 round trip instead of three
               if (ub_c + 32 < ue_c) {
-                ull u_b[UG];
-                int pos_b[UG];
+                ull u_a[UG], u_b[UG];
+                int pos_a[UG], pos_b[UG];
                 int q0 = ub_c + 32;
-                if (!a_loaded) {
 #pragma unroll
-                  for (int g = 0; g < UG; ++g) {
-                    u_a[g] = 0ULL; pos_a[g] = 0;
-                    const int q = q0 + g * 32 + lane;
-                    if (q < ue_c) { pos_a[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_a[g] = ld_poll_u64(lu.val + q); }
-                  }
+                for (int g = 0; g < UG; ++g) {
+                  u_a[g] = 0ULL; pos_a[g] = 0;
+                  const int q = q0 + g * 32 + lane;
+                  if (q < ue_c) { pos_a[g] = lu.upd_pos[mb_c + (q - ub_c)]; u_a[g] = ld_poll_u64(lu.val + q); }
                 }
                 while (true) {
                   const int q1 = q0 + 32 * UG;
