@@ -1,7 +1,6 @@
 """Matrix-sequence wire format (reference scripts/capture_benchmark_matrices.py:36-99,225-308,
 scripts/extract_c6288_jacobian.py:170-190): exact 17-digit round trip on the CPU, replay through seam S1
 of the library on the GPU."""
-import os
 
 import numpy as np
 import pytest

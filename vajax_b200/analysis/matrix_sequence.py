@@ -18,7 +18,7 @@ import glob
 import os
 import re
 import time
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 

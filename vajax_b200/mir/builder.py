@@ -18,7 +18,6 @@ This is setup-time tooling; nothing here runs inside the transient loop.
 
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 U32_MAX = 4294967295
