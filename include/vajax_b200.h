@@ -169,15 +169,26 @@ int vjx_tran_records(vjx_handle* h, int first, int count, double* out, vjx_strea
 /* Current solution / charge state (device -> host): X[n_total+n_vs], Q_prev[n_unknowns]. */
 int vjx_tran_state(vjx_handle* h, double* X, double* Q_prev, double* dQdt_prev, vjx_stream stream);
 
+/* Sizes of a handle: out8 = {n_total, n_external, n_vsources, n_isources, n_unknowns, n_aug, nse,
+ * total_limit_states}.  What an FFI handler needs to validate operand shapes (the reference's handler
+ * reads them from the buffer dimensions, vajax/sparse/umfpack_ffi.cpp:196-215). */
+int vjx_sizes(vjx_handle* h, int* out8);
+/* XLA FFI attributes cannot carry pointers, so a handle travels through a jitted function as a 64-bit id
+ * (the reference needs none: its caches are process-global, umfpack_ffi.cpp:140-179).  vjx_handle_id
+ * registers the handle (idempotent), vjx_handle_from_id resolves it (NULL if unknown or destroyed). */
+long long vjx_handle_id(vjx_handle* h);
+vjx_handle* vjx_handle_from_id(long long id);
+
 /* Kernel timing probe used by bench.py: average device time (ms) of `reps` launches of one phase
- * on the handle's current state: 0=device eval, 1=jacobian stamp, 2=residual, 3=LU refactor,
- * 4=L solve, 5=U solve, 6=NR update. Also returns the number of kernels launched per phase. */
+ * on the handle's current state: 0=device eval, 1=jacobian stamp, 2=residual, 3=LU refactorisation
+ * with the forward solve folded in, 4=(nothing: reports 0), 5=back solve, 6=NR update. Also returns
+ * the number of kernels launched per phase. */
 int vjx_time_phase(vjx_handle* h, int phase, int reps, double* ms_avg, int* launches, vjx_stream stream);
 /* Device time in ms (CUDA events recorded on `stream` tightly around the loop launch) of the last
  * vjx_tran_run and the total since vjx_tran_begin. */
 int vjx_tran_run_ms(vjx_handle* h, double* last_ms, double* total_ms);
 /* Debug probe (not on the product path): per permuted row, completion time in ns since kernel start
- * and dependency level of one LU phase (3 = refactorisation, 4 = forward solve, 5 = back solve). */
+ * and dependency level of one LU phase (3 = refactorisation + forward solve, 5 = back solve). */
 int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* level_out, vjx_stream stream);
 /* Number of kernels launched by this handle since creation (for bench.py's gpu_launches). */
 long long vjx_launch_count(vjx_handle* h);

@@ -155,3 +155,28 @@ def test_transient_parity(name, graph, bundles):
     assert rms < 1e-6, rms
     assert relerr(Vg[:n], Vo[:n], 1e-6) < 1e-7
     g.close()
+
+
+def test_handle_ids_and_sizes(bundles):
+    """What the FFI handlers rely on: a handle resolves from its id until it is destroyed, ids are stable
+    and distinct, vjx_sizes reports the shapes the handlers validate operands against."""
+    import ctypes as C
+
+    from vajax_b200 import ffi
+    from vajax_b200 import lib as vlib
+    from vajax_b200.analysis.engine import B200Engine
+
+    lib = vlib.load()
+    lib.vjx_handle_from_id.restype = C.c_void_p
+    lib.vjx_handle_from_id.argtypes = [C.c_longlong]
+    a = B200Engine(CIRCUITS["ring"](), bundles).prepare()
+    b = B200Engine(CIRCUITS["rc"](), bundles).prepare()
+    ia, ib = ffi.handle_id(a.handle), ffi.handle_id(b.handle)
+    assert ia > 0 and ib > 0 and ia != ib and ffi.handle_id(a.handle) == ia
+    assert lib.vjx_handle_from_id(ia) == a.handle.value and lib.vjx_handle_from_id(ib) == b.handle.value
+    sz = ffi.sizes(a.handle)
+    assert sz["n_aug"] == a.n_aug and sz["nse"] == a.nse and sz["n_total"] == a.n_total
+    assert sz["n_unknowns"] == a.n_unknowns and sz["n_vsources"] == a.n_vs
+    b.close()
+    assert lib.vjx_handle_from_id(ib) is None and lib.vjx_handle_from_id(ia) == a.handle.value
+    a.close()

@@ -22,6 +22,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <set>
@@ -1630,6 +1631,7 @@ struct vjx_handle {
   bool lu_ready = false;
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_init, lu_kub, lu_order_u, lu_perm_r, lu_perm_c;
+  long long ffi_id = 0;           // id handed out by vjx_handle_id (0 = none)
   cudaStream_t last_stream = 0;   // most recent stream an entry point was called with (vjx_destroy waits for it)
   DevBuf<double> lu_scratch, lu_dense;
   DevBuf<int> lu_dense_lstop;
@@ -1763,8 +1765,40 @@ extern "C" int vjx_device_count(void) {
 }
 extern "C" void vjx_clear_cache(void) {}
 
+// ---- handle ids for FFI attributes (include/vajax_b200.h) ------------------------------------------
+static std::mutex g_id_mu;
+static std::map<long long, vjx_handle*> g_id_to_handle;
+static long long g_next_id = 1;
+
+extern "C" long long vjx_handle_id(vjx_handle* h) {
+  if (!h) return 0;
+  std::lock_guard<std::mutex> lk(g_id_mu);
+  if (h->ffi_id == 0) {
+    h->ffi_id = g_next_id++;
+    g_id_to_handle[h->ffi_id] = h;
+  }
+  return h->ffi_id;
+}
+
+extern "C" vjx_handle* vjx_handle_from_id(long long id) {
+  std::lock_guard<std::mutex> lk(g_id_mu);
+  auto it = g_id_to_handle.find(id);
+  return it == g_id_to_handle.end() ? nullptr : it->second;
+}
+
+extern "C" int vjx_sizes(vjx_handle* h, int* out8) {
+  if (!h || !out8) return fail(VJX_ERR_INVALID, "null argument");
+  out8[0] = h->n_total; out8[1] = h->n_ext; out8[2] = h->n_vs; out8[3] = h->n_is;
+  out8[4] = h->n_unknowns; out8[5] = h->n_aug; out8[6] = h->nse; out8[7] = h->total_lim;
+  return VJX_OK;
+}
+
 extern "C" void vjx_destroy(vjx_handle* h) {
   if (!h) return;
+  if (h->ffi_id) {
+    std::lock_guard<std::mutex> lk(g_id_mu);
+    g_id_to_handle.erase(h->ffi_id);
+  }
   cudaSetDevice(h->device);
   // not cudaDeviceSynchronize: another host thread may be capturing a graph for its own handle
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);

@@ -100,6 +100,7 @@ EXPORTS = [
     "vjx_update_model_data", "vjx_update_sources", "vjx_build_system", "vjx_lu_solve", "vjx_lu_analyze",
     "vjx_lu_stats", "vjx_nr_solve", "vjx_tran_begin", "vjx_tran_run", "vjx_tran_scalars", "vjx_tran_read",
     "vjx_tran_set_step_limit", "vjx_tran_run_ms", "vjx_tran_records", "vjx_tran_state", "vjx_time_phase", "vjx_lu_timeline", "vjx_launch_count",
+    "vjx_sizes", "vjx_handle_id", "vjx_handle_from_id",
 ]
 
 _lib: Optional[C.CDLL] = None
