@@ -211,8 +211,11 @@ __global__ void k_isrc(int n2, const int* __restrict__ dest, const double* __res
 enum { SLOT_DIAG = 1, SLOT_NOI_ZERO = 2, SLOT_NOI_ONE = 4 };
 
 // Segments longer than this are reduced by a whole CTA (supply-rail diagonals collect one
-// contribution per attached transistor: 10^4 at c6288 size, 10^5 at mul64 size).
-#define VJX_LONG_SEG 96
+// contribution per attached transistor: 10^4 at c6288 size, 10^5 at mul64 size).  Shorter ones are summed
+// by one thread, which sets the kernel's duration: at c6288 size 99 % of the node rows hold <= 18
+// contributions, 34 input nets hold 64-96.  Measured (residual / stamp, us): 96 -> 22 / 12.4, 32 -> 14 / 11.6,
+// 16 -> 16 / 18.5.
+#define VJX_LONG_SEG 32
 
 // Deterministic CTA sum: fixed strided partials, fixed shuffle butterfly, fixed warp order.
 __device__ __forceinline__ double block_sum_256(double v, double* sh) {
