@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Golden vector at BASELINE.json's largest size: the first accepted steps of the mul64 transient computed by
+the CPU oracle (about 30 s per NR iteration, so this runs once, here, not in the test suite).
+
+    python tests/golden/make_mul64_steps.py      ->  tests/golden/mul64_first_steps.npz
+
+Stored: the accepted-step records (step, t_next, dt, nr_iters, accept), the output times, the waveform rows at
+every 64th external node, and the max-norm / sum of every full row (a checksum of the columns not stored).
+tests/test_gpu_fullsize.py::test_mul64_first_steps_match_the_oracle_golden compares the CUDA path with it."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.engine import OracleEngine  # noqa: E402
+from vajax_b200.benchmarks.circuits import mul64_circuit  # noqa: E402
+from vajax_b200.models.fixtures import get_bundle  # noqa: E402
+
+ROWS = 3   # row 0 = initial condition, then two accepted steps
+bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
+o = OracleEngine(mul64_circuit(64), bundles)
+rec = []
+t, V, st = o.run_transient(max_steps=ROWS, record=rec)
+n = st["n_steps"]
+cols = np.arange(0, V.shape[1], 64)
+np.savez_compressed(
+    os.path.join(ROOT, "tests", "golden", "mul64_first_steps.npz"),
+    times=np.asarray(t[:n]), cols=cols, V_cols=np.asarray(V[:n][:, cols]),
+    row_absmax=np.max(np.abs(V[:n]), axis=1), row_sum=np.sum(V[:n], axis=1),
+    records=np.array([[r["step"], r["t_next"], r["dt"], r["nr_iters"], float(r["accept"])] for r in rec]),
+    n_steps=n, total_nr=st["total_nr_iterations"], rejected=st["rejected_steps"], n_external=V.shape[1])
+print("rows", n, "nr", st["total_nr_iterations"], "records", len(rec))

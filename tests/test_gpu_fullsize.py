@@ -200,3 +200,35 @@ def test_mul64_scale_properties(bundles):
     assert np.max(np.abs(r)) <= 1e-9 * max(1.0, np.max(np.abs(A @ np.abs(x))))
     assert np.array_equal(x, e.lu_solve(csr, rhs))
     e.close()
+
+
+@pytest.mark.timeout(600)
+def test_mul64_first_steps_match_the_oracle_golden(bundles):
+    """BASELINE.json's largest configuration against the CPU oracle: the oracle needs ~30 s per NR iteration
+    at this size, so its first two accepted steps are a committed golden vector
+    (tests/golden/mul64_first_steps.npz, generated by tests/golden/make_mul64_steps.py).  Same accepted-step
+    sequence, t / dt to the accuracy of the solves, waveforms within 1e-6 RMS relative on the stored columns,
+    and the row checksums over ALL 133,463 external nodes."""
+    import os
+
+    from vajax_b200.analysis.engine import B200Engine
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mul64_first_steps.npz"))
+    n = int(g["n_steps"])
+    e = B200Engine(circuits.mul64_circuit(64), bundles, use_device_graph=True).prepare()
+    t, V, st = e.run_transient(max_steps=n)
+    assert st["error_flags"] == 0 and st["n_steps"] == n and V.shape[1] == int(g["n_external"])
+    assert st["total_nr_iterations"] == int(g["total_nr"]) and st["rejected_steps"] == int(g["rejected"])
+    rec = e.step_records()
+    assert len(rec) == len(g["records"])
+    for a, b in zip(rec, g["records"]):
+        assert int(a[0]) == int(b[0]) and int(a[3]) == int(b[3]) and bool(a[4]) == bool(b[4])
+        assert abs(a[1] - b[1]) <= 1e-9 * abs(b[1]) and abs(a[2] - b[2]) <= 1e-9 * b[2]
+    assert np.max(np.abs(t[:n] - g["times"])) <= 1e-9 * g["times"][-1]
+    Vc = V[:n][:, g["cols"]]
+    span = max(np.max(g["V_cols"]) - np.min(g["V_cols"]), 1e-12)
+    assert np.sqrt(np.mean((Vc - g["V_cols"]) ** 2)) / span < 1e-6
+    assert np.max(np.abs(Vc - g["V_cols"])) < 1e-7
+    assert np.allclose(np.max(np.abs(V[:n]), axis=1), g["row_absmax"], rtol=0, atol=1e-7)
+    assert np.allclose(np.sum(V[:n], axis=1), g["row_sum"], rtol=1e-9, atol=1e-4)
+    e.close()
