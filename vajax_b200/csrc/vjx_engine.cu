@@ -1730,11 +1730,20 @@ static void* plugin_open(const char* path, std::string& key) {
     }
     return dl;
   }
+  // private copy: $TMPDIR, /tmp, or next to the plugin itself
   const char* td = getenv("TMPDIR");
-  std::string tmpl = std::string(td && *td ? td : "/tmp") + "/vjx_plugin_XXXXXX.so";
-  std::vector<char> name(tmpl.begin(), tmpl.end());
-  name.push_back(0);
-  int fd = mkstemps(name.data(), 3);
+  std::string self(path);
+  const size_t slash = self.rfind('/');
+  const std::string dirs[3] = {td && *td ? td : "/tmp", "/tmp", slash == std::string::npos ? "." : self.substr(0, slash)};
+  std::vector<char> name;
+  int fd = -1;
+  for (const std::string& dir : dirs) {
+    const std::string tmpl = dir + "/vjx_plugin_XXXXXX.so";
+    name.assign(tmpl.begin(), tmpl.end());
+    name.push_back(0);
+    fd = mkstemps(name.data(), 3);
+    if (fd >= 0) break;
+  }
   if (fd < 0) return nullptr;
   FILE* in = fopen(path, "rb");
   bool ok = in != nullptr;
