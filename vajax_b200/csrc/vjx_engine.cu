@@ -576,11 +576,11 @@ __global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restr
 #define VJX_UG 4   // chunks of 32 U entries requested together per k-step (beyond the first)
 #endif
 #ifndef VJX_PF
-#define VJX_PF 4   // k-steps whose first chunk is in flight
+#define VJX_PF 4   // k-steps whose first chunks are in flight
 #endif
 extern __shared__ double vjx_lu_smem[];
 
-template <int UG, bool PIPE>
+template <int UG, bool PIPE, int RC>
 __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, const double* __restrict__ csr,
                                                                     const double* __restrict__ b, double scale,
                                                                     const unsigned char* __restrict__ zero_mask, NRStat* st,
@@ -622,15 +622,20 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
         yk_l = ld_poll_u64(lu.y + k);
       }
       // ring of VJX_PF steps in flight: the first 32 U values / positions of steps bb .. bb+VJX_PF-1
-      ull u_r[VJX_PF];
-      int pos_r[VJX_PF];
+      ull u_r[VJX_PF][RC];
+      int pos_r[VJX_PF][RC];
 #pragma unroll
       for (int j = 0; j < VJX_PF; ++j) {
-        u_r[j] = 0ULL; pos_r[j] = 0;
+#pragma unroll
+        for (int c = 0; c < RC; ++c) { u_r[j][c] = 0ULL; pos_r[j][c] = 0; }
         if (j < nb) {
           const int ub_j = __shfl_sync(0xffffffffu, ub, j), ue_j = __shfl_sync(0xffffffffu, ue, j);
           const long long mb_j = __shfl_sync(0xffffffffu, mb, j);
-          if (ub_j + lane < ue_j) { pos_r[j] = lu.upd_pos[mb_j + lane]; u_r[j] = ld_poll_u64(lu.val + ub_j + lane); }
+#pragma unroll
+          for (int c = 0; c < RC; ++c) {
+            const int q = ub_j + 32 * c + lane;
+            if (q < ue_j) { pos_r[j][c] = lu.upd_pos[mb_j + 32 * c + lane]; u_r[j][c] = ld_poll_u64(lu.val + q); }
+          }
         }
       }
       for (int bb0 = 0; bb0 < nb; bb0 += VJX_PF) {
@@ -649,7 +654,7 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
               unsigned spins = 0;
               while (true) {
                 if (lane == 0) { inv_s = ld_poll_u64(lu.inv_diag + k_s); yk_s = ld_poll_u64(lu.y + k_s); }
-                if (has0) u_r[j] = ld_poll_u64(lu.val + ub_c + lane);
+                if (has0) u_r[j][0] = ld_poll_u64(lu.val + ub_c + lane);
                 inv_s = __shfl_sync(0xffffffffu, inv_s, 0);
                 yk_s = __shfl_sync(0xffffffffu, yk_s, 0);
                 if (inv_s != VJX_SENTINEL && yk_s != VJX_SENTINEL) break;
@@ -658,34 +663,43 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
             }
             const int kpos = pb + bb - rb;
             const double l = w[kpos] * bits_f64(inv_s);
-            // first chunk: from the ring (re-polled only while it still holds the sentinel)
+            // first RC chunks: from the ring (re-polled only while they still hold the sentinel)
             {
-              const bool has = ub_c + lane < ue_c;
-              ull u0 = u_r[j];
               unsigned spins = 0;
               while (true) {
-                const bool ok = !has || u0 != VJX_SENTINEL;
+                bool ok = true;
+#pragma unroll
+                for (int c = 0; c < RC; ++c) {
+                  const int q = ub_c + 32 * c + lane;
+                  if (q < ue_c && u_r[j][c] == VJX_SENTINEL) { u_r[j][c] = ld_poll_u64(lu.val + q); ok = false; }
+                }
                 if (__all_sync(0xffffffffu, ok)) break;
-                if (!ok) u0 = ld_poll_u64(lu.val + ub_c + lane);
                 if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
               }
-              if (has) w[pos_r[j]] = __fma_rn(-l, bits_f64(u0), w[pos_r[j]]);
+#pragma unroll
+              for (int c = 0; c < RC; ++c)
+                if (ub_c + 32 * c + lane < ue_c) w[pos_r[j][c]] = __fma_rn(-l, bits_f64(u_r[j][c]), w[pos_r[j][c]]);
             }
             // refill this ring slot with step bb + VJX_PF before the long tail of this step
-            u_r[j] = 0ULL;
+#pragma unroll
+            for (int c = 0; c < RC; ++c) u_r[j][c] = 0ULL;
             if (bb + VJX_PF < nb) {
               const int ub_n = __shfl_sync(0xffffffffu, ub, bb + VJX_PF), ue_n = __shfl_sync(0xffffffffu, ue, bb + VJX_PF);
               const long long mb_n = __shfl_sync(0xffffffffu, mb, bb + VJX_PF);
-              if (ub_n + lane < ue_n) { pos_r[j] = lu.upd_pos[mb_n + lane]; u_r[j] = ld_poll_u64(lu.val + ub_n + lane); }
+#pragma unroll
+              for (int c = 0; c < RC; ++c) {
+                const int q = ub_n + 32 * c + lane;
+                if (q < ue_n) { pos_r[j][c] = lu.upd_pos[mb_n + 32 * c + lane]; u_r[j][c] = ld_poll_u64(lu.val + q); }
+              }
             }
             if constexpr (PIPE) {
               // long rows (their launch is limited by shared memory, registers are free): the next request of
               // UG chunks is in flight while the current one is validated and applied, so a 300-entry U row
               // costs about one L2 round trip instead of three
-              if (ub_c + 32 < ue_c) {
+              if (ub_c + 32 * RC < ue_c) {
                 ull u_a[UG], u_b[UG];
                 int pos_a[UG], pos_b[UG];
-                int q0 = ub_c + 32;
+                int q0 = ub_c + 32 * RC;
 #pragma unroll
                 for (int g = 0; g < UG; ++g) {
                   u_a[g] = 0ULL; pos_a[g] = 0;
@@ -726,7 +740,7 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
             } else {
               // rest of U(k,:), UG chunks of 32 requested together (keeping the next request in flight
               // costs 6 registers: one block per SM less in the wide launch, which is bound by occupancy)
-              for (int q0 = ub_c + 32; q0 < ue_c; q0 += 32 * UG) {
+              for (int q0 = ub_c + 32 * RC; q0 < ue_c; q0 += 32 * UG) {
                 ull u_c[UG];
                 int pos_c[UG];
   #pragma unroll
@@ -2191,12 +2205,18 @@ static void launch_residual(vjx_handle* h, const BuildPtrs& b, int check, cudaSt
 
 static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s);
 
+typedef void (*lu_rows_fn)(LUDev, const double*, const double*, double, const unsigned char*, NRStat*, unsigned*, int, int, int);
+static lu_rows_fn lu_rows_kernel(int rowbuf, bool two_launches) {
+  if (rowbuf > 1024) return k_lu_rows<VJX_UG, true, 1>;
+  return two_launches ? k_lu_rows<VJX_UG, false, 1> : k_lu_rows<VJX_UG, false, 2>;
+}
+
 static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr, const double* b, double scale,
                              const unsigned char* zero_mask, double* x, cudaStream_t s) {
   k_lu_load<<<h->lu_grid_load, 256, 0, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
   h->launches += 1;
   for (int g = 0; g < h->lu_nseg; ++g) {
-    auto kfn = h->lu_seg_rowbuf[g] > 1024 ? k_lu_rows<VJX_UG, true> : k_lu_rows<VJX_UG, false>;
+    auto kfn = lu_rows_kernel(h->lu_seg_rowbuf[g], h->lu_nseg > 1 || h->lu_seg_rowbuf[g] > 1024);
     kfn<<<h->lu_seg_grid[g], 32 * VJX_FACTOR_WARPS, h->lu_seg_rowbuf[g] * VJX_FACTOR_WARPS * sizeof(double), s>>>(
         lud, csr, b, scale, zero_mask, h->st.p, g == 0 ? &h->st.p->ticket_f : &h->st.p->ticket_l, h->lu_seg_t0[g],
         h->lu_seg_t1[g], h->lu_seg_rowbuf[g]);
@@ -2371,7 +2391,10 @@ static int upload_symbolic(vjx_handle* h) {
       const int smem = rowbuf * VJX_FACTOR_WARPS * (int)sizeof(double);
       int occ = 1;
       // (request size for the long rows, pipelined: 2 / 4 / 8 chunks -> mul64 1.78 / 1.54 / 1.98 ms)
-      auto kfn = rowbuf > 1024 ? k_lu_rows<VJX_UG, true> : k_lu_rows<VJX_UG, false>;
+      // ring slots of 2 chunks (64 U entries per prefetched step) cost 24 registers: worth it when one launch
+      // holds everything and the heaviest rows set its duration (c6288: rows phase 113 -> 108 us), not when the
+      // wide launch lives on occupancy (mul64: 1.54 -> 1.62 ms)
+      auto kfn = lu_rows_kernel(rowbuf, n_cut < n);
       CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kRowbufCap * VJX_FACTOR_WARPS * (int)sizeof(double)));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 32 * VJX_FACTOR_WARPS, smem));
