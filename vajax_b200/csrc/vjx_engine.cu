@@ -107,6 +107,7 @@ struct LUDev {
   int n_long_u, n_bulk_u;      // order_u holds n_bulk_u rows
   const long long* upd_ptr;    // [nnz+1] start of each L entry's scatter list
   const int* upd_pos;          // position inside row i of each column of U(k,:)
+  long long n_upd_prefetch;    // entries of upd_pos k_lu_load prefetches into L2 (0: the description is larger than L2)
   unsigned long long* ts;      // optional per-row completion timestamps (globaltimer, debug probe)
   double* val;
   double* inv_diag;
@@ -518,6 +519,7 @@ __device__ __forceinline__ void st_pub_f64(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ double bits_f64(ull b) { return __longlong_as_double((long long)b); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Flat pass, full grid: rows without an L part (peeled singletons, leaves of the elimination forest -
 // 80 % of all rows) are plain copies of A's values and are finished here, pivot reciprocal and y
@@ -528,6 +530,18 @@ __global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restr
   const long long nt = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const double sent = bits_f64(VJX_SENTINEL);
+  // When the static description of the factorisation fits in L2, pull it there now, with full-grid coalesced
+  // prefetches: the row kernels read it inside dependency chains, where a miss to HBM costs a k-step its
+  // whole latency budget (first NR iteration after anything evicted it; free when it is resident already).
+  if (lu.n_upd_prefetch > 0) {
+    for (long long q = t0 * 32; q < lu.n_upd_prefetch; q += nt * 32) prefetch_l2(lu.upd_pos + q);   // 128 B lines
+    for (long long q = t0 * 32; q < lu.nnz; q += nt * 32) {
+      prefetch_l2(lu.col + q);
+      prefetch_l2(lu.kub + q);
+      prefetch_l2(lu.src + q);
+    }
+    for (long long q = t0 * 16; q < lu.nnz + 1; q += nt * 16) prefetch_l2(lu.upd_ptr + q);
+  }
   for (long long p = t0; p < lu.nnz; p += nt) {
     const int c = lu.init[p];
     if (c >= 0) lu.val[p] = csr[c];
@@ -2314,6 +2328,11 @@ static int upload_symbolic(vjx_handle* h) {
   L.perm_r = h->lu_perm_r.p; L.perm_c = h->lu_perm_c.p;
   L.ts = nullptr;
   L.upd_ptr = h->lu_upd_ptr.p; L.upd_pos = h->lu_upd_pos.p;
+  {
+    // static bytes the row kernels walk: scatter program + per-entry tables; prefetch when well inside L2
+    const double static_bytes = 4.0 * (double)S.upd_pos.size() + (4.0 * 3 + 8.0) * (double)S.nnz_lu;
+    L.n_upd_prefetch = static_bytes < 48e6 ? (long long)S.upd_pos.size() : 0;
+  }
   CK(h->lu_order_f.upload(S.order_f));
   L.order_f = h->lu_order_f.p;
   L.n_nol = n_nol;
