@@ -224,6 +224,14 @@ def run_b200(args, rank, world, local_rank):
     for e in engines:
         e.tran_begin(max_steps=1 + W)
         e.tran_run()
+    if world > 1:
+        import torch.distributed as dist
+
+        # ... and of the gather path: NCCL sets up its point-to-point channels on the first gather (about a
+        # second, once per process group), which is start-up cost like the graph build, not part of a sweep
+        probe = torch.zeros(1024, dtype=torch.float64, device=dev)
+        dist.gather(probe, [torch.empty_like(probe) for _ in range(world)] if rank == 0 else None, dst=0)
+        torch.cuda.synchronize()
     # ---- value: per-step graph launches with an L2 flush in between (events inside vjx_tran_run)
     sampler = ClockSampler(local_rank)
     sampler.start()
