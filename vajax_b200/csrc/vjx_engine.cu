@@ -638,6 +638,11 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
       // ring of VJX_PF steps in flight: the first 32 U values / positions of steps bb .. bb+VJX_PF-1
       ull u_r[VJX_PF][RC];
       int pos_r[VJX_PF][RC];
+      // (single-launch variant, registers to spare: the bounds of the prefetched steps stay in registers too,
+      // which saves the step its own three shuffles)
+      constexpr bool KEEP = RC > 1;
+      int ub_k[KEEP ? VJX_PF : 1], ue_k[KEEP ? VJX_PF : 1];
+      long long mb_k[KEEP ? VJX_PF : 1];
 #pragma unroll
       for (int j = 0; j < VJX_PF; ++j) {
 #pragma unroll
@@ -645,6 +650,7 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
         if (j < nb) {
           const int ub_j = __shfl_sync(0xffffffffu, ub, j), ue_j = __shfl_sync(0xffffffffu, ue, j);
           const long long mb_j = __shfl_sync(0xffffffffu, mb, j);
+          if constexpr (KEEP) { ub_k[j] = ub_j; ue_k[j] = ue_j; mb_k[j] = mb_j; }
 #pragma unroll
           for (int c = 0; c < RC; ++c) {
             const int q = ub_j + 32 * c + lane;
@@ -657,8 +663,14 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
         for (int j = 0; j < VJX_PF; ++j) {
           const int bb = bb0 + j;
           if (bb < nb) {   // warp-uniform
-            const int ub_c = __shfl_sync(0xffffffffu, ub, bb), ue_c = __shfl_sync(0xffffffffu, ue, bb);
-            const long long mb_c = __shfl_sync(0xffffffffu, mb, bb);
+            int ub_c, ue_c;
+            long long mb_c;
+            if constexpr (KEEP) {
+              ub_c = ub_k[j]; ue_c = ue_k[j]; mb_c = mb_k[j];
+            } else {
+              ub_c = __shfl_sync(0xffffffffu, ub, bb); ue_c = __shfl_sync(0xffffffffu, ue, bb);
+              mb_c = __shfl_sync(0xffffffffu, mb, bb);
+            }
             ull inv_s = __shfl_sync(0xffffffffu, inv_l, bb), yk_s = __shfl_sync(0xffffffffu, yk_l, bb);
             if (inv_s == VJX_SENTINEL || yk_s == VJX_SENTINEL) {
               // row k is not finished yet: poll its pivot / y and, in the same round trip, its first 32 U
@@ -700,6 +712,7 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
             if (bb + VJX_PF < nb) {
               const int ub_n = __shfl_sync(0xffffffffu, ub, bb + VJX_PF), ue_n = __shfl_sync(0xffffffffu, ue, bb + VJX_PF);
               const long long mb_n = __shfl_sync(0xffffffffu, mb, bb + VJX_PF);
+              if constexpr (KEEP) { ub_k[j] = ub_n; ue_k[j] = ue_n; mb_k[j] = mb_n; }
 #pragma unroll
               for (int c = 0; c < RC; ++c) {
                 const int q = ub_n + 32 * c + lane;
