@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
       constexpr bool KEEP = RC > 1;
       int ub_k[KEEP ? VJX_PF : 1], ue_k[KEEP ? VJX_PF : 1];
       long long mb_k[KEEP ? VJX_PF : 1];
+      ull inv_k[KEEP ? VJX_PF : 1], yk_k[KEEP ? VJX_PF : 1];
 #pragma unroll
       for (int j = 0; j < VJX_PF; ++j) {
 #pragma unroll
@@ -650,7 +651,11 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
         if (j < nb) {
           const int ub_j = __shfl_sync(0xffffffffu, ub, j), ue_j = __shfl_sync(0xffffffffu, ue, j);
           const long long mb_j = __shfl_sync(0xffffffffu, mb, j);
-          if constexpr (KEEP) { ub_k[j] = ub_j; ue_k[j] = ue_j; mb_k[j] = mb_j; }
+          if constexpr (KEEP) {
+            ub_k[j] = ub_j; ue_k[j] = ue_j; mb_k[j] = mb_j;
+            inv_k[j] = __shfl_sync(0xffffffffu, inv_l, j);
+            yk_k[j] = __shfl_sync(0xffffffffu, yk_l, j);
+          }
 #pragma unroll
           for (int c = 0; c < RC; ++c) {
             const int q = ub_j + 32 * c + lane;
@@ -671,7 +676,12 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
               ub_c = __shfl_sync(0xffffffffu, ub, bb); ue_c = __shfl_sync(0xffffffffu, ue, bb);
               mb_c = __shfl_sync(0xffffffffu, mb, bb);
             }
-            ull inv_s = __shfl_sync(0xffffffffu, inv_l, bb), yk_s = __shfl_sync(0xffffffffu, yk_l, bb);
+            ull inv_s, yk_s;
+            if constexpr (KEEP) {
+              inv_s = inv_k[j]; yk_s = yk_k[j];
+            } else {
+              inv_s = __shfl_sync(0xffffffffu, inv_l, bb); yk_s = __shfl_sync(0xffffffffu, yk_l, bb);
+            }
             if (inv_s == VJX_SENTINEL || yk_s == VJX_SENTINEL) {
               // row k is not finished yet: poll its pivot / y and, in the same round trip, its first 32 U
               // values, so that the step can start as soon as the row appears
@@ -712,7 +722,11 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
             if (bb + VJX_PF < nb) {
               const int ub_n = __shfl_sync(0xffffffffu, ub, bb + VJX_PF), ue_n = __shfl_sync(0xffffffffu, ue, bb + VJX_PF);
               const long long mb_n = __shfl_sync(0xffffffffu, mb, bb + VJX_PF);
-              if constexpr (KEEP) { ub_k[j] = ub_n; ue_k[j] = ue_n; mb_k[j] = mb_n; }
+              if constexpr (KEEP) {
+                ub_k[j] = ub_n; ue_k[j] = ue_n; mb_k[j] = mb_n;
+                inv_k[j] = __shfl_sync(0xffffffffu, inv_l, bb + VJX_PF);
+                yk_k[j] = __shfl_sync(0xffffffffu, yk_l, bb + VJX_PF);
+              }
 #pragma unroll
               for (int c = 0; c < RC; ++c) {
                 const int q = ub_n + 32 * c + lane;
