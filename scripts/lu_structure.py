@@ -63,3 +63,16 @@ for a in range(0, nl, step):
     print(f"{a:5d}-{b-1:5d}: rows={int(cnt[a:b].sum()):7d} sumL={int(ll[a:b].sum()):9d} sumU={int(ul[a:b].sum()):9d} maxL={int(mx[a:b].max()):5d}")
 single = np.where(cnt == 1)[0]
 print("levels with one row:", len(single), " first such:", single[:5])
+# heavy rows with the dense trailing block in place: sequential k-steps today vs dependency depths
+bulk, nd = np.zeros(n, np.int32), C.c_int(0)
+lib.vjx_symbolic_rows2.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_double, C.c_int] + [C.c_void_p] * 6 + [C.c_void_p]
+rc = lib.vjx_symbolic_rows2(n, p(ip), p(ix), p(csr), 1e-3, 159, p(lv_l), p(lv_u), p(l_len), p(u_len), p(waves), p(bulk), C.byref(nd))
+print(f"dense trailing block: {nd.value} rows")
+heavy = np.argsort(-bulk)[:12]
+print("heaviest rows: index  k-steps of k_lu_rows  distinct dependency depths among them  (dense-block row?)")
+for i in heavy:
+    print(f"   {int(i):8d} {int(bulk[i]):6d} {int(waves[i]):6d}   {'dense' if i >= n - nd.value else ''}")
+hl = bulk >= 32
+if hl.any():
+    print(f"rows with >= 32 k-steps: {int(hl.sum())}, k-steps {int(bulk[hl].sum())}, depths {int(waves[hl].sum())} "
+          f"(ratio {bulk[hl].sum() / max(waves[hl].sum(), 1):.1f}x)")

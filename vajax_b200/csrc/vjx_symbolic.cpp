@@ -482,7 +482,8 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
     const int ds = n - nd;
     // depth[k]: dependency depth of row k counting both what it waits for (L(k,j) != 0: row j finished)
     // and what must be applied before it inside any row that holds both (U(j,k) != 0)
-    std::vector<int> depth(n, 0);
+    std::vector<int>& depth = S.depth;
+    depth.assign(n, 0);
     for (int k = 0; k < n; ++k) {
       int d = depth[k];   // pushed from rows j < k with U(j,k) != 0
       for (int pp = S.lu_ptr[k]; pp < S.lu_diag[k]; ++pp) d = std::max(d, depth[S.lu_col[pp]] + 1);
@@ -628,20 +629,39 @@ extern "C" int vjx_symbolic_probe(int n, const int* indptr, const int* indices, 
   return 0;
 }
 
-// Per-row diagnostics of the analysis (CPU-only tests and offline tuning): L / U dependency level,
-// number of L and U entries and number of in-row waves, all indexed by permuted row.
-extern "C" int vjx_symbolic_rows(int n, const int* indptr, const int* indices, const double* values,
-                                 double pivot_tol, int* level_l, int* level_u, int* l_len, int* u_len, int* waves) {
+// Per-row diagnostics of the analysis (CPU-only tests and offline tuning), indexed by permuted row: L / U
+// dependency level, number of L and U entries, and for the k-steps the row kernel executes itself (the L entries
+// left of the dense trailing block of `dense_cap` rows): their number (bulk_len) and the number of distinct
+// dependency depths among them (waves) - k-steps of equal depth are independent of each other, so `waves` is the
+// length of the row's sequential chain if a depth were processed at a time (DESIGN.md 8, round-2 plan).
+extern "C" int vjx_symbolic_rows2(int n, const int* indptr, const int* indices, const double* values,
+                                  double pivot_tol, int dense_cap, int* level_l, int* level_u, int* l_len, int* u_len,
+                                  int* waves, int* bulk_len, int* n_dense_out) {
   VjxSymbolic S;
   std::string err;
-  int rc = vjx_symbolic_analyze(n, indptr, indices, values, pivot_tol, true, S, err);
+  int rc = vjx_symbolic_analyze(n, indptr, indices, values, pivot_tol, true, S, err, dense_cap);
   if (rc != 0) return rc;
+  const int ds = n - S.n_dense;
+  if (n_dense_out) *n_dense_out = S.n_dense;
   for (int i = 0; i < n; ++i) {
     if (level_l) level_l[i] = S.level_l[i];
     if (level_u) level_u[i] = S.level_u[i];
     if (l_len) l_len[i] = S.lu_diag[i] - S.lu_ptr[i];
     if (u_len) u_len[i] = S.lu_ptr[i + 1] - S.lu_diag[i] - 1;
-    if (waves) waves[i] = S.lu_diag[i] - S.lu_ptr[i];
+    int w = 0, last = -1, nb = 0;
+    for (int pp = S.lu_ptr[i]; pp < S.lu_diag[i]; ++pp) {
+      const int k = S.lu_col[pp];
+      if (i >= ds && k >= ds) continue;   // handed to the dense kernel
+      ++nb;
+      if (S.depth[k] != last) { ++w; last = S.depth[k]; }
+    }
+    if (waves) waves[i] = w;
+    if (bulk_len) bulk_len[i] = nb;
   }
   return 0;
+}
+
+extern "C" int vjx_symbolic_rows(int n, const int* indptr, const int* indices, const double* values,
+                                 double pivot_tol, int* level_l, int* level_u, int* l_len, int* u_len, int* waves) {
+  return vjx_symbolic_rows2(n, indptr, indices, values, pivot_tol, 0, level_l, level_u, l_len, u_len, waves, nullptr, nullptr);
 }

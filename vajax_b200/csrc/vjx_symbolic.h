@@ -55,6 +55,7 @@ struct VjxSymbolic {
   // rows finish early first keeps a row from idling at one late dependency with hundreds of ready
   // steps queued behind it.
   int n_dense = 0;
+  std::vector<int> depth;         // the dependency depth used for that order (see vjx_symbolic.cpp)
   int n_singletons = 0;           // pivots peeled as row / column singletons (no fill, no updates)
   int n_core = 0;                 // unknowns left for AMD + Gilbert-Peierls
   double flops = 0.0;             // 2 * sum_k nnz(L(:,k)) * nnz(U(k,:)) + nnz(L)
