@@ -7,6 +7,7 @@ max_i |a_i - b_i| / max(|b_i|, floor).
 import numpy as np
 import pytest
 
+from golden_util import assert_vector_parity
 from vajax_b200.benchmarks import circuits
 
 pytestmark = pytest.mark.gpu
@@ -54,12 +55,8 @@ def test_setup_and_build_system_parity(name, limiting, bundles):
     for (c0, c1, d1, c2, it) in [(0.0, 0.0, 0.0, 0.0, 0), (2e12, -2e12, -1.0, 0.0, 1), (1.5e9, -2e9, 0.0, 0.5e9, 3)]:
         ro = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, ls, it)
         rg = g.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, ls, it)
-        names = ["csr", "f", "Q", "Ivs", "limit", "maxres"]
-        floors = [1e-12, 1e-12, 1e-24, 1e-12, 1e-6, 1e-12]
-        for nm, a, b, fl in zip(names, rg, ro, floors):
-            scale = max(np.max(np.abs(b)) if b.size else 0.0, fl)
-            err = relerr(a, b, max(fl, 1e-13 * scale))
-            assert err < 1e-12 if nm in ("csr",) else err < 1e-10, (name, nm, err)
+        for nm, a, b in zip(["csr", "f", "Q", "Ivs", "limit", "maxres"], rg, ro):
+            assert_vector_parity(nm, a, b, (name, limiting, c0))
     g.close()
 
 

@@ -294,22 +294,43 @@ def _unary(op: str):
     def f(x: Dual) -> Dual:
         fb = x.fb
         r = fb.emit(op, [x.v])
-        if not x.d:
+        if not x.d or op in ("floor", "ceil", "clog2"):
             return Dual(fb, r)
+        one, e, xv = fb.fconst(1.0), fb.emit, x.v
         if op == "exp":
             dr = r
         elif op == "ln":
-            dr = fb.emit("fdiv", [fb.fconst(1.0), x.v])
+            dr = e("fdiv", [one, xv])
+        elif op == "log":  # log10
+            dr = e("fdiv", [fb.fconst(0.4342944819032518), xv])
         elif op == "sqrt":
-            dr = fb.emit("fdiv", [fb.fconst(0.5), r])
+            dr = e("fdiv", [fb.fconst(0.5), r])
         elif op == "tanh":
-            dr = fb.emit("fsub", [fb.fconst(1.0), fb.emit("fmul", [r, r])])
+            dr = e("fsub", [one, e("fmul", [r, r])])
+        elif op == "tan":
+            dr = e("fadd", [one, e("fmul", [r, r])])
         elif op == "sin":
-            dr = fb.emit("cos", [x.v])
+            dr = e("cos", [xv])
         elif op == "cos":
-            dr = fb.emit("fneg", [fb.emit("sin", [x.v])])
+            dr = e("fneg", [e("sin", [xv])])
+        elif op == "sinh":
+            dr = e("cosh", [xv])
+        elif op == "cosh":
+            dr = e("sinh", [xv])
         elif op == "atan":
-            dr = fb.emit("fdiv", [fb.fconst(1.0), fb.emit("fadd", [fb.fconst(1.0), fb.emit("fmul", [x.v, x.v])])])
+            dr = e("fdiv", [one, e("fadd", [one, e("fmul", [xv, xv])])])
+        elif op == "asin":
+            dr = e("fdiv", [one, e("sqrt", [e("fsub", [one, e("fmul", [xv, xv])])])])
+        elif op == "acos":
+            dr = e("fneg", [e("fdiv", [one, e("sqrt", [e("fsub", [one, e("fmul", [xv, xv])])])])])
+        elif op == "asinh":
+            dr = e("fdiv", [one, e("sqrt", [e("fadd", [e("fmul", [xv, xv]), one])])])
+        elif op == "acosh":
+            dr = e("fdiv", [one, e("sqrt", [e("fsub", [e("fmul", [xv, xv]), one])])])
+        elif op == "atanh":
+            dr = e("fdiv", [one, e("fsub", [one, e("fmul", [xv, xv])])])
+        elif op in ("abs", "fabs"):
+            dr = e("select", [e("flt", [xv, fb.fconst(0.0)], ty="b"), fb.fconst(-1.0), one])
         else:
             raise NotImplementedError(op)
         return x._chain(r, dr)
@@ -319,11 +340,73 @@ def _unary(op: str):
 
 exp = _unary("exp")
 ln = _unary("ln")
+log10 = _unary("log")
 sqrt = _unary("sqrt")
 tanh = _unary("tanh")
+tan = _unary("tan")
 sin = _unary("sin")
 cos = _unary("cos")
+sinh = _unary("sinh")
+cosh = _unary("cosh")
 atan = _unary("atan")
+asin = _unary("asin")
+acos = _unary("acos")
+asinh = _unary("asinh")
+acosh = _unary("acosh")
+atanh = _unary("atanh")
+fabs = _unary("abs")
+floor = _unary("floor")
+ceil = _unary("ceil")
+clog2 = _unary("clog2")
+
+
+def _binary(op: str):
+    def f(a, b) -> Dual:
+        if not isinstance(a, Dual):
+            a = b._lift(a)
+        b = a._lift(b)
+        fb = a.fb
+        e = fb.emit
+        r = e(op, [a.v, b.v])
+        if not a.d and not b.d:
+            return Dual(fb, r)
+        if op == "pow":
+            da = e("fmul", [b.v, e("pow", [a.v, e("fsub", [b.v, fb.fconst(1.0)])])]) if a.d else None
+            db = e("fmul", [r, e("ln", [a.v])]) if b.d else None
+        elif op == "atan2":  # atan2(y = a, x = b)
+            den = e("fadd", [e("fmul", [a.v, a.v]), e("fmul", [b.v, b.v])])
+            da = e("fdiv", [b.v, den]) if a.d else None
+            db = e("fneg", [e("fdiv", [a.v, den])]) if b.d else None
+        elif op == "hypot":
+            da = e("fdiv", [a.v, r]) if a.d else None
+            db = e("fdiv", [b.v, r]) if b.d else None
+        elif op in ("fmin", "fmax"):
+            c = e("flt" if op == "fmin" else "fgt", [a.v, b.v], ty="b")
+            zero = fb.fconst(0.0)
+            d = {}
+            for k in list(a.d) + [k for k in b.d if k not in a.d]:
+                d[k] = e("select", [c, a.d.get(k, zero), b.d.get(k, zero)])
+            return Dual(fb, r, d)
+        else:
+            raise NotImplementedError(op)
+        d = {}
+        for k in list(a.d) + [k for k in b.d if k not in a.d]:
+            terms = []
+            if k in a.d:
+                terms.append(e("fmul", [da, a.d[k]]))
+            if k in b.d:
+                terms.append(e("fmul", [db, b.d[k]]))
+            d[k] = terms[0] if len(terms) == 1 else e("fadd", terms)
+        return Dual(fb, r, d)
+
+    return f
+
+
+power = _binary("pow")
+atan2 = _binary("atan2")
+hypot = _binary("hypot")
+fmin = _binary("fmin")
+fmax = _binary("fmax")
 
 
 def cmp(op: str, a: Dual, b) -> Val:

@@ -25,7 +25,8 @@ from __future__ import annotations
 import pickle
 from typing import Dict
 
-from ..mir.builder import Dual, IfElse, ModelBuilder, cmp, exp, ln, sqrt
+from ..mir import builder as B
+from ..mir.builder import Dual, IfElse, ModelBuilder, cmp, exp, ln, select, sqrt
 
 KB_Q = 1.380649e-23 / 1.602176634e-19
 
@@ -126,6 +127,170 @@ def diode_bundle() -> dict:
     m.contrib("A", "CI", resist=idio * mf, react=qd * mf)
     vser = m.voltage("CI", "C")
     m.contrib("CI", "C", resist=vser * gs * mf)
+    return m.finalize()
+
+
+def opcov_bundle() -> dict:
+    """Opcode-coverage model: every MIR opcode and callback class the reference translates
+    (openvaf_jax/codegen/instruction.py:156-263 opcodes, :469-703 callbacks) is on the executed path of a small
+    device, so that the reference code generator, the oracle interpreter and the emitted CUDA kernel can be
+    compared on ``pow atan2 hypot fmin fmax``, the trigonometric / hyperbolic family, ``floor ceil clog2 log``,
+    ``frem``, casts, integer / bitwise / boolean ops, every comparison, ``select copy optbarrier``, ``$simparam``,
+    ``analysis()``, ``ddt``, ``ddx``, noise, ``abs/min/max`` calls, ``$limit`` with pnjlim AND fetlim, nested
+    diamonds, triangles and a three-way PHI.  Topology: A --[nonlinear branch]-- M --[rser]-- B, M collapses
+    into B when rser == 0.  Every branch current is a bounded, smooth-ish function of its voltage plus a linear
+    conductance, so the device also survives a DC solve and a transient."""
+    m = ModelBuilder("opcov", ["A", "B"], ["M"])
+    P = {}
+    for pname, dflt, inst in [("g0", 1e-3, False), ("pexp", 1.7, False), ("nf", 3.0, True), ("mode", 2.0, False),
+                              ("rser", 50.0, False), ("cq", 1e-12, False), ("vto", 0.4, False), ("isat", 1e-12, False),
+                              ("scale", 1.0, True)]:
+        P[pname] = m.model_param(pname, dflt, is_instance=inst)
+    t_i, t_e = m.temperature()
+    mf = m.mfactor()
+    fi, fe = m.init, m.eval
+    I = lambda k: P[k][0]  # noqa: E731
+    E = lambda k: P[k][1]  # noqa: E731
+
+    # ---- init: integer arithmetic on the finger count, casts, cache values, collapse decision
+    nf_i = fi.emit("ficast", [I("nf").v], ty="i")                        # int(floor(nf))
+    nf2 = fi.emit("imul", [nf_i, fi.iconst(2)], ty="i")
+    nf3 = fi.emit("iadd", [nf2, fi.iconst(1)], ty="i")
+    nfh = fi.emit("idiv", [nf3, fi.iconst(2)], ty="i")                   # floor division
+    nfr = fi.emit("irem", [nf3, fi.iconst(4)], ty="i")
+    nfs = fi.emit("isub", [nfh, nfr], ty="i")
+    nfn = fi.emit("ineg", [nfs], ty="i")
+    nfx = fi.emit("ixor", [fi.emit("iand", [nf3, fi.iconst(6)], ty="i"), fi.emit("ior", [nfr, fi.iconst(8)], ty="i")], ty="i")
+    nfsh = fi.emit("ishr", [fi.emit("ishl", [nfx, fi.iconst(3)], ty="i"), fi.iconst(1)], ty="i")
+    nfnot = fi.emit("inot", [nfn], ty="i")
+    geo_i = Dual(fi, fi.emit("ifcast", [fi.emit("iadd", [nfsh, nfnot], ty="i")]))
+    odd = fi.emit("ine", [nfr, fi.iconst(0)], ty="b")
+    big = fi.emit("ige", [nf_i, fi.iconst(3)], ty="b")
+    both = fi.emit("beq", [odd, big], ty="b")
+    fsel = Dual(fi, fi.emit("select", [both, fi.fconst(1.25), fi.fconst(0.75)]))
+    vt_i = t_i * KB_Q
+    geff_i = I("g0") * I("scale") * (1.0 + geo_i * 1e-3) * fsel
+    lg2_i = B.clog2(I("nf") + 4.0)
+    l10_i = B.log10(I("g0") * 1e6 + 10.0)
+    rs_pos = cmp("fgt", I("rser"), 0.0)
+    ie = IfElse(fi, rs_pos, "triangle")
+    gs_then = 1.0 / I("rser")
+    ie.end()
+    gs_i = ie.phi(gs_then, 0.0)
+    vt, geff, lg2, l10, gs = m.cache(vt_i), m.cache(geff_i), m.cache(lg2_i), m.cache(l10_i), m.cache(gs_i)
+    vcrit = m.cache(vt_i * ln(vt_i / (I("isat") * 1.4142135623730951)))
+    m.collapsible("M", "B", decision_init=rs_pos, negate=True)
+
+    # ---- eval
+    vraw = m.voltage("A", "M")
+    prev0, _en = m.limit_params(0)
+    prev1, _en = m.limit_params(1)
+    # $limit(V(A,M), "pnjlim", vt, vcrit) feeds the junction term; $limit(V(A,M), "fetlim", vto) the FET-like term
+    vl0 = fe.call("BuiltinLimit { name: pnjlim, num_args: 4 }", [vraw.v, prev0.v, vt.v, vcrit.v])
+    vj = Dual(fe, fe.call("StoreLimit(LimState(0))", [vl0]), dict(vraw.d))
+    vl1 = fe.call("BuiltinLimit { name: fetlim, num_args: 3 }", [vraw.v, prev1.v, E("vto").v])
+    vf = Dual(fe, fe.call("StoreLimit(LimState(1))", [vl1]), dict(vraw.d))
+    v = vraw
+    gmin = Dual(fe, fe.call("SimParam", [fe.sconst("gmin")]))
+    abst = Dual(fe, fe.call("SimParam", [fe.sconst("abstol")]))
+    tnom = Dual(fe, fe.call("SimParamOpt", [fe.sconst("tnom"), fe.fconst(27.0)]))
+    is_tran = fe.call("Analysis", [fe.sconst("tran")], ty="b")
+    is_dc = fe.call("Analysis", [fe.sconst("dc")], ty="b")
+    unit = geff * 1e-1  # currents of the exotic terms: ~1e-4 A/V scale
+
+    # (1) powers / two-argument functions
+    t1 = B.power(B.fabs(v) + 0.1, E("pexp")) * 0.3 + B.atan2(v, v * v + 0.5) + B.hypot(v, E("vto")) \
+        + B.fmin(v, 0.8) * 0.5 + B.fmax(v, -0.2) * 0.25
+    # (2) trigonometric / hyperbolic family on bounded arguments
+    vb = B.tanh(v)                      # in (-1, 1)
+    t2 = B.sin(v) + B.cos(v * 2.0) + B.tan(vb * 0.5) + B.sinh(vb) + B.cosh(vb) + B.asin(vb * 0.5) + B.acos(vb * 0.5) \
+        + B.atan(v) + B.asinh(v) + B.acosh(v * v + 1.5) + B.atanh(vb * 0.5)
+    # (3) piecewise-constant functions of the voltage (zero derivative), float remainder, casts
+    seg = B.floor(v * 3.0) + B.ceil(v * 2.0) * 0.5
+    k_i = fe.emit("ficast", [(v * 4.0).v], ty="i")
+    k_odd = fe.emit("ibcast", [fe.emit("iand", [k_i, fe.iconst(1)], ty="i")], ty="b")
+    k_f = Dual(fe, fe.emit("bfcast", [k_odd]))
+    k_b = Dual(fe, fe.emit("ifcast", [fe.emit("bicast", [fe.emit("fbcast", [seg.v], ty="b")], ty="i")]))
+    rem = Dual(fe, fe.emit("frem", [(v * v + 0.3).v, fe.fconst(0.25)]))
+    t3 = (seg * 0.01 + k_f * 0.02 + k_b * 0.03 + rem * 0.04) * v
+    # (4) comparisons + select + boolean ops
+    c_lt, c_le = cmp("flt", v, 0.1), cmp("fle", v, 0.3)
+    c_gt, c_ge = cmp("fgt", v, 0.7), cmp("fge", v, 0.9)
+    c_eq, c_ne = cmp("feq", v, 0.0), cmp("fne", v, 0.5)
+    c_a = fe.emit("bne", [c_lt, c_ge], ty="b")
+    c_b = fe.emit("bnot", [fe.emit("beq", [c_le, c_gt], ty="b")], ty="b")
+    mode_i = fe.emit("ficast", [E("mode").v], ty="i")
+    c_m = fe.emit("ieq", [mode_i, fe.iconst(2)], ty="b")
+    c_m2 = fe.emit("ilt", [mode_i, fe.iconst(5)], ty="b")
+    c_m3 = fe.emit("igt", [mode_i, fe.iconst(0)], ty="b")
+    c_m4 = fe.emit("ile", [mode_i, fe.iconst(2)], ty="b")
+    t4 = select(c_a, v * 0.2, v * 0.1) + select(c_b, v * v * 0.05, 0.0) + select(c_eq, v + 1.0, 0.0) * 1e-3 \
+        + select(c_ne, v, 0.0) * 0.01 + select(c_m, v, 0.0) * 0.02 + select(c_m2, v, 0.0) * 0.03 \
+        + select(c_m3, v, 0.0) * 0.04 + select(c_m4, v, 0.0) * 0.05
+    # (5) logs, copy / optbarrier, call-style abs / min / max
+    cp = Dual(fe, fe.emit("copy", [v.v]), dict(v.d))
+    ob = Dual(fe, fe.emit("optbarrier", [(v * 0.5).v]), {k: fe.emit("fmul", [fe.fconst(0.5), d]) for k, d in v.d.items()})
+    c_abs = Dual(fe, fe.call("abs", [v.v]), {k: fe.emit("select", [c_lt, d, d]) for k, d in v.d.items()})
+    c_min = Dual(fe, fe.call("min", [v.v, fe.fconst(0.6)]))
+    c_max = Dual(fe, fe.call("max", [v.v, fe.fconst(-0.1)]))
+    t5 = B.log10(v * v + 1.0) + ln(v * v + 2.0) + sqrt(v * v + 0.01) + exp(vb) + cp * 0.1 + ob * 0.1 \
+        + c_abs * 1e-3 + (c_min + c_max) * 1e-3 + lg2 * 1e-3 + l10 * 1e-3
+    # (6) control flow: nested diamond inside a diamond, a triangle, and a three-way merge
+    outer = IfElse(fe, c_gt, "diamond")
+    inner = IfElse(fe, c_ge, "diamond")
+    a_in = v * 0.9 + 0.07
+    inner.otherwise()
+    b_in = v * v
+    inner.end()
+    hi = inner.phi(a_in, b_in)
+    outer.otherwise()
+    tri = IfElse(fe, c_lt, "triangle")
+    lo_then = B.sin(v) * 0.5
+    tri.end()
+    lo = tri.phi(lo_then, v * 0.5)
+    outer.end()
+    t6 = outer.phi(hi, lo)
+    # three-way PHI: block X branches to P or Q, Q branches to R or S; P, R, S all jump to the merge block
+    b_p, b_q, b_r, b_s, b_m = (fe.new_block() for _ in range(5))
+    fe.br(c_le, b_p, b_q)
+    fe.cur = b_p
+    w_p = v * 0.11
+    fe.jmp(b_m)
+    fe.cur = b_q
+    fe.br(c_gt, b_r, b_s)
+    fe.cur = b_r
+    w_r = v * 0.07 + 0.028
+    fe.jmp(b_m)
+    fe.cur = b_s
+    w_s = v * v * 0.1
+    fe.jmp(b_m)
+    fe.cur = b_m
+    zero = fe.fconst(0.0)
+    t7 = Dual(fe, fe.phi([(b_p, w_p.v), (b_r, w_r.v), (b_s, w_s.v)]),
+              {k: fe.phi([(b_p, w_p.d.get(k, zero)), (b_r, w_r.d.get(k, zero)), (b_s, w_s.d.get(k, zero))]) for k in v.d})
+    # (7) callbacks that evaluate to zero or pass through
+    fe.call("white_noise", [(gmin * 4.0).v, fe.sconst("thermal")])
+    fe.call("flicker_noise", [gmin.v, fe.fconst(1.0), fe.sconst("flicker")])
+    ddx0 = Dual(fe, fe.call("ddx", [v.v]))
+    fe.call("LimDiscontinuity", [])
+    fe.call("Print { kind: Display, arg_tys: [] }", [fe.sconst("opcov\n")])
+    fe.call("set_MinInclusive", [v.v])
+    fe.call("SetRetFlag(Finish)", [])
+    fe.call("CollapseHint(node2, Some(node1))", [])
+    tran_f = Dual(fe, fe.emit("bfcast", [is_tran]))
+    dc_f = Dual(fe, fe.emit("bfcast", [is_dc]))
+    # junction (pnjlim-limited) and FET-like (fetlim-limited) terms
+    ij = E("isat") * (_limexp(vj / vt) - 1.0)
+    vov = vf - E("vto")
+    ifet = geff * 0.5 * (vov + sqrt(vov * vov + 0.01)) * B.tanh(vf * 2.0)
+    inl = geff * v + unit * (t1 + t2 + t3 + t4 + t5 + t6 + t7) * 1e-2 + ij + ifet + gmin * v + abst * 1e-3 * v \
+        + (tnom - 27.0) * 1e-9 * v + ddx0 + tran_f * 1e-9 * v + dc_f * 2e-9 * v
+    qch = Dual(fe, fe.call("ddt", [(E("cq") * (v + B.tanh(v) * 0.2)).v]), None)
+    q = E("cq") * (v + B.tanh(v) * 0.2)
+    qd = Dual(fe, qch.v, dict(q.d))
+    _ = t_e
+    m.contrib("A", "M", resist=inl * mf, react=qd * mf)
+    m.contrib("M", "B", resist=m.voltage("M", "B") * gs * mf)
     return m.finalize()
 
 
@@ -259,6 +424,7 @@ _BUILDERS = {
     "capacitor": capacitor_bundle,
     "diode": diode_bundle,
     "psp103": mos_psp_shaped_bundle,
+    "opcov": opcov_bundle,
 }
 _CACHE: Dict[str, dict] = {}
 
