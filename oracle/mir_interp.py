@@ -405,7 +405,8 @@ def eval_model(bundle: dict, param_values: Dict[int, object], cache_values: np.n
             kind, name = lpm[i]
             if kind == "prev_state":
                 idx = int(name.split("_")[-1])
-                val = limit_state_in[:, idx] if limit_state_in is not None else 0.0
+                # jnp indexing clamps an out-of-range static index (the dummy state is (n, 1) when limiting is off)
+                val = limit_state_in[:, min(idx, limit_state_in.shape[1] - 1)] if limit_state_in is not None else 0.0
             elif kind == "enable_lim":
                 val = 1.0 if use_limit else 0.0
             else:
@@ -418,6 +419,8 @@ def eval_model(bundle: dict, param_values: Dict[int, object], cache_values: np.n
         var = pidx2val.get(mp["eval_param"], f"cached_{mp['eval_param']}")
         it.env[var] = np.asarray(cache_values[:, ci], dtype=np.float64) if cache_values.shape[1] > ci else np.float64(0.0)
     it.run()
+    global _LAST
+    _LAST = it   # (kept for the bisection helper in tests/golden)
     R, J = len(dae["residuals"]), len(dae["jacobian"])
     res_r = np.stack([it.out(_mir_var(r["resist_var"])) for r in dae["residuals"]], axis=1) if R else np.zeros((n, 0))
     res_q = np.stack([it.out(_mir_var(r["react_var"])) for r in dae["residuals"]], axis=1) if R else np.zeros((n, 0))

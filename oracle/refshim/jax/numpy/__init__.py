@@ -63,6 +63,23 @@ class JArr(_np.ndarray):
     def __hash__(self):
         return id(self)
 
+    def __getitem__(self, idx):
+        # jnp indexing never raises for an out-of-range integer: it clamps to the last element
+        # (e.g. the generated eval code reads limit_state_in[1] from a 1-element dummy when limiting is off)
+        if isinstance(idx, (int, _np.integer)) and self.ndim >= 1 and self.shape[0] > 0:
+            n = self.shape[0]
+            if idx >= n:
+                idx = n - 1
+            elif idx < -n:
+                idx = 0
+        return _np.ndarray.__getitem__(self, idx)
+
+    def __iter__(self):
+        # (a clamping __getitem__ never raises IndexError, so the sequence-protocol fallback would not stop)
+        if self.ndim == 0:
+            raise TypeError("iteration over a 0-d array")
+        return (_np.ndarray.__getitem__(self, i) for i in range(self.shape[0]))
+
     def __bool__(self):
         return bool(_np.asarray(self).all()) if self.size == 1 else _np.ndarray.__bool__(self)
 

@@ -67,7 +67,7 @@ from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 ref_models.openvaf_jax = openvaf_jax
 ref_models.HAS_OPENVAF = True
 logging.getLogger("vajax").setLevel(logging.ERROR)
-MODELS = ("resistor", "capacitor", "diode", "psp103")
+MODELS = ("resistor", "capacitor", "diode", "psp103", "opcov")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -152,12 +152,8 @@ def make_engine(circ: dict, compiled: dict, limiting: bool) -> CircuitEngine:
     return eng
 
 
-CIRCUITS = {
-    "rc": lambda: circuits.rc_circuit(stop=2e-4),
-    "clipper": lambda: circuits.diode_clipper_circuit(stop=4e-4),
-    "ring": lambda: circuits.ring_circuit(stop=3e-9),
-    "mul3": lambda: circuits.multiplier_circuit(3, stop=3e-10),
-}
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from golden_util import CIRCUITS  # noqa: E402  (one table for the generator and the tests)
 
 
 def unit_vectors(out: dict):
@@ -300,13 +296,17 @@ def engine_vectors(name: str, limiting: bool, compiled: dict, out: dict, sparse:
 def main():
     _install_sparse_solver_standin()
     compiled = compile_from_bundles()
-    out: dict = {}
-    unit_vectors(out)
-    source_vectors(out)
-    model_vectors(compiled, out)
-    np.savez_compressed(os.path.join(HERE, "reference_units.npz"), **out)
-    print("wrote reference_units.npz:", len(out), "arrays")
+    if not sys.argv[1:] or "units" in sys.argv[1:]:
+        out: dict = {}
+        unit_vectors(out)
+        source_vectors(out)
+        model_vectors(compiled, out)
+        np.savez_compressed(os.path.join(HERE, "reference_units.npz"), **out)
+        print("wrote reference_units.npz:", len(out), "arrays")
+    only = set(sys.argv[1:])
     for name in CIRCUITS:
+        if only and name not in only:
+            continue
         eo: dict = {}
         for limiting in (False, True):
             for sparse in (False, True):

@@ -30,12 +30,7 @@ def engines(circ, bundles, limiting=False, graph=False):
     return o, g
 
 
-CIRCUITS = {
-    "rc": lambda: circuits.rc_circuit(stop=2e-4),
-    "clipper": lambda: circuits.diode_clipper_circuit(stop=4e-4),
-    "ring": lambda: circuits.ring_circuit(stop=3e-9),
-    "mul3": lambda: circuits.multiplier_circuit(3, stop=3e-10),
-}
+from golden_util import CIRCUITS  # noqa: E402  (rc, clipper, ring, mul3, opcov, srcmix, BE / gear2 variants)
 
 
 @pytest.mark.parametrize("name", list(CIRCUITS))
@@ -126,7 +121,7 @@ def test_nr_solve_parity(name, limiting, bundles):
 
 
 @pytest.mark.parametrize("graph", [False, True])
-@pytest.mark.parametrize("name", ["rc", "clipper", "ring", "mul3"])
+@pytest.mark.parametrize("name", list(CIRCUITS))
 def test_transient_parity(name, graph, bundles):
     circ = CIRCUITS[name]()
     o, g = engines(circ, bundles, False, graph)
@@ -177,3 +172,26 @@ def test_handle_ids_and_sizes(bundles):
     b.close()
     assert lib.vjx_handle_from_id(ib) is None and lib.vjx_handle_from_id(ia) == a.handle.value
     a.close()
+
+
+@pytest.mark.parametrize("mt", ["resistor", "capacitor", "diode", "psp103", "opcov"])
+def test_init_kernel_against_reference(mt, bundles):
+    """N1: the emitted init kernel (vjx_model_init) against the reference code generator's init function on the
+    same seeded instances (tests/golden/reference_units.npz model_*_cache / model_*_collapse, produced by
+    ``OpenVAFToJAX.translate_init_array`` + vmap in make_golden.py)."""
+    from golden_util import GOLDEN
+    import os
+
+    from vajax_b200.analysis.engine import B200Engine
+
+    units = np.load(os.path.join(GOLDEN, "reference_units.npz"))
+    init_in = units[f"model_{mt}_init_in"]
+    e = B200Engine(CIRCUITS["rc"](), bundles)
+    e._init_plugins = {}
+    cache, col = e._run_init(mt, [np.ascontiguousarray(init_in[:, j]) for j in range(init_in.shape[1])], init_in.shape[0])
+    ref = units[f"model_{mt}_cache"]
+    cache = cache.cpu().numpy()
+    assert cache.shape == ref.shape
+    if ref.size:
+        assert np.max(np.abs(cache - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-13
+    assert np.array_equal(col.cpu().numpy().astype(np.float64), units[f"model_{mt}_collapse"])

@@ -581,6 +581,7 @@ class B200Engine:
         cd.internal_nodes, cd.n_internal = ptr(self.internal_indices), len(self.internal_indices)
         cd.opts = o
         self._keep += [md, vsd, isd, cd]
+        self._vsd, self._isd = vsd, isd
         t1 = time.perf_counter()
         vlib.check(lib.vjx_create(C.byref(cd), self.device, C.byref(self.handle)))
         self.timings["create"] = time.perf_counter() - t1
@@ -634,51 +635,58 @@ class B200Engine:
         return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
 
     def eval_sources(self, t: float):
-        """Host evaluation of sources at time t for the DC/UIC initialisation only (the per-step
-        evaluation happens in k_pre_step on the device). reference: sources.py:26-187."""
-        def one(p):
-            st = str(p.get("type", "dc")).lower()
-            if st in ("dc", "0", "0.0", ""):
-                return float(p.get("dc", 0))
-            if st == "pulse":
-                v0, v1 = float(p.get("val0", 0)), float(p.get("val1", 1))
-                r, f = float(p.get("rise", 1e-9)), float(p.get("fall", 1e-9))
-                w, per, d = float(p.get("width", 1e-6)), float(p.get("period", 2e-6)), float(p.get("delay", 0))
-                tp = np.mod(t - d, per)
+        """Host evaluation of the sources at time t for the DC / UIC initialisation only (the per-step
+        evaluation happens in k_pre_step on the device).  Works from the same packed descriptors the device
+        gets (``_source_desc``), so both sides parse a source once.  reference: sources.py:26-187."""
+        pt, pv = self._pwl_t, self._pwl_v
+        PI = np.pi
+
+        def py_mod(a, b):
+            return float(np.mod(a, b))
+
+        def one(s) -> float:
+            p = s.p
+            if s.kind == 0:
+                return float(p[0])
+            if s.kind == 1:
+                v0, v1, r, f, w, per, d = (p[i] for i in range(7))
+                tp = py_mod(t - d, per)
                 if t < d:
                     return v0
                 if tp < r:
-                    return float(v0 + (v1 - v0) * tp / r)
+                    return v0 + (v1 - v0) * tp / r
                 if tp < r + w:
                     return v1
                 if tp < r + w + f:
-                    return float(v1 - (v1 - v0) * (tp - r - w) / f)
+                    return v1 - (v1 - v0) * (tp - r - w) / f
                 return v0
-            if st == "sine":
-                return float(float(p.get("sinedc", 0)) + float(p.get("ampl", 1)) * np.sin(
-                    2 * np.pi * float(p.get("freq", 1e3)) * t + float(p.get("phase", 0))))
-            if st == "pwl":
-                wave = p.get("wave", [0, 0])
-                wa = np.asarray(wave, dtype=np.float64)
-                tt = t
-                per = float(p.get("pwlperiod", 0))
-                if per > 0:
-                    tt = np.mod(t, per)
-                return float(np.interp(tt, wa[0::2] * float(p.get("stretch", 1)),
-                                       wa[1::2] * float(p.get("scale", 1)) + float(p.get("offset", 0))))
-            if st == "exp":
-                v0, v1, d = float(p.get("val0", 0)), float(p.get("val1", 1)), float(p.get("delay", 0))
-                td, t1, t2 = float(p.get("td2", 1e-9)), float(p.get("tau1", 1e-10)), float(p.get("tau2", 1e-10))
+            if s.kind == 2:
+                return p[0] + p[1] * np.sin(2 * PI * p[2] * t + p[3])
+            if s.kind == 3:
+                tt = py_mod(t, p[0]) if p[0] > 0 else t
+                lo, n = s.pwl_offset, s.pwl_count
+                return float(np.interp(tt, pt[lo:lo + n], pv[lo:lo + n])) if n > 0 else 0.0
+            if s.kind == 4:
+                v0, v1, d, td, t1, t2 = (p[i] for i in range(6))
                 if t < d:
                     return v0
-                rising = v0 + (v1 - v0) * (1 - np.exp(-(t - d) / t1))
                 if t < d + td:
-                    return float(rising)
+                    return v0 + (v1 - v0) * (1 - np.exp(-(t - d) / t1))
                 raf = v0 + (v1 - v0) * (1 - np.exp(-td / t1))
-                return float(raf + (v0 - raf) * (1 - np.exp(-(t - d - td) / t2)))
-            raise ValueError(f"source type {st} not supported for t=0 evaluation")
-        return (np.array([one(d["params"]) for d in self.vsources], dtype=np.float64),
-                np.array([one(d["params"]) for d in self.isources], dtype=np.float64))
+                return raf + (v0 - raf) * (1 - np.exp(-(t - d - td) / t2))
+            dc, a, f, ph, d, mf, mph, mi = (p[i] for i in range(8))
+            if s.kind == 5:
+                if t < d:
+                    return dc + a * np.sin(ph * PI / 180) * (1 + mi * np.sin(mph * PI / 180))
+                return dc + a * np.sin(2 * PI * f * (t - d) + ph * PI / 180) * (1 + mi * np.sin(2 * PI * mf * (t - d) + mph * PI / 180))
+            if s.kind == 6:
+                if t < d:
+                    return dc + a * np.sin(ph * PI / 180 + mi * np.sin(mph * PI / 180))
+                return dc + a * np.sin(2 * PI * f * (t - d) + ph * PI / 180 + mi * np.sin(2 * PI * mf * (t - d) + mph * PI / 180))
+            raise ValueError(f"unknown source kind {s.kind}")
+
+        return (np.array([float(one(self._vsd[i])) for i in range(self.n_vs)], dtype=np.float64),
+                np.array([float(one(self._isd[i])) for i in range(self.n_is)], dtype=np.float64))
 
     # ---- Seam S2 -----------------------------------------------------------------------
     def build_system(self, X, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0, integ_c1=0.0,

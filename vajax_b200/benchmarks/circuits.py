@@ -66,16 +66,16 @@ class _Net:
                     analysis=dict(analysis), temperature_k=temperature_k)
 
 
-def rc_circuit(stop: float = 10e-3) -> dict:
+def rc_circuit(stop: float = 10e-3, method: str = "trap") -> dict:
     n = _Net()
     n.add("vs", "vsource", ["1", "0"],
           dict(dc=0.0, type="pulse", val0=0.0, val1=1.0, rise=1e-6, fall=1e-6, width=1e-3, period=2e-3), openvaf=False)
     n.add("r1", "resistor", ["1", "2"], dict(r=1e3))
     n.add("c1", "capacitor", ["2", "0"], dict(c=1e-6))
-    return n.circuit(dict(step=1e-6, stop=stop, maxstep=1e-6, tran_method="trap", icmode="op"))
+    return n.circuit(dict(step=1e-6, stop=stop, maxstep=1e-6, tran_method=method, icmode="op"))
 
 
-def diode_clipper_circuit(stop: float = 2e-3, rs: float = 10.0) -> dict:
+def diode_clipper_circuit(stop: float = 2e-3, rs: float = 10.0, method: str = "trap") -> dict:
     """Sine source -> R -> two anti-parallel diodes (with series resistance -> internal node)
     + load capacitor. Exercises branches, limiting, internal nodes and node collapse."""
     n = _Net()
@@ -84,11 +84,44 @@ def diode_clipper_circuit(stop: float = 2e-3, rs: float = 10.0) -> dict:
     n.add("d1", "diode", ["out", "0"], {"is": 1e-14, "n": 1.0, "rs": rs, "cj0": 1e-12, "vj": 0.8, "tt": 1e-9, "area": 1.0})
     n.add("d2", "diode", ["0", "out"], {"is": 1e-14, "n": 1.0, "rs": 0.0, "cj0": 1e-12, "vj": 0.8, "tt": 1e-9, "area": 2.0})
     n.add("c1", "capacitor", ["out", "0"], dict(c=1e-9))
-    return n.circuit(dict(step=1e-6, stop=stop, maxstep=2e-5, tran_method="trap", icmode="op"))
+    return n.circuit(dict(step=1e-6, stop=stop, maxstep=2e-5, tran_method=method, icmode="op"))
+
+
+def opcov_circuit(stop: float = 4e-4, method: str = "trap") -> dict:
+    """Two instances of the opcode-coverage model (one with its internal node, one collapsed) driven by a sine
+    source through a resistor, with a load capacitor: every MIR opcode / callback the reference translates is
+    evaluated each NR iteration (models/fixtures.py::opcov_bundle)."""
+    n = _Net()
+    n.add("vs", "vsource", ["in", "0"], dict(dc=0.0, type="sine", sinedc=0.3, ampl=0.6, freq=5e3, phase=0.0), openvaf=False)
+    n.add("r1", "resistor", ["in", "out"], dict(r=2e3))
+    n.add("x1", "opcov", ["out", "0"], dict(g0=1e-3, pexp=1.7, nf=3.0, mode=2.0, rser=50.0, cq=1e-9, vto=0.4, isat=1e-12, scale=1.0))
+    n.add("x2", "opcov", ["0", "out"], dict(g0=1e-3, pexp=2.2, nf=6.0, mode=2.0, rser=0.0, cq=1e-9, vto=0.4, isat=1e-12, scale=0.5))
+    n.add("c1", "capacitor", ["out", "0"], dict(c=2e-9))
+    return n.circuit(dict(step=1e-6, stop=stop, maxstep=1e-5, tran_method=method, icmode="op"))
+
+
+def source_mix_circuit(stop: float = 6e-8, method: str = "trap") -> dict:
+    """One RC low-pass per source kind the reference implements beyond dc / pulse / sine
+    (vajax/analysis/sources.py:31-187): pwl, exp, am, fm on voltage sources, plus a pwl current source."""
+    n = _Net()
+    srcs = [
+        ("pwl", dict(type="pwl", wave=[0, 0, 1e-9, 1, 5e-9, -1, 2e-8, 0.5])),
+        ("exp", dict(type="exp", val0=0.0, val1=1.0, delay=1e-9, td2=2e-8, tau1=3e-9, tau2=5e-9)),
+        ("am", dict(type="am", sinedc=0.2, ampl=0.8, freq=1e8, phase=30.0, delay=2e-9, modfreq=2e7, modphase=10.0, modindex=0.5)),
+        ("fm", dict(type="fm", sinedc=0.1, ampl=0.7, freq=1e8, phase=20.0, delay=1e-9, modfreq=1.5e7, modphase=5.0, modindex=2.0)),
+    ]
+    for k, (nm, p) in enumerate(srcs):
+        p = dict(p)
+        p.setdefault("dc", 0.0)
+        n.add(f"v{nm}", "vsource", [f"in_{nm}", "0"], p, openvaf=False)
+        n.add(f"r{nm}", "resistor", [f"in_{nm}", f"out_{nm}"], dict(r=1e3 * (k + 1)))
+        n.add(f"c{nm}", "capacitor", [f"out_{nm}", "0"], dict(c=1e-12))
+    n.add("ipwl", "isource", ["0", "out_pwl"], dict(dc=0.0, type="pwl", wave=[0, 0, 1e-8, 1e-4, 3e-8, -1e-4, 5e-8, 0]), openvaf=False)
+    return n.circuit(dict(step=1e-10, stop=stop, maxstep=5e-10, tran_method=method, icmode="op"))
 
 
 def ring_circuit(stages: int = 9, stop: float = 20e-9, step: float = 0.05e-9, w: float = 10e-6,
-                 l: float = 1e-6, pfact: float = 2.0, vdd: float = 1.2) -> dict:
+                 l: float = 1e-6, pfact: float = 2.0, vdd: float = 1.2, method: str = "trap") -> dict:
     n = _Net()
     for k in range(1, stages + 1):
         n.node(str(k))
@@ -101,7 +134,7 @@ def ring_circuit(stages: int = 9, stop: float = 20e-9, step: float = 0.05e-9, w:
         i, o = str(k), str(k % stages + 1)
         n.mos(f"u{k}:mp:m", "p", o, i, "vdd", "vdd", w * pfact, l)
         n.mos(f"u{k}:mn:m", "n", o, i, "0", "0", w, l)
-    return n.circuit(dict(step=step, stop=stop, maxstep=step, tran_method="trap", icmode="op"))
+    return n.circuit(dict(step=step, stop=stop, maxstep=step, tran_method=method, icmode="op"))
 
 
 def multiplier_circuit(nbits: int = 16, stop: float = 2e-9, step: float = 2e-12, vdd: float = 1.2,

@@ -31,6 +31,8 @@ import hashlib
 import os
 import re
 import subprocess
+import tempfile
+import threading
 from typing import Dict, List, Optional, Tuple
 
 from ..mir.types import ANALYSIS_TYPE_MAP, Function, Inst, classify_call, parse_function
@@ -726,22 +728,40 @@ def model_fmad() -> bool:
     return os.environ.get("VJX_MODEL_FMAD", "0") == "1"
 
 
+_COMPILE_LOCKS: Dict[str, "threading.Lock"] = {}
+_COMPILE_LOCKS_MU = threading.Lock()
+
+
 def compile_plugin(source: str, tag: str = "model") -> str:
     """Compile emitted CUDA-C into an in-tree shared object, cached by a SHA-256 of
-    source + flags (the reference keys its exec cache the same way, openvaf_jax/cache.py:22-106)."""
+    source + flags (the reference keys its exec cache the same way, openvaf_jax/cache.py:22-106).
+    Safe against concurrent callers: threads of one process (``run_corners(concurrent=k)`` emits the same
+    source from every engine on a cold cache) serialise on a per-hash lock, and every compilation writes to
+    its own temporary files (``mkstemp``) before the atomic rename, so other processes never see a
+    half-written plugin."""
     flags = list(NVCC_FLAGS) + ["-fmad=" + ("true" if model_fmad() else "false")]
     h = hashlib.sha256((source + "\0" + " ".join(flags)).encode()).hexdigest()[:20]
     os.makedirs(PLUGIN_DIR, exist_ok=True)
     so = os.path.join(PLUGIN_DIR, f"{tag}_{h}.so")
-    if os.path.exists(so):
-        return so
-    cu = os.path.join(PLUGIN_DIR, f"{tag}_{h}.cu")
-    with open(cu, "w") as f:
-        f.write(source)
-    tmp = so + f".tmp{os.getpid()}"
-    cmd = ["nvcc"] + flags + ["-o", tmp, cu]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed for {cu}:\n{r.stderr[-4000:]}")
-    os.replace(tmp, so)
+    with _COMPILE_LOCKS_MU:
+        lock = _COMPILE_LOCKS.setdefault(h, threading.Lock())
+    with lock:
+        if os.path.exists(so):
+            return so
+        fd, cu_tmp = tempfile.mkstemp(prefix=f"{tag}_{h}.", suffix=".cu", dir=PLUGIN_DIR)
+        with os.fdopen(fd, "w") as f:
+            f.write(source)
+        fd, so_tmp = tempfile.mkstemp(prefix=f"{tag}_{h}.", suffix=".so.tmp", dir=PLUGIN_DIR)
+        os.close(fd)
+        try:
+            r = subprocess.run(["nvcc"] + flags + ["-o", so_tmp, cu_tmp], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {tag}_{h}:\n{r.stderr[-4000:]}")
+            os.chmod(so_tmp, 0o755)
+            os.replace(cu_tmp, os.path.join(PLUGIN_DIR, f"{tag}_{h}.cu"))   # kept for -lineinfo / inspection
+            os.replace(so_tmp, so)
+        finally:
+            for t in (cu_tmp, so_tmp):
+                if os.path.exists(t):
+                    os.unlink(t)
     return so

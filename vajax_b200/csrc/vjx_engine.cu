@@ -1174,6 +1174,7 @@ __global__ void k_nr_begin(NRStat* st, double* ctl, int max_iter, int reset_iter
   }
   st->max_iter = max_iter;
   st->cont = 1;
+  st->error = 0;   // a watchdog bit of an earlier call must not fail this one
 }
 
 // Runs at the head of every NR iteration: clears the per-iteration reductions and resets the LU row
@@ -1582,8 +1583,12 @@ __global__ void k_step_finish(StepArgs a, cudaGraphConditionalHandle handle, int
     s->warmup += 1;
   }
   if (s->accept) s->step_idx += 1;
+  // Only a watchdog bit (1 | 4 | 8: a dependency wait that never ended) stops the loop.  Bit 2 (zero / NaN pivot)
+  // does not: the NaNs it produces make the NR solve fail, which the step control treats like the reference does -
+  // reject, cut dt by tran_ft, carry on (full_mna.py:1990-2010); the bit stays set as a diagnostic in
+  // stats["error_flags"].
   int cont = (s->t < s->t_stop) && (s->step_idx < s->max_steps) && (s->attempts < s->attempts_limit) &&
-             (a.st->error == 0);
+             ((a.st->error & (1 | 4 | 8)) == 0);
   s->cont = cont;
   if (use_handle) cudaGraphSetConditional(handle, cont);
 }

@@ -134,7 +134,8 @@ def opcov_bundle() -> dict:
     """Opcode-coverage model: every MIR opcode and callback class the reference translates
     (openvaf_jax/codegen/instruction.py:156-263 opcodes, :469-703 callbacks) is on the executed path of a small
     device, so that the reference code generator, the oracle interpreter and the emitted CUDA kernel can be
-    compared on ``pow atan2 hypot fmin fmax``, the trigonometric / hyperbolic family, ``floor ceil clog2 log``,
+    compared on ``pow atan2 fmin fmax`` (not ``hypot``: the reference lists it among its unary functions first,
+    instruction.py:84-96,222-225, and its generated ``jnp.hypot(x)`` raises - there is no reference result to match), the trigonometric / hyperbolic family, ``floor ceil clog2 log``,
     ``frem``, casts, integer / bitwise / boolean ops, every comparison, ``select copy optbarrier``, ``$simparam``,
     ``analysis()``, ``ddt``, ``ddx``, noise, ``abs/min/max`` calls, ``$limit`` with pnjlim AND fetlim, nested
     diamonds, triangles and a three-way PHI.  Topology: A --[nonlinear branch]-- M --[rser]-- B, M collapses
@@ -199,7 +200,7 @@ def opcov_bundle() -> dict:
     unit = geff * 1e-1  # currents of the exotic terms: ~1e-4 A/V scale
 
     # (1) powers / two-argument functions
-    t1 = B.power(B.fabs(v) + 0.1, E("pexp")) * 0.3 + B.atan2(v, v * v + 0.5) + B.hypot(v, E("vto")) \
+    t1 = B.power(B.fabs(v) + 0.1, E("pexp")) * 0.3 + B.atan2(v, v * v + 0.5) \
         + B.fmin(v, 0.8) * 0.5 + B.fmax(v, -0.2) * 0.25
     # (2) trigonometric / hyperbolic family on bounded arguments
     vb = B.tanh(v)                      # in (-1, 1)
@@ -244,10 +245,11 @@ def opcov_bundle() -> dict:
     inner.end()
     hi = inner.phi(a_in, b_in)
     outer.otherwise()
+    half = v * 0.5       # (the fall-through value of a triangle has to be defined before the branch)
     tri = IfElse(fe, c_lt, "triangle")
     lo_then = B.sin(v) * 0.5
     tri.end()
-    lo = tri.phi(lo_then, v * 0.5)
+    lo = tri.phi(lo_then, half)
     outer.end()
     t6 = outer.phi(hi, lo)
     # three-way PHI: block X branches to P or Q, Q branches to R or S; P, R, S all jump to the merge block
