@@ -74,29 +74,40 @@ def eval_flops(eng):
     return tot
 
 
-def make_circuit(workload: str, nbits: int, corner: int = 0):
+MODEL_DESC = {"psp103w": "PSP103-weight MOSFETs (psp103w: R=13, J=56, 754 parameters, 6.4k MIR instructions per evaluation)",
+              "psp103": "light PSP103-shaped surrogate MOSFETs (J=42, ~0.9k flops; round-1 stand-in)"}
+
+
+def make_circuit(workload: str, nbits: int, corner: int = 0, model: str = "psp103w"):
     from vajax_b200.benchmarks import circuits
 
     if workload == "ring":
-        return circuits.ring_circuit(), "9-stage ring oscillator (47 unknowns)"
+        return circuits.ring_circuit(mos_model=model), f"9-stage ring oscillator (47 unknowns), {MODEL_DESC[model]}"
     if workload == "mul":
         nb = nbits
     else:
         nb = 16
-    circ = circuits.multiplier_circuit(nb)
+    circ = circuits.multiplier_circuit(nb, mos_model=model)
     if corner:  # corner 0 of the sweep is the nominal circuit itself
         from vajax_b200.analysis.corners import apply_corner, sweep_corners
 
         circ = apply_corner(circ, sweep_corners(64)[corner % 64])
-    desc = (f"{nb}x{nb} carry-save array multiplier in the c6288/mul64 gate library "
-            f"({sum(1 for d in circ['devices'] if d['model'] == 'psp103')} PSP103-shaped MOSFETs), trap, uic")
+    desc = (f"{nb}x{nb} carry-save array multiplier in the c6288/mul64 gate library, "
+            f"{sum(1 for d in circ['devices'] if d['model'] == model)} {MODEL_DESC[model]}, trap, uic")
     return circ, desc
+
+
+def config_dict(args, desc, world, n_unknowns, csr_nnz):
+    """The same dict in both arms (the driver compares them)."""
+    return {"workload": desc, "circuit": args.workload, "model": args.model, "n_unknowns": int(n_unknowns), "csr_nnz": int(csr_nnz),
+            "parallelism": f"replicas x{world}" if world > 1 else "single circuit",
+            "l2": "256 MB flush between timed steps (value); value_l2_resident is the uninterrupted device loop"}
 
 
 def get_bundles():
     from vajax_b200.models.fixtures import get_bundle
 
-    return {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
+    return {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103", "psp103w")}
 
 
 class ClockSampler:
@@ -205,7 +216,7 @@ def run_b200(args, rank, world, local_rank):
 
     for gid in shard(n_corners * world, rank, world):  # rotated block-cyclic (corners.shard)
         corner_ids.append(gid)
-        circ, desc = make_circuit(args.workload, args.nbits, corner=gid)
+        circ, desc = make_circuit(args.workload, args.nbits, corner=gid, model=args.model)
         # every engine on its own stream: the sweep leg below runs the corners of a rank concurrently
         engines.append(B200Engine(circ, bundles, device=local_rank, use_device_graph=not args.no_graph,
                                   stream="own").prepare())
@@ -369,10 +380,9 @@ def run_b200(args, rank, world, local_rank):
         "metric": METRIC, "value": ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "circuit": args.workload, "n_unknowns": eng.n_aug, "csr_nnz": eng.nse,
-                   "corners_per_gpu": n_corners, "parallelism": f"replicas x{world}" if world > 1 else "single circuit",
-                   "l2": "256 MB flush between timed steps (value); value_l2_resident is the uninterrupted device loop",
-                   "steps_timed": g_steps, "attempts": int(cnts[3]), "nr_iterations": int(cnts[4]), "rejected": int(cnts[5])},
+        "config": config_dict(args, desc, world, eng.n_aug, eng.nse),
+        "run_stats": {"steps_timed": g_steps, "attempts": int(cnts[3]), "nr_iterations": int(cnts[4]), "rejected": int(cnts[5]),
+                      "corners_per_gpu": n_corners},
         "value_l2_resident": vals[1] / max(g_res_steps, 1),
         "value_nominal": per_corner[0] if corner_ids[0] == 0 else None,
         "rank0_corners": {"ids": corner_ids, "ms_per_step": per_corner},
@@ -400,6 +410,7 @@ def run_b200(args, rank, world, local_rank):
         out["mul64"] = mul64_record(args, local_rank, peak)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
+        out["cpu_baseline"].pop("n_unknowns"), out["cpu_baseline"].pop("csr_nnz")
     _emit(json.dumps(out))
 
 
@@ -410,7 +421,7 @@ def mul64_record(args, local_rank, peak):
     from vajax_b200.benchmarks.circuits import mul64_circuit
 
     t0 = time.perf_counter()
-    e = B200Engine(mul64_circuit(64), get_bundles(), device=local_rank, use_device_graph=True).prepare()
+    e = B200Engine(mul64_circuit(64, mos_model=args.model), get_bundles(), device=local_rank, use_device_graph=True).prepare()
     prep = time.perf_counter() - t0
     W, K = 3, args.mul64_steps
     e.tran_begin(max_steps=1 + W)
@@ -443,7 +454,7 @@ def cpu_baseline(args, sample_steps: int, threads_note: str = "") -> dict:
     """The oracle port (NumPy MIR interpreter + SciPy SuperLU) on the host cores, bounded sample."""
     from oracle.engine import OracleEngine
 
-    circ, _ = make_circuit(args.workload, args.nbits)
+    circ, _ = make_circuit(args.workload, args.nbits, model=args.model)
     o = OracleEngine(circ, get_bundles())
     o.setup()
     o.run_transient(max_steps=3)  # warm-up (imports, first factorisation)
@@ -452,7 +463,7 @@ def cpu_baseline(args, sample_steps: int, threads_note: str = "") -> dict:
     dt = time.perf_counter() - t0
     n = max(st["n_steps"] - 1, 1)
     return {"value": dt * 1e3 / n, "unit": UNIT, "cores": 1, "kind": "port",
-            "host_cores_available": os.cpu_count(),
+            "host_cores_available": os.cpu_count(), "n_unknowns": int(o.n_aug), "csr_nnz": int(len(o.csr_indices)),
             "sample": f"first {n} accepted steps of the same transient (NumPy interpreter + SuperLU, 1 thread){threads_note}"}
 
 
@@ -464,11 +475,11 @@ def run_reference(args, rank, world):
     K, W = args.steps, max(args.warmup, 3)
     sample = min(K, args.cpu_steps)
     cb = cpu_baseline(args, sample_steps=sample)
-    _, desc = make_circuit(args.workload, args.nbits)
+    _, desc = make_circuit(args.workload, args.nbits, model=args.model)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": K,
            "warmup": W, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": desc, "circuit": args.workload},
+           "config": config_dict(args, desc, world, cb.pop("n_unknowns"), cb.pop("csr_nnz")),
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(json.dumps(out))
@@ -486,6 +497,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c6288", choices=["c6288", "mul", "ring"])
     ap.add_argument("--nbits", type=int, default=16)
+    ap.add_argument("--model", default="psp103w", choices=["psp103w", "psp103"],
+                    help="MOSFET model: psp103w = PSP103-weight (default, the headline), psp103 = round-1 light surrogate")
     ap.add_argument("--corners", type=int, default=8,
                     help="PVT corners (whole-circuit replicas) per GPU; 8 per GPU = the 64-point sweep at 8 GPUs; "
                          "corner 0 is the nominal circuit (value_nominal)")

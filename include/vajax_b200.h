@@ -144,6 +144,21 @@ int vjx_nr_solve(vjx_handle* h, const double* X_init_dev, const double* vsrc_dev
                  double* Q_out_dev, double* dQdt_out_dev, double* Ivs_out_dev, double* limit_out_dev,
                  double* maxres_out_dev, vjx_stream stream);
 
+/* Stream-ordered form of vjx_nr_solve for callers that must not block the host (an XLA FFI handler runs inside
+ * XLA's stream; the reference's handler contract is vajax/sparse/umfpack_ffi.cpp:189-338): same operands, the NR
+ * loop runs as a CUDA graph WHILE node on `stream`, and (iterations, converged, max_f, error_flags) are written
+ * to scalars4_out_dev by the device.  Nothing is read back and nothing synchronises, except on the very first
+ * call on a handle (symbolic analysis of the first Jacobian + graph construction).  Inputs are copied into
+ * handle-owned staging buffers, so the caller's buffers may be reused as soon as the call returns in stream
+ * order.  error_flags != 0 (LU watchdog / zero pivot) is the caller's to check. */
+int vjx_nr_solve_async(vjx_handle* h, const double* X_init_dev, const double* vsrc_dev, const double* isrc_dev,
+                       const double* Q_prev_dev, double c0, double gmin, double gshunt, double c1, double d1,
+                       const double* dQdt_prev_dev, double c2, const double* Q_prev2_dev,
+                       const double* limit_in_dev, const double* res_tol_floor_dev, int max_iterations,
+                       double* X_out_dev, double* scalars4_out_dev,
+                       double* Q_out_dev, double* dQdt_out_dev, double* Ivs_out_dev, double* limit_out_dev,
+                       double* maxres_out_dev, vjx_stream stream);
+
 /* ---- Seam S3': device-resident adaptive transient loop (full_mna.py:1840-2194 body_fn,
  * chunked like _run_with_checkpoints :1443-1699).  State lives in the handle. */
 int vjx_tran_begin(vjx_handle* h, const double* X0_dev, const double* Q_init_dev, const double* I0_dev,

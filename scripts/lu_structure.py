@@ -16,8 +16,10 @@ from vajax_b200.benchmarks.circuits import mul64_circuit, multiplier_circuit  # 
 from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
-circ = mul64_circuit(nb) if nb == 64 else multiplier_circuit(nb)
+model = sys.argv[2] if len(sys.argv) > 2 else "psp103w"
+keep_noi = len(sys.argv) > 3 and sys.argv[3] == "keep-noi"   # analyse the unfiltered pattern (what round 1 did)
+bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103", "psp103w")}
+circ = mul64_circuit(nb, mos_model=model) if nb == 64 else multiplier_circuit(nb, mos_model=model)
 t0 = time.time()
 o = OracleEngine(circ, bundles)
 o.setup()
@@ -37,9 +39,16 @@ rows = np.repeat(np.arange(o.n_aug), np.diff(ip))
 noi = np.zeros(o.n_aug, bool)
 if len(o.noi_indices):
     noi[np.asarray(o.noi_indices) - 1] = True
-csr[noi[rows] | ((rows < nu) & noi[ix])] = 0.0
+zero = (noi[rows] | ((rows < nu) & noi[ix])) & ~(noi[rows] & (rows == ix))
+csr[zero] = 0.0
 csr[noi[rows] & (rows == ix)] = 1.0
-np.savez("/tmp/jac_%d.npz" % nb, indptr=ip, indices=ix, data=csr)
+np.savez("/tmp/jac_%s_%d.npz" % (model, nb), indptr=ip, indices=ix, data=csr)
+if not keep_noi:
+    # the slots enforce_noi rewrites to zero are structural zeros for the factorisation (vjx_engine.cu ensure_lu)
+    keep = ~zero
+    ip = np.concatenate([[0], np.cumsum(np.bincount(rows[keep], minlength=o.n_aug))]).astype(np.int32)
+    ix, csr = ix[keep].copy(), csr[keep].copy()
+    print(f"pattern without the NOI-zero slots: {len(ix)} of {len(zero)} entries")
 print(f"jacobian built {time.time()-t0:.1f}s", flush=True)
 lib = vlib.load()
 n = o.n_aug

@@ -15,9 +15,10 @@ from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 
 nbits = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
+model = sys.argv[3] if len(sys.argv) > 3 else "psp103w"
+bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103", "psp103w")}
 t0 = time.perf_counter()
-circ = mul64_circuit(nbits)
+circ = mul64_circuit(nbits, mos_model=model)
 print(f"netlist: {len(circ['devices'])} devices, {circ['num_nodes']} nodes, {time.perf_counter() - t0:.1f}s", flush=True)
 t0 = time.perf_counter()
 e = B200Engine(circ, bundles, use_device_graph=True).prepare()

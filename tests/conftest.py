@@ -16,4 +16,4 @@ def pytest_configure(config):
 def bundles():
     from vajax_b200.models.fixtures import get_bundle
 
-    return {k: get_bundle(k) for k in ["resistor", "capacitor", "diode", "psp103", "opcov"]}
+    return {k: get_bundle(k) for k in ["resistor", "capacitor", "diode", "psp103", "opcov", "psp103w"]}

@@ -67,7 +67,7 @@ from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 ref_models.openvaf_jax = openvaf_jax
 ref_models.HAS_OPENVAF = True
 logging.getLogger("vajax").setLevel(logging.ERROR)
-MODELS = ("resistor", "capacitor", "diode", "psp103", "opcov")
+MODELS = ("resistor", "capacitor", "diode", "psp103", "opcov", "psp103w")
 
 
 # ------------------------------------------------------------------------------------------------

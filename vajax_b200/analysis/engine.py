@@ -404,7 +404,7 @@ class B200Engine:
         # ---- emit + compile the eval kernel for this layout
         layout = emitter.compute_eval_layout(b, shared_idx, varying_idx, shared_cache_idx, varying_cache_idx,
                                              limit_param_map)
-        src, meta = emitter.emit_eval_source(b, layout, self.use_device_limiting)
+        src, meta = emitter.emit_eval_source(b, layout, self.use_device_limiting, n_slices=emitter.default_slices(n_dev))
         use_lim = self.use_device_limiting and not meta.get("limiting_disabled", False)
         plugin = emitter.compile_plugin(src, f"{mt}_eval")
         # ---- node name -> model node index (device independent), then vectorised over instances
@@ -729,8 +729,15 @@ class B200Engine:
     # ---- Seam S3 -----------------------------------------------------------------------
     def nr_solve(self, X_init, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0, integ_c1=0.0,
                  integ_d1=0.0, dQdt_prev=None, integ_c2=0.0, Q_prev2=None, limit_state_in=None, res_tol_floor=None,
-                 max_iterations=None, return_device=False):
+                 max_iterations=None, return_device=False, stream_ordered=False):
+        """``stream_ordered=True`` goes through ``vjx_nr_solve_async`` (what the XLA FFI handler calls): the NR loop
+        is a CUDA-graph WHILE node and the three scalars are written by the device, nothing is read back until
+        this method's own final synchronisation."""
         self.prepare()
+        if stream_ordered:
+            return self._nr_solve_async(X_init, vsource_vals, isource_vals, Q_prev, integ_c0, gmin, gshunt, integ_c1,
+                                        integ_d1, dQdt_prev, integ_c2, Q_prev2, limit_state_in, res_tol_floor,
+                                        max_iterations, return_device)
         torch = self._torch()
         dev = f"cuda:{self.device}"
         z = lambda n: torch.zeros(max(n, 1), dtype=torch.float64, device=dev)  # noqa: E731
@@ -749,6 +756,32 @@ class B200Engine:
             self._p(lim), self._p(mrc), self._sarg()))
         self._sync()
         outs = (X_out[:nx], it.value, bool(cv.value), mf.value, Q[:self.n_unknowns], dQdt[:self.n_unknowns],
+                Ivs[:self.n_vs], lim[:self.total_limit_states], mrc[:self.n_unknowns])
+        if return_device:
+            return outs
+        return tuple(o.cpu().numpy() if hasattr(o, "cpu") else o for o in outs)
+
+    def _nr_solve_async(self, X_init, vsource_vals, isource_vals, Q_prev, integ_c0, gmin, gshunt, integ_c1, integ_d1,
+                        dQdt_prev, integ_c2, Q_prev2, limit_state_in, res_tol_floor, max_iterations, return_device):
+        torch = self._torch()
+        dev = f"cuda:{self.device}"
+        z = lambda n: torch.zeros(max(n, 1), dtype=torch.float64, device=dev)  # noqa: E731
+        nx = self.n_total + self.n_vs
+        X_out, Q, dQdt, Ivs = z(nx), z(self.n_unknowns), z(self.n_unknowns), z(self.n_vs)
+        lim, mrc, sc = z(self.total_limit_states), z(self.n_unknowns), z(4)
+        a = [self._dev(X_init), self._dev(vsource_vals), self._dev(isource_vals), self._dev(Q_prev),
+             self._dev(dQdt_prev), self._dev(Q_prev2), self._dev(limit_state_in), self._dev(res_tol_floor)]
+        vlib.check(vlib.load().vjx_nr_solve_async(
+            self.handle, self._p(a[0]), self._p(a[1]) if self.n_vs else None, self._p(a[2]) if self.n_is else None,
+            self._p(a[3]), float(integ_c0), float(gmin), float(gshunt), float(integ_c1), float(integ_d1), self._p(a[4]),
+            float(integ_c2), self._p(a[5]), self._p(a[6]), self._p(a[7]),
+            -1 if max_iterations is None else int(max_iterations),
+            self._p(X_out), self._p(sc), self._p(Q), self._p(dQdt), self._p(Ivs), self._p(lim), self._p(mrc), self._sarg()))
+        self._sync()
+        sch = sc.cpu().numpy()
+        if int(sch[3]) & (1 | 4 | 8):
+            raise vlib.VjxError(f"nr_solve (stream-ordered): device error flags {int(sch[3])}")
+        outs = (X_out[:nx], int(sch[0]), bool(sch[1]), float(sch[2]), Q[:self.n_unknowns], dQdt[:self.n_unknowns],
                 Ivs[:self.n_vs], lim[:self.total_limit_states], mrc[:self.n_unknowns])
         if return_device:
             return outs

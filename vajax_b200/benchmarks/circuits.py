@@ -25,10 +25,20 @@ PMOS_CARD = dict(type=-1.0, vto=0.35, kp=1.2e-4, nfac=1.35, theta=0.15, gamma=0.
                  cgso=3e-10, cgdo=3e-10, cgbo=1e-11, js=1e-6, cj=1e-3, cjsw=1e-10, tcv=1e-3, tnom=27.0)
 
 
+# psp103w (models/psp103w.py): the two model cards of the reference's benchmarks differ in TYPE only
+# (vajax/benchmarks/data/mul64/runme.sim model psp103n / psp103p); everything else is the model default
+# the knobs of the process corners (analysis/corners.py) are spelled out so that a corner has something to scale
+NMOS_CARD_W = dict(type=1.0, uoo=3.5e-2, vfbo=-0.70, toxo=1.5e-9)
+PMOS_CARD_W = dict(type=-1.0, uoo=1.75e-2, vfbo=-0.70, toxo=1.5e-9)
+MOS_MODELS = ("psp103", "psp103w")
+
+
 class _Net:
-    def __init__(self):
+    def __init__(self, mos_model: str = "psp103"):
+        assert mos_model in MOS_MODELS, mos_model
         self.names: Dict[str, int] = {"0": 0}
         self.devices: List[dict] = []
+        self.mos_model = mos_model
 
     def node(self, name: str) -> int:
         if name not in self.names:
@@ -40,14 +50,17 @@ class _Net:
                                  params=dict(params), is_openvaf=openvaf))
 
     def mos(self, name, kind, d, g, s, b, w, l, ld=0.5e-6):
-        card = NMOS_CARD if kind == "n" else PMOS_CARD
+        if self.mos_model == "psp103w":
+            card = NMOS_CARD_W if kind == "n" else PMOS_CARD_W
+        else:
+            card = NMOS_CARD if kind == "n" else PMOS_CARD
         p = dict(card)
         p.update(w=w, l=l)
         p["as"] = w * ld
         p["ad"] = w * ld
         p["ps"] = 2 * (w + ld)
         p["pd"] = 2 * (w + ld)
-        self.add(name, "psp103", [d, g, s, b], p)
+        self.add(name, self.mos_model, [d, g, s, b], p)
 
     def renumber_sorted(self):
         """Node indices by sorted node name, ground = 0 (reference: build_node_mapping,
@@ -121,8 +134,9 @@ def source_mix_circuit(stop: float = 6e-8, method: str = "trap") -> dict:
 
 
 def ring_circuit(stages: int = 9, stop: float = 20e-9, step: float = 0.05e-9, w: float = 10e-6,
-                 l: float = 1e-6, pfact: float = 2.0, vdd: float = 1.2, method: str = "trap") -> dict:
-    n = _Net()
+                 l: float = 1e-6, pfact: float = 2.0, vdd: float = 1.2, method: str = "trap",
+                 mos_model: str = "psp103") -> dict:
+    n = _Net(mos_model)
     for k in range(1, stages + 1):
         n.node(str(k))
     n.node("vdd")
@@ -139,14 +153,14 @@ def ring_circuit(stages: int = 9, stop: float = 20e-9, step: float = 0.05e-9, w:
 
 def multiplier_circuit(nbits: int = 16, stop: float = 2e-9, step: float = 2e-12, vdd: float = 1.2,
                        a_val: Optional[int] = None, b_val: Optional[int] = None,
-                       wn: float = 0.5e-6, wp: float = 1e-6, l: float = 0.2e-6) -> dict:
+                       wn: float = 0.5e-6, wp: float = 1e-6, l: float = 0.2e-6, mos_model: str = "psp103") -> dict:
     """n x n unsigned carry-save array multiplier, all-ones operands by default (mul64's stimulus),
     ``icmode=uic tran_lteratio=1.5 nr_convtol=1`` as in the c6288/mul64 control blocks
     (docs/transient_options.md:158-163)."""
     N = nbits
     a_val = (1 << N) - 1 if a_val is None else a_val
     b_val = (1 << N) - 1 if b_val is None else b_val
-    net = _Net()
+    net = _Net(mos_model)
     net.node("vdd")
     net.node("vss")
     net.add("vdd", "vsource", ["vdd", "0"], dict(dc=vdd, type="dc"), openvaf=False)
@@ -238,7 +252,7 @@ def multiplier_circuit(nbits: int = 16, stop: float = 2e-9, step: float = 2e-12,
 
 
 def mul64_circuit(nbits: int = 64, stop: float = 2e-9, step: float = 2e-12, vdd: float = 1.2,
-                  wn: float = 0.5e-6, wp: float = 1e-6, l: float = 0.2e-6) -> dict:
+                  wn: float = 0.5e-6, wp: float = 1e-6, l: float = 0.2e-6, mos_model: str = "psp103") -> dict:
     """The reference's mul64 benchmark (vajax/benchmarks/data/mul64/runme.sim), flattened.
 
     Gate library of the netlist's generate block (:23-59): not = 2 T, nor = 4 T, and = 6 T
@@ -254,7 +268,7 @@ def mul64_circuit(nbits: int = 64, stop: float = 2e-9, step: float = 2e-12, vdd:
     and its node numbering (sorted names, parsing.py:146-168); tests/golden/mul64_topology.json holds
     the digest of the reference parser's own result for n=64."""
     N = nbits
-    net = _Net()
+    net = _Net(mos_model)
     net.node("vdd")
     net.node("vss")
     net.add("vdd", "vsource", ["vdd", "0"], dict(dc=vdd, type="dc"), openvaf=False)

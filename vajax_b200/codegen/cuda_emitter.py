@@ -450,6 +450,87 @@ def _mir_var(ref: str) -> str:
     return ref or ""
 
 
+# ---- output slicing -------------------------------------------------------------------------------
+# One thread per instance walks the whole MIR: a serial chain of ~4e4 SASS instructions for a PSP103-weight model,
+# so a c6288-sized circuit (10 k instances = 0.5 warps per scheduler) is bound by that chain's latency.  The chain
+# is the value path plus one derivative path per Jacobian column; the columns are independent of each other.
+# With K slices the same body is instantiated K times (template parameter), slice k stores only its own group
+# of outputs and the compiler's dead-code elimination removes what the group does not need.  blockIdx.y picks the
+# slice (uniform per CTA), so K x more warps each walk a shorter chain.  Every output is still computed by exactly
+# the same sequence of fp64 operations (no contraction, no reassociation): results are bit-identical for any K.
+SLICE_WEIGHT = {"fdiv": 20, "exp": 60, "ln": 60, "log": 60, "sqrt": 25, "pow": 150, "sin": 60, "cos": 60, "tan": 80,
+                "sinh": 80, "cosh": 80, "tanh": 80, "atan": 60, "atan2": 80, "hypot": 40, "asin": 80, "acos": 80,
+                "asinh": 80, "acosh": 80, "atanh": 80, "clog2": 60, "call": 40}
+
+
+SLICE_MIN_COST = 3000   # weighted instruction count below which a model is never sliced
+
+
+def plan_slices(fn: Function, dae: dict, n_slices: int) -> List[dict]:
+    """Group the outputs (Jacobian entries by column node; all residuals together) into ``n_slices`` groups with a
+    small maximum backward-slice cost.  Returns [{"jac": [entry ids], "res": bool, "cost": int}]."""
+    R, J = len(dae["residuals"]), len(dae["jacobian"])
+    if n_slices <= 1:
+        return [{"jac": list(range(J)), "res": True, "cost": 0}]
+    defs: Dict[str, Inst] = {}
+    for insts in fn.blocks.values():
+        for ins in insts:
+            if ins.result:
+                defs[ins.result] = ins
+
+    def back(vars_) -> set:
+        seen, st = set(), [v for v in vars_ if v in defs]
+        while st:
+            v = st.pop()
+            if v in seen:
+                continue
+            seen.add(v)
+            ins = defs[v]
+            for o in list(ins.operands) + [x for _, x in ins.phi]:
+                if o in defs and o not in seen:
+                    st.append(o)
+        return seen
+
+    def cost(sl: set) -> int:
+        return sum(SLICE_WEIGHT.get(defs[v].opcode, 1) for v in sl)
+
+    if cost(set(defs)) < SLICE_MIN_COST:   # a resistor / diode is not worth K x the CTAs
+        return [{"jac": list(range(J)), "res": True, "cost": cost(set(defs))}]
+    ctrl = back([ins.cond for insts in fn.blocks.values() for ins in insts if ins.opcode == "br" and ins.cond])
+    items = []   # (set, jac ids, is_res)
+    res_vars = [_mir_var(r[k]) for r in dae["residuals"] for k in ("resist_var", "react_var")]
+    items.append((back(res_vars) | ctrl, [], True))
+    cols: Dict[str, List[int]] = {}
+    for j, e in enumerate(dae["jacobian"]):
+        cols.setdefault(e["col_node_name"], []).append(j)
+    for _c, js in cols.items():
+        vs = [_mir_var(dae["jacobian"][j][k]) for j in js for k in ("resist_var", "react_var")]
+        items.append((back(vs) | ctrl, js, False))
+    items.sort(key=lambda it: -cost(it[0]))
+    K = min(n_slices, len(items))
+    bins = [{"set": set(), "jac": [], "res": False} for _ in range(K)]
+    for sl, js, is_res in items:
+        # the bin whose cost after taking this item is smallest
+        best = min(range(K), key=lambda b: cost(bins[b]["set"] | sl))
+        bins[best]["set"] |= sl
+        bins[best]["jac"].extend(js)
+        bins[best]["res"] = bins[best]["res"] or is_res
+    out = [{"jac": sorted(b["jac"]), "res": b["res"], "cost": cost(b["set"])} for b in bins if b["jac"] or b["res"]]
+    assert sorted(j for b in out for j in b["jac"]) == list(range(J)) and sum(1 for b in out if b["res"]) == 1
+    return out
+
+
+def default_slices(n_dev: int) -> int:
+    """Slices for a model with ``n_dev`` instances: enough to give every SM sub-partition of a B200 (148 x 4) a few
+    warps, none when the instance count alone fills the machine.  VJX_EVAL_SLICES overrides."""
+    env = os.environ.get("VJX_EVAL_SLICES")
+    if env:
+        return max(1, int(env))
+    warps = max(1, (n_dev + 31) // 32)
+    return int(max(1, min(6, (4 * 592) // warps)))
+
+
+
 def compute_eval_layout(bundle: dict, shared_indices, varying_indices, shared_cache_indices,
                         varying_cache_indices, limit_param_map=None) -> dict:
     """Build the emitter's parameter-source tables from the host-side split
@@ -483,7 +564,7 @@ def compute_eval_layout(bundle: dict, shared_indices, varying_indices, shared_ca
     }
 
 
-def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = False) -> Tuple[str, dict]:
+def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = False, n_slices: int = 1) -> Tuple[str, dict]:
     fn = parse_function("eval", bundle["mir_data"], bundle.get("str_constants"))
     dae = bundle["dae_data"]
     param_idx_to_val = {p[0]: f"v{p[1]}" for p in bundle["all_func_params"]}
@@ -589,22 +670,28 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
     if use_limit_functions and n_lim > 0 and not body.limit_raw:
         # inline limiting without BuiltinLimit: the reference disables limiting for the model
         # (openvaf_models.py:972-990) - signal it to the caller.
-        src2, meta2 = emit_eval_source(bundle, layout, use_limit_functions=False)
+        src2, meta2 = emit_eval_source(bundle, layout, use_limit_functions=False, n_slices=n_slices)
         meta2["limiting_disabled"] = True
         return src2, meta2
 
+    slices = plan_slices(fn, dae, n_slices)
+    K = len(slices)
     tail.append("const double c0 = a.ctl[VJX_CTL_C0];")
-    for e in range(J):
-        tail.append(
-            f"{{ int p = a.jdest[(size_t){e} * n + d]; if (p >= 0) a.jsorted[p] = vjx_nan0({jac_r[e]} + c0 * {jac_q[e]}); }}")
-    for r in range(R):
-        tail.append(
-            f"{{ int p = a.vdest[(size_t){r} * n + d]; if (p >= 0) {{ double2* q = reinterpret_cast<double2*>(a.vsorted + (size_t)p * 4); "
-            f"q[0] = make_double2(vjx_nan0({res_r[r]}), vjx_nan0({res_q[r]})); q[1] = make_double2(vjx_nan0({lim_r[r]}), vjx_nan0({lim_q[r]})); }} }}")
-    for li in range(n_lim):
-        if li not in body.limit_store:
-            raise ValueError(f"Limit state {li} was registered (LoadLimit) but no StoreLimit found.")
-        tail.append(f"if (a.limit_out) a.limit_out[(size_t)d * NLIM + {li}] = {body.as_f(body.limit_store[li])};")
+    for k, sl in enumerate(slices):
+        tail.append(f"if constexpr (S < 0 || S == {k}) {{")
+        for e in sl["jac"]:
+            tail.append(
+                f"  {{ int p = a.jdest[(size_t){e} * n + d]; if (p >= 0) a.jsorted[p] = vjx_nan0({jac_r[e]} + c0 * {jac_q[e]}); }}")
+        if sl["res"]:
+            for r in range(R):
+                tail.append(
+                    f"  {{ int p = a.vdest[(size_t){r} * n + d]; if (p >= 0) {{ double2* q = reinterpret_cast<double2*>(a.vsorted + (size_t)p * 4); "
+                    f"q[0] = make_double2(vjx_nan0({res_r[r]}), vjx_nan0({res_q[r]})); q[1] = make_double2(vjx_nan0({lim_r[r]}), vjx_nan0({lim_q[r]})); }} }}")
+            for li in range(n_lim):
+                if li not in body.limit_store:
+                    raise ValueError(f"Limit state {li} was registered (LoadLimit) but no StoreLimit found.")
+                tail.append(f"  if (a.limit_out) a.limit_out[(size_t)d * NLIM + {li}] = {body.as_f(body.limit_store[li])};")
+        tail.append("}")
 
     # ---- simparams prologue
     sp_lines = []
@@ -625,20 +712,33 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
     src.append(f"#define NLIM {max(1, n_lim)}")
     src.append(f"struct VjxConst {{ double shared[{ns}]; double shared_cache[{nsc}]; double simparam_defaults[{nsp}]; }};")
     src.append("__constant__ VjxConst C;")
-    src.append("extern \"C\" __global__ void __launch_bounds__(128) vjx_eval_kernel(VjxEvalArgs a) {")
-    src.append("  const int d = blockIdx.x * blockDim.x + threadIdx.x;")
-    src.append("  const int n = a.n_dev;")
-    src.append("  if (d >= n) return;")
+    # the body once, as a template: S < 0 stores every output, S = k only the outputs of slice k
+    src.append("template <int S> __device__ __forceinline__ void vjx_eval_body(const VjxEvalArgs& a, const int d, const int n) {")
     src.extend("  " + s for s in body.decls())
     src.extend("  " + s for s in sp_lines)
     src.extend("  " + s for s in head)
     src.extend("  " + s for s in code)
     src.extend("  " + s for s in tail)
     src.append("}")
+    tb = int(os.environ.get("VJX_EVAL_BLOCK", "128"))
+    minb = os.environ.get("VJX_EVAL_MINBLOCKS")
+    lb = f"__launch_bounds__({tb}, {int(minb)})" if minb else f"__launch_bounds__({tb})"
+    src.append(f"extern \"C\" __global__ void {lb} vjx_eval_kernel(VjxEvalArgs a) {{")
+    src.append("  const int d = blockIdx.x * blockDim.x + threadIdx.x;")
+    src.append("  const int n = a.n_dev;")
+    src.append("  if (d >= n) return;")
+    if K == 1:
+        src.append("  vjx_eval_body<-1>(a, d, n);")
+    else:
+        src.append("  switch (blockIdx.y) {")
+        for k in range(K):
+            src.append(f"    case {k}: vjx_eval_body<{k}>(a, d, n); break;")
+        src.append("  }")
+    src.append("}")
     src.append(f"""
 extern "C" int vjx_model_eval(const VjxEvalArgs* a, cudaStream_t s) {{
   if (a->n_dev <= 0) return 0;
-  vjx_eval_kernel<<<(a->n_dev + 127) / 128, 128, 0, s>>>(*a);
+  vjx_eval_kernel<<<dim3((a->n_dev + {tb - 1}) / {tb}, {K}), {tb}, 0, s>>>(*a);
   return (int)cudaGetLastError();
 }}
 extern "C" int vjx_model_set_const(const double* sh, int ns, const double* sc, int nsc,
@@ -661,6 +761,7 @@ extern "C" int vjx_model_abi_version() {{ return 1; }}
         "limit_metadata": {"limit_count": n_lim, "raw_operands": dict(body.limit_raw),
                            "store_operands": dict(body.limit_store), "limited_branches": limited},
         "flops_static": dict(body.flops),
+        "n_slices": K, "slice_costs": [sl["cost"] for sl in slices],
         "warnings": list(body.warnings),
         "use_limit_functions": bool(use_limit_functions),
         "node_names": [r["node_name"] for r in dae["residuals"]],

@@ -1675,6 +1675,8 @@ struct vjx_handle {
   int n_total = 0, n_unknowns = 0, n_ext = 0, n_vs = 0, n_is = 0, n_aug = 0, nse = 0, total_lim = 0;
   vjx_options o{};
   std::vector<int> h_indptr, h_indices;
+  long long lu_nnz_a = 0;                    // entries of A the factorisation reads (CSR slots minus structural zeros)
+  std::vector<unsigned char> h_slot_flags;   // host copy: SLOT_NOI_ZERO slots are structural zeros for the LU
   std::vector<ModelState*> models;
   // stamping tables
   DevBuf<int> jseg, vseg, isrc_dest, att_ptr, att_idx, vs_p, vs_n;
@@ -1718,6 +1720,8 @@ struct vjx_handle {
   cudaGraphExec_t g_iter = nullptr;    // one NR iteration
   cudaGraphExec_t g_final = nullptr;   // final build + dQdt
   cudaGraphExec_t g_step_pre = nullptr, g_step_post = nullptr;
+  cudaGraphExec_t g_nrs = nullptr;     // stand-alone NR loop (WHILE node) of vjx_nr_solve_async, on staging buffers
+  DevBuf<double> nrs_X, nrs_in;        // staging: X | vsrc, isrc, Q_prev, dQdt_prev, Q_prev2, res_tol_floor
   cudaGraphExec_t g_tran = nullptr;    // whole device-resident loop (WHILE nodes)
   int g_tran_limit = 0;
   cudaStream_t own_stream = nullptr;
@@ -1740,6 +1744,7 @@ vjx_handle::~vjx_handle() {
   if (g_final) cudaGraphExecDestroy(g_final);
   if (g_step_pre) cudaGraphExecDestroy(g_step_pre);
   if (g_step_post) cudaGraphExecDestroy(g_step_post);
+  if (g_nrs) cudaGraphExecDestroy(g_nrs);
   if (g_tran) cudaGraphExecDestroy(g_tran);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -1999,6 +2004,7 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
         if (r < nu && noi_row[c]) flags[p] |= SLOT_NOI_ZERO;
         if (noi_row[r] && c == r) flags[p] |= SLOT_NOI_ONE;
       }
+  h->h_slot_flags = flags;
   CK(h->slot_flags.upload(flags));
   CK(h->slot_const.upload(cst));
   CK(h->is_noi.upload(is_noi));
@@ -2488,7 +2494,35 @@ static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s) {
   int dense_cap = VJX_DT_MAX;
   if (getenv("VJX_DT_ROWS")) dense_cap = std::min(VJX_DT_MAX, atoi(getenv("VJX_DT_ROWS")));
   if (getenv("VJX_NO_DENSE_TAIL")) dense_cap = 0;
-  int rc = vjx_symbolic_analyze(h->n_aug, h->h_indptr.data(), h->h_indices.data(), vals.data(), tol, true, h->sym, err, dense_cap);
+  // The linear solve only ever sees the NOI-enforced matrix (solver_factories.py:1268-1276 precedes every
+  // linear_solve): the slots that enforce_noi rewrites to zero are STRUCTURAL zeros.  Leaving them in the
+  // pattern would keep every noise node of every MOSFET (a row reaching D G S B, a column reaching G S D) out
+  // of the singleton peel and in the core of the factorisation.  The analysis runs on the filtered pattern;
+  // lu_src is mapped back to the slots of the full CSR afterwards.
+  bool filtered = false;
+  for (unsigned char f : h->h_slot_flags) if ((f & SLOT_NOI_ZERO) && !(f & SLOT_NOI_ONE)) { filtered = true; break; }
+  if (getenv("VJX_LU_KEEP_NOI_SLOTS")) filtered = false;
+  int rc;
+  if (filtered) {
+    std::vector<int> f_indptr(h->n_aug + 1, 0), f_indices, f_slot;
+    std::vector<double> f_vals;
+    f_indices.reserve(h->nse); f_slot.reserve(h->nse); f_vals.reserve(h->nse);
+    for (int r = 0; r < h->n_aug; ++r) {
+      for (int p = h->h_indptr[r]; p < h->h_indptr[r + 1]; ++p) {
+        const unsigned char f = h->h_slot_flags[p];
+        if ((f & SLOT_NOI_ZERO) && !(f & SLOT_NOI_ONE)) continue;
+        f_indices.push_back(h->h_indices[p]); f_slot.push_back(p); f_vals.push_back(vals[p]);
+      }
+      f_indptr[r + 1] = (int)f_indices.size();
+    }
+    rc = vjx_symbolic_analyze(h->n_aug, f_indptr.data(), f_indices.data(), f_vals.data(), tol, true, h->sym, err, dense_cap);
+    if (rc == 0)
+      for (int& src : h->sym.lu_src) if (src >= 0) src = f_slot[src];
+    h->lu_nnz_a = (long long)f_indices.size();
+  } else {
+    rc = vjx_symbolic_analyze(h->n_aug, h->h_indptr.data(), h->h_indices.data(), vals.data(), tol, true, h->sym, err, dense_cap);
+    h->lu_nnz_a = h->nse;
+  }
   if (rc != 0) return fail(VJX_ERR_SINGULAR, "LU analysis failed: " + err);
   return upload_symbolic(h);
 }
@@ -2498,6 +2532,7 @@ extern "C" int vjx_lu_analyze(vjx_handle* h, const double* csr_data_dev, vjx_str
   CK(cudaSetDevice(h->device));
   h->lu_ready = false;
   if (h->g_iter) { cudaGraphExecDestroy(h->g_iter); h->g_iter = nullptr; }
+  if (h->g_nrs) { cudaGraphExecDestroy(h->g_nrs); h->g_nrs = nullptr; }
   if (h->g_tran) { cudaGraphExecDestroy(h->g_tran); h->g_tran = nullptr; }
   return ensure_lu(h, csr_data_dev, (cudaStream_t)stream);
 }
@@ -2639,6 +2674,130 @@ extern "C" int vjx_nr_solve(vjx_handle* h, const double* X_init, const double* v
   if (iterations) *iterations = hs->iter;
   if (converged) *converged = hs->converged;
   if (max_f) { double mfv = INFINITY; if (max_iterations > 0) memcpy(&mfv, &hs->max_f_bits, sizeof(double)); *max_f = mfv; }
+  CK(cudaGetLastError());
+  return VJX_OK;
+}
+
+
+// ---- stream-ordered nr_solve (the form an XLA FFI handler needs: no host read, no synchronisation) ----------
+__global__ void k_nr_scalars(const NRStat* st, int max_iterations, double* out4) {
+  out4[0] = (double)st->iter;
+  out4[1] = (double)st->converged;
+  out4[2] = max_iterations > 0 ? __longlong_as_double((long long)st->max_f_bits) : INFINITY;
+  out4[3] = (double)st->error;
+}
+
+struct NrsLayout { double *vsrc, *isrc, *Q_prev, *dQdt_prev, *Q_prev2, *rtf; };
+static NrsLayout nrs_layout(vjx_handle* h) {
+  const size_t nu = std::max(h->n_unknowns, 1), nv = std::max(h->n_vs, 1), ni = std::max(h->n_is, 1);
+  NrsLayout L;
+  double* p = h->nrs_in.p;
+  L.vsrc = p; p += nv; L.isrc = p; p += ni; L.Q_prev = p; p += nu; L.dQdt_prev = p; p += nu; L.Q_prev2 = p; p += nu; L.rtf = p;
+  return L;
+}
+
+static int build_nrs_graph(vjx_handle* h) {
+  cudaGraph_t g;
+  CK(cudaGraphCreate(&g, 0));
+  cudaGraphConditionalHandle h_nr;
+  CK(cudaGraphConditionalHandleCreate(&h_nr, g, 1, cudaGraphCondAssignDefault));
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = h_nr;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t nr_node;
+  CK(cudaGraphAddNode(&nr_node, g, nullptr, 0, &np));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  NrsLayout L = nrs_layout(h);
+  BuildPtrs b{};
+  fill_build_ptrs_nr(h, b, h->nrs_X.p, L.vsrc, L.isrc, L.Q_prev, L.dQdt_prev, L.Q_prev2, L.rtf);
+  cudaStream_t cs = h->own_stream;
+  long long launches_before = h->launches;
+  CK(cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  int rc = launch_nr_iteration(h, b, h->nrs_X.p, h_nr, 1, cs);
+  cudaGraph_t tmp;
+  CK(cudaStreamEndCapture(cs, &tmp));
+  h->launches = launches_before;
+  if (rc) return rc;
+  CK(cudaGraphInstantiate(&h->g_nrs, g, 0));
+  CK(cudaGraphDestroy(g));
+  return VJX_OK;
+}
+
+extern "C" int vjx_nr_solve_async(vjx_handle* h, const double* X_init, const double* vsrc, const double* isrc,
+                                  const double* Q_prev, double c0, double gmin, double gshunt, double c1, double d1,
+                                  const double* dQdt_prev, double c2, const double* Q_prev2, const double* limit_in,
+                                  const double* res_tol_floor, int max_iterations, double* X_out, double* scalars4_out,
+                                  double* Q_out, double* dQdt_out, double* Ivs_out, double* limit_out, double* maxres_out,
+                                  vjx_stream stream) {
+  if (!h || !X_init || !X_out || !Q_prev || !scalars4_out) return fail(VJX_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, stream);
+  const int nx = h->n_total + h->n_vs, nu = h->n_unknowns;
+  if (max_iterations < 0) max_iterations = h->o.tran_itl;
+  if (!h->nrs_X.p) {
+    CK(h->nrs_X.alloc(nx));
+    CK(h->nrs_in.alloc((size_t)std::max(h->n_vs, 1) + std::max(h->n_is, 1) + 4 * (size_t)std::max(nu, 1)));
+  }
+  NrsLayout L = nrs_layout(h);
+  k_set_ctl<<<1, 1, 0, s>>>(h->ctl.p, c0, c1, d1, c2, gmin, gshunt, 0.0, h->o.gmin);
+  k_copy<<<grid_for(h, nx), 256, 0, s>>>(nx, X_init, h->nrs_X.p);
+  auto stage = [&](const double* src, double* dst, int n, double dflt) {
+    if (n <= 0) return;
+    if (src) k_copy<<<grid_for(h, n), 256, 0, s>>>(n, src, dst);
+    else k_fill<<<grid_for(h, n), 256, 0, s>>>(n, dflt, dst);
+    h->launches++;
+  };
+  stage(vsrc, L.vsrc, h->n_vs, 0.0);
+  stage(isrc, L.isrc, h->n_is, 0.0);
+  stage(Q_prev, L.Q_prev, nu, 0.0);
+  stage(dQdt_prev, L.dQdt_prev, nu, 0.0);
+  stage(Q_prev2, L.Q_prev2, nu, 0.0);
+  stage(res_tol_floor, L.rtf, nu, h->o.abstol);
+  if (h->total_lim > 0) stage(limit_in, h->limit_w.p, h->total_lim, 0.0);
+  h->launches += 2;
+  BuildPtrs b{};
+  fill_build_ptrs_nr(h, b, h->nrs_X.p, L.vsrc, L.isrc, L.Q_prev, L.dQdt_prev, L.Q_prev2, L.rtf);
+  k_nr_begin<<<1, 1, 0, s>>>(h->st.p, h->ctl.p, max_iterations, 1);
+  h->launches++;
+  if (!h->lu_ready) {
+    // one-time set-up of the handle (symbolic analysis on the first Jacobian): this call, and only this one,
+    // synchronises the stream
+    k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
+    int rc = launch_eval(h, b, s);
+    if (rc) return rc;
+    launch_stamp(h, h->csr.p, 1, s);
+    rc = ensure_lu(h, h->csr.p, s);
+    if (rc) return rc;
+  }
+  if (max_iterations > 0) {
+    if (!h->g_nrs) {
+      CK(cudaStreamSynchronize(s));   // graph construction captures on the handle's own stream (one-time)
+      int rc = build_nrs_graph(h);
+      if (rc) return rc;
+    }
+    CK(cudaGraphLaunch(h->g_nrs, s));
+  }
+  // final build at X_final for Q, I_vsource, max_res_contrib (solver_factories.py:689-713)
+  BuildPtrs bf = b;
+  bf.csr = nullptr; bf.f = h->f.p; bf.Q = Q_out ? Q_out : h->Qw.p; bf.Ivs = Ivs_out ? Ivs_out : h->Ivs.p;
+  bf.maxres = maxres_out ? maxres_out : h->maxres_w.p;
+  bf.limit_out = h->limit_out.p;
+  int rc = launch_eval(h, bf, s);
+  if (rc) return rc;
+  launch_residual(h, bf, 0, s);
+  if (dQdt_out) {
+    k_dqdt<<<grid_for(h, nu), 256, 0, s>>>(nu, h->ctl.p, bf.Q, L.Q_prev, L.dQdt_prev, L.Q_prev2, dQdt_out);
+    h->launches++;
+  }
+  if (limit_out && h->total_lim > 0) {
+    k_copy<<<grid_for(h, h->total_lim), 256, 0, s>>>(h->total_lim, h->limit_w.p, limit_out);
+    h->launches++;
+  }
+  k_copy<<<grid_for(h, nx), 256, 0, s>>>(nx, h->nrs_X.p, X_out);
+  k_nr_scalars<<<1, 1, 0, s>>>(h->st.p, max_iterations, scalars4_out);
+  h->launches += 2;
   CK(cudaGetLastError());
   return VJX_OK;
 }

@@ -421,7 +421,14 @@ def mos_psp_shaped_bundle(name: str = "psp103") -> dict:
     return m.finalize()
 
 
+def _psp103w_bundle() -> dict:
+    from .psp103w import psp103w_bundle
+
+    return psp103w_bundle()
+
+
 _BUILDERS = {
+    "psp103w": _psp103w_bundle,
     "resistor": resistor_bundle,
     "capacitor": capacitor_bundle,
     "diode": diode_bundle,
