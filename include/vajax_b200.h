@@ -164,6 +164,10 @@ int vjx_nr_solve_async(vjx_handle* h, const double* X_init_dev, const double* vs
 int vjx_tran_begin(vjx_handle* h, const double* X0_dev, const double* Q_init_dev, const double* I0_dev,
                    const double* hist_maxres_dev, double t_stop, double dt, double max_dt, int max_steps,
                    vjx_stream stream);
+/* N4: device-side save list (netlist `save v(p0) ...`, vajax/benchmarks/data/mul64/runme.sim:296-308; the
+ * reference records all external nodes, full_mna.py:1017-1023,2122).  node_idx_host[k] = index into X of V_out
+ * column k; n_save = 0 = every external node.  Call before vjx_tran_begin. */
+int vjx_tran_set_save_list(vjx_handle* h, const int* node_idx_host, int n_save);
 /* Run until t >= t_stop, step_idx >= max_steps, or `max_attempts` step attempts were made.
  * Returns the number of attempts made in *attempts. */
 int vjx_tran_run(vjx_handle* h, int max_attempts, int* attempts, vjx_stream stream);

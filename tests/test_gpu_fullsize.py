@@ -79,6 +79,31 @@ def test_c6288_graph_equals_host_loop_and_chunks(c6288, bundles):
     assert np.all(np.isfinite(V1[:41])) and V1[:41].min() > -0.6 and V1[:41].max() < 1.8
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_save_list_filters_the_output_rows_on_the_device(bundles, graph):
+    """N4: with a save list V_out holds one column per listed node, bit-identical to the same columns of the full
+    record (reference: full record full_mna.py:1017-1023,2122; `save` lines runme.sim:296-308); None restores it."""
+    from vajax_b200.analysis.engine import B200Engine
+
+    circ = circuits.multiplier_circuit(4, stop=3e-10, step=2e-12, mos_model="psp103w")
+    e = B200Engine(circ, bundles, use_device_graph=graph).prepare()
+    t0, V0, s0 = e.run_transient()
+    n = s0["n_steps"]
+    assert V0.shape[1] == e.n_external
+    names = [f"p{k}" for k in range(4, 8)] + ["vdd", "a0", "0"]
+    e.set_save_list(names)
+    t1, V1, s1 = e.run_transient()
+    assert s1["n_steps"] == n and np.array_equal(t0, t1) and V1.shape[1] == len(names)
+    for k, nm in enumerate(names):
+        assert s1["node_indices"].get(nm, k) == k or nm == "0"
+        assert np.array_equal(V1[:n, k], V0[:n, e.node_names[nm]]), nm
+    assert e._tran["d2h_bytes"] < 0.2 * 8 * V0.shape[0] * V0.shape[1]
+    e.set_save_list(None)
+    t2, V2, s2 = e.run_transient()
+    assert np.array_equal(V2, V0) and np.array_equal(t2, t0)
+    e.close()
+
+
 def test_mul4_settles_to_the_product(bundles):
     """4x4 multiplier, operands 15 x 15 = 225: after the inputs have risen and the array has
     settled, the product bits read 0b11100001."""

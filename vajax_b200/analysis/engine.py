@@ -404,7 +404,8 @@ class B200Engine:
         # ---- emit + compile the eval kernel for this layout
         layout = emitter.compute_eval_layout(b, shared_idx, varying_idx, shared_cache_idx, varying_cache_idx,
                                              limit_param_map)
-        src, meta = emitter.emit_eval_source(b, layout, self.use_device_limiting, n_slices=emitter.default_slices(n_dev))
+        src, meta = emitter.emit_eval_source(b, layout, self.use_device_limiting, n_slices=emitter.default_slices(n_dev),
+                                              min_blocks=emitter.default_min_blocks(n_dev))
         use_lim = self.use_device_limiting and not meta.get("limiting_disabled", False)
         plugin = emitter.compile_plugin(src, f"{mt}_eval")
         # ---- node name -> model node index (device independent), then vectorised over instances
@@ -876,18 +877,38 @@ class B200Engine:
                 "consecutive_rejects", "attempts", "error_flags"]
         return {k: (float(v) if k in ("t", "dt", "min_dt_used", "max_dt_used") else int(v)) for k, v in zip(keys, sc)}
 
+    def set_save_list(self, nodes=None):
+        """N4: record only these nodes (names or indices; the netlist's ``save v(...)`` lines, reference:
+        vajax/benchmarks/data/mul64/runme.sim:296-308) instead of every external node (full_mna.py:1017-1023).
+        ``None`` restores the reference behaviour.  Takes effect at the next ``tran_begin``."""
+        self.prepare()
+        if nodes is None:
+            idx = np.zeros(0, dtype=np.int32)
+        else:
+            idx = np.array([self.node_names[n] if isinstance(n, str) else int(n) for n in nodes], dtype=np.int32)
+            if len(idx) == 0:
+                raise ValueError("empty save list (use None for all external nodes)")
+        vlib.check(vlib.load().vjx_tran_set_save_list(self.handle, idx.ctypes.data_as(C.c_void_p), len(idx)))
+        self._save_idx = idx if len(idx) else None
+
+    @property
+    def n_out(self) -> int:
+        """Columns of V_out."""
+        si = getattr(self, "_save_idx", None)
+        return self.n_external if si is None else len(si)
+
     def tran_read(self, rows: Optional[int] = None):
         """Device -> host copy of the recorded outputs (times, V_out, I_out)."""
         max_steps = self._tran["max_steps"]
         rows = max_steps if rows is None else min(int(rows), max_steps)
         nvs = self.n_vs
         times = np.zeros(max_steps)
-        V_out = np.zeros((max_steps, self.n_external))
+        V_out = np.zeros((max_steps, self.n_out))
         I_out = np.zeros((max_steps, max(nvs, 1)))
         if rows > 0:
             vlib.check(vlib.load().vjx_tran_read(self.handle, 0, rows, times.ctypes.data_as(C.c_void_p),
                                                  V_out.ctypes.data_as(C.c_void_p), I_out.ctypes.data_as(C.c_void_p), self._sarg()))
-        self._tran["d2h_bytes"] = 8 * rows * (1 + self.n_external + max(nvs, 1))
+        self._tran["d2h_bytes"] = 8 * rows * (1 + self.n_out + max(nvs, 1))
         return times, V_out, I_out
 
     def run_transient(self, t_stop: Optional[float] = None, dt: Optional[float] = None, max_steps: Optional[int] = None,
@@ -915,9 +936,14 @@ class B200Engine:
             times, V_out, I_out = self.tran_read(max_steps)
         else:
             times = np.zeros(max_steps)
-            V_out = np.zeros((max_steps, self.n_external))
+            V_out = np.zeros((max_steps, self.n_out))
             I_out = np.zeros((max_steps, max(nvs, 1)))
-        node_indices = {name: idx for name, idx in self.node_names.items() if 0 < idx < self.n_external}
+        si = getattr(self, "_save_idx", None)
+        if si is None:
+            node_indices = {name: idx for name, idx in self.node_names.items() if 0 < idx < self.n_external}
+        else:   # column of V_out per saved node
+            col = {int(n): k for k, n in enumerate(si)}
+            node_indices = {name: col[idx] for name, idx in self.node_names.items() if idx in col}
         rejected = sc["rejected"]
         stats = {
             "n_steps": n_steps, "total_timesteps": n_steps, "accepted_steps": n_steps, "rejected_steps": rejected,

@@ -564,7 +564,19 @@ def compute_eval_layout(bundle: dict, shared_indices, varying_indices, shared_ca
     }
 
 
-def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = False, n_slices: int = 1) -> Tuple[str, dict]:
+def default_min_blocks(n_dev: int) -> int:
+    """Resident CTAs per SM asked of ptxas (``__launch_bounds__`` second argument; 0 = unconstrained).  A model
+    kernel that fills the machine several times over (mul64: 2,082 CTAs) is bound by how many warps an SM
+    sub-partition can switch between: 4 CTAs of 128 threads (128 registers, some spills) beat 2 CTAs at 255
+    registers (1.21 against 1.45 ms, profiles/r2_eval_variants.txt).  VJX_EVAL_MINBLOCKS overrides."""
+    env = os.environ.get("VJX_EVAL_MINBLOCKS")
+    if env:
+        return max(0, int(env))
+    return 4 if (n_dev + 127) // 128 > 4 * 148 else 0
+
+
+def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = False, n_slices: int = 1,
+                     min_blocks: int = 0) -> Tuple[str, dict]:
     fn = parse_function("eval", bundle["mir_data"], bundle.get("str_constants"))
     dae = bundle["dae_data"]
     param_idx_to_val = {p[0]: f"v{p[1]}" for p in bundle["all_func_params"]}
@@ -670,23 +682,36 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
     if use_limit_functions and n_lim > 0 and not body.limit_raw:
         # inline limiting without BuiltinLimit: the reference disables limiting for the model
         # (openvaf_models.py:972-990) - signal it to the caller.
-        src2, meta2 = emit_eval_source(bundle, layout, use_limit_functions=False, n_slices=n_slices)
+        src2, meta2 = emit_eval_source(bundle, layout, use_limit_functions=False, n_slices=n_slices, min_blocks=min_blocks)
         meta2["limiting_disabled"] = True
         return src2, meta2
 
     slices = plan_slices(fn, dae, n_slices)
     K = len(slices)
+    # The destination indices are read through the non-coherent path in groups, ahead of the stores that use them:
+    # emitted as "load index, test, store" per output the compiler keeps that order (a store through jsorted may
+    # alias the next jdest load as far as it knows), and the tail becomes R + J sequential memory round trips -
+    # 39 % of the kernel's time at mul64 size (profiles/r2_ncu_eval_kernel_mul64_psp103w.txt).
+    GROUP = 16
     tail.append("const double c0 = a.ctl[VJX_CTL_C0];")
     for k, sl in enumerate(slices):
         tail.append(f"if constexpr (S < 0 || S == {k}) {{")
-        for e in sl["jac"]:
-            tail.append(
-                f"  {{ int p = a.jdest[(size_t){e} * n + d]; if (p >= 0) a.jsorted[p] = vjx_nan0({jac_r[e]} + c0 * {jac_q[e]}); }}")
+        items = [("j", e) for e in sl["jac"]] + ([("r", r) for r in range(R)] if sl["res"] else [])
+        for g0 in range(0, len(items), GROUP):
+            grp = items[g0:g0 + GROUP]
+            tail.append("  {")
+            for kind, e in grp:
+                arr = "jdest" if kind == "j" else "vdest"
+                tail.append(f"    const int p{kind}{e} = __ldg(a.{arr} + (size_t){e} * n + d);")
+            for kind, e in grp:
+                if kind == "j":
+                    tail.append(f"    if (pj{e} >= 0) a.jsorted[pj{e}] = vjx_nan0({jac_r[e]} + c0 * {jac_q[e]});")
+                else:
+                    tail.append(
+                        f"    if (pr{e} >= 0) {{ double2* q = reinterpret_cast<double2*>(a.vsorted + (size_t)pr{e} * 4); "
+                        f"q[0] = make_double2(vjx_nan0({res_r[e]}), vjx_nan0({res_q[e]})); q[1] = make_double2(vjx_nan0({lim_r[e]}), vjx_nan0({lim_q[e]})); }}")
+            tail.append("  }")
         if sl["res"]:
-            for r in range(R):
-                tail.append(
-                    f"  {{ int p = a.vdest[(size_t){r} * n + d]; if (p >= 0) {{ double2* q = reinterpret_cast<double2*>(a.vsorted + (size_t)p * 4); "
-                    f"q[0] = make_double2(vjx_nan0({res_r[r]}), vjx_nan0({res_q[r]})); q[1] = make_double2(vjx_nan0({lim_r[r]}), vjx_nan0({lim_q[r]})); }} }}")
             for li in range(n_lim):
                 if li not in body.limit_store:
                     raise ValueError(f"Limit state {li} was registered (LoadLimit) but no StoreLimit found.")
@@ -721,8 +746,7 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
     src.extend("  " + s for s in tail)
     src.append("}")
     tb = int(os.environ.get("VJX_EVAL_BLOCK", "128"))
-    minb = os.environ.get("VJX_EVAL_MINBLOCKS")
-    lb = f"__launch_bounds__({tb}, {int(minb)})" if minb else f"__launch_bounds__({tb})"
+    lb = f"__launch_bounds__({tb}, {int(min_blocks)})" if min_blocks else f"__launch_bounds__({tb})"
     src.append(f"extern \"C\" __global__ void {lb} vjx_eval_kernel(VjxEvalArgs a) {{")
     src.append("  const int d = blockIdx.x * blockDim.x + threadIdx.x;")
     src.append("  const int n = a.n_dev;")

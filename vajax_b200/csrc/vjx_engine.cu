@@ -1314,6 +1314,8 @@ struct StepArgs {
   double* ctl;
   vjx_options o;
   int n_total, n_unknowns, n_vs, n_is, n_ext, n_lim, H;
+  int n_out;             // columns of V_out: n_ext, or the length of the save list
+  const int* save_idx;   // node index (into X) per V_out column; null = the first n_ext nodes
   const vjx_source_desc* vsrc_desc;
   const vjx_source_desc* isrc_desc;
   const double* pwl_t;
@@ -1561,7 +1563,10 @@ __global__ void k_step_commit(StepArgs a, cudaGraphConditionalHandle handle, int
       }
     }
     if (accept) {
-      if (i < a.n_ext) a.V_out[(size_t)row * a.n_ext + i] = use_new ? xn : a.X[i];
+      if (i < a.n_out) {
+        const int src = a.save_idx ? a.save_idx[i] : i;   // Xw is never written here, X only when use_new
+        a.V_out[(size_t)row * a.n_out + i] = use_new ? a.Xw[src] : a.X[src];
+      }
       if (i < nvs1) a.I_out[(size_t)row * nvs1 + i] = (a.n_vs > 0 && !nr_fail_min) ? a.Ivs[i] : 0.0;
     }
   }
@@ -1715,6 +1720,8 @@ struct vjx_handle {
   DevBuf<TranScalars> ts;
   DevBuf<double> X, Vpred, Vhist, Vmax, Q_prev, dQdt_prev, Q_prev2, hist_mrc, res_tol_floor, limit_state;
   DevBuf<double> times_out, V_out, I_out, records;
+  DevBuf<int> save_idx;                // N4: node per V_out column (empty = all external nodes)
+  int n_out = 0;                       // columns of V_out
   int max_steps = 0, max_records = 0, H = 4;
   // graphs
   cudaGraphExec_t g_iter = nullptr;    // one NR iteration
@@ -2807,6 +2814,7 @@ static StepArgs make_step_args(vjx_handle* h) {
   StepArgs a;
   a.ts = h->ts.p; a.st = h->st.p; a.ctl = h->ctl.p; a.o = h->o;
   a.n_total = h->n_total; a.n_unknowns = h->n_unknowns; a.n_vs = h->n_vs; a.n_is = h->n_is; a.n_ext = h->n_ext;
+  a.n_out = h->n_out > 0 ? h->n_out : h->n_ext; a.save_idx = h->n_out > 0 ? h->save_idx.p : nullptr;
   a.n_lim = h->total_lim; a.H = h->H;
   a.vsrc_desc = h->vsrc_desc.p; a.isrc_desc = h->isrc_desc.p; a.pwl_t = h->pwl_t.p; a.pwl_v = h->pwl_v.p;
   a.vsrc = h->vsrc_val.p; a.isrc = h->isrc_val.p;
@@ -2819,6 +2827,9 @@ static StepArgs make_step_args(vjx_handle* h) {
   return a;
 }
 
+__global__ void k_gather(int n, const int* idx, const double* src, double* dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
 __global__ void k_abs_copy(int n, const double* src, double* dst) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = fabs(src[i]);
 }
@@ -2843,13 +2854,14 @@ extern "C" int vjx_tran_begin(vjx_handle* h, const double* X0, const double* Q_i
   const int nt = h->n_total, nu = std::max(h->n_unknowns, 1), nx = h->n_total + h->n_vs, nvs1 = std::max(h->n_vs, 1);
   h->H = h->o.max_order + 2;
   if (h->H > 4 || h->H < 3) return fail(VJX_ERR_INVALID, "max_order must be 1 or 2");
-  if (max_steps != h->max_steps || !h->X.p) {
+  const int n_out = h->n_out > 0 ? h->n_out : h->n_ext;
+  if (max_steps != h->max_steps || !h->X.p || h->V_out.n != (size_t)max_steps * n_out) {
     h->max_steps = max_steps;
     h->max_records = 4 * max_steps + 64;
     CK(h->X.alloc(nx)); CK(h->Vpred.alloc(nt)); CK(h->Vhist.alloc((size_t)h->H * nt)); CK(h->Vmax.alloc(nt));
     CK(h->Q_prev.alloc(nu)); CK(h->dQdt_prev.alloc(nu)); CK(h->Q_prev2.alloc(nu)); CK(h->hist_mrc.alloc(nu));
     CK(h->res_tol_floor.alloc(nu)); CK(h->limit_state.alloc(std::max(h->total_lim, 1)));
-    CK(h->times_out.alloc(max_steps)); CK(h->V_out.alloc((size_t)max_steps * h->n_ext));
+    CK(h->times_out.alloc(max_steps)); CK(h->V_out.alloc((size_t)max_steps * n_out));
     CK(h->I_out.alloc((size_t)max_steps * nvs1)); CK(h->records.alloc((size_t)h->max_records * 8));
     if (h->g_tran) { cudaGraphExecDestroy(h->g_tran); h->g_tran = nullptr; }
   }
@@ -2858,11 +2870,12 @@ extern "C" int vjx_tran_begin(vjx_handle* h, const double* X0, const double* Q_i
   CK(cudaMemsetAsync(h->Q_prev2.p, 0, sizeof(double) * nu, s));
   CK(cudaMemsetAsync(h->limit_state.p, 0, sizeof(double) * std::max(h->total_lim, 1), s));
   CK(cudaMemsetAsync(h->times_out.p, 0, sizeof(double) * max_steps, s));
-  CK(cudaMemsetAsync(h->V_out.p, 0, sizeof(double) * (size_t)max_steps * h->n_ext, s));
+  CK(cudaMemsetAsync(h->V_out.p, 0, sizeof(double) * (size_t)max_steps * n_out, s));
   CK(cudaMemsetAsync(h->I_out.p, 0, sizeof(double) * (size_t)max_steps * nvs1, s));
   CK(cudaMemcpyAsync(h->X.p, X0, sizeof(double) * nx, cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(h->Vhist.p, X0, sizeof(double) * nt, cudaMemcpyDeviceToDevice, s));
-  CK(cudaMemcpyAsync(h->V_out.p, X0, sizeof(double) * h->n_ext, cudaMemcpyDeviceToDevice, s));
+  if (h->n_out > 0) k_gather<<<grid_for(h, n_out), 256, 0, s>>>(n_out, h->save_idx.p, X0, h->V_out.p);
+  else CK(cudaMemcpyAsync(h->V_out.p, X0, sizeof(double) * h->n_ext, cudaMemcpyDeviceToDevice, s));
   k_copy<<<grid_for(h, nu), 256, 0, s>>>(h->n_unknowns, Q_init, h->Q_prev.p);
   k_copy<<<grid_for(h, nu), 256, 0, s>>>(h->n_unknowns, hist_maxres, h->hist_mrc.p);
   if (h->n_vs > 0 && I0) CK(cudaMemcpyAsync(h->I_out.p, I0, sizeof(double) * h->n_vs, cudaMemcpyDeviceToDevice, s));
@@ -2969,6 +2982,28 @@ static int build_tran_graph(vjx_handle* h, int attempts_limit, cudaStream_t s) {
   CK(cudaGraphDestroy(g));
   h->g_tran_limit = attempts_limit;
   (void)s;
+  return VJX_OK;
+}
+
+
+// N4: device-side save list.  The reference records every external node (full_mna.py:1017-1023,
+// 2122) and filters afterwards; for mul64 that is 133 k columns per accepted step where the netlist's `save`
+// lines ask for 128 (vajax/benchmarks/data/mul64/runme.sim:296-308).  With a save list V_out has one column per
+// listed node (index into X: 0 = ground, 1..n_total-1), written by k_step_commit.  n_save = 0 restores "all
+// external nodes".  Takes effect at the next vjx_tran_begin.
+extern "C" int vjx_tran_set_save_list(vjx_handle* h, const int* node_idx_host, int n_save) {
+  if (!h || n_save < 0 || (n_save > 0 && !node_idx_host)) return fail(VJX_ERR_INVALID, "bad save list");
+  if (n_save > h->n_total) return fail(VJX_ERR_INVALID, "save list longer than the node count");
+  CK(cudaSetDevice(h->device));
+  for (int k = 0; k < n_save; ++k)
+    if (node_idx_host[k] < 0 || node_idx_host[k] >= h->n_total) return fail(VJX_ERR_INVALID, "save list: node index out of range");
+  if (n_save > 0) {
+    std::vector<int> v(node_idx_host, node_idx_host + n_save);
+    CK(h->save_idx.upload(v));
+  }
+  h->n_out = n_save;
+  if (h->g_tran) { cudaGraphExecDestroy(h->g_tran); h->g_tran = nullptr; }   // kernel arguments change
+  h->max_steps = -1;                                                         // force re-allocation of V_out
   return VJX_OK;
 }
 
@@ -3087,7 +3122,8 @@ extern "C" int vjx_tran_read(vjx_handle* h, int row0, int rows, double* times, d
   cudaStream_t s = use_stream(h, stream);
   const int nvs1 = std::max(h->n_vs, 1);
   if (times) CK(cudaMemcpyAsync(times, h->times_out.p + row0, sizeof(double) * rows, cudaMemcpyDeviceToHost, s));
-  if (V_out) CK(cudaMemcpyAsync(V_out, h->V_out.p + (size_t)row0 * h->n_ext, sizeof(double) * (size_t)rows * h->n_ext, cudaMemcpyDeviceToHost, s));
+  const int n_out = h->n_out > 0 ? h->n_out : h->n_ext;
+  if (V_out) CK(cudaMemcpyAsync(V_out, h->V_out.p + (size_t)row0 * n_out, sizeof(double) * (size_t)rows * n_out, cudaMemcpyDeviceToHost, s));
   if (I_out) CK(cudaMemcpyAsync(I_out, h->I_out.p + (size_t)row0 * nvs1, sizeof(double) * (size_t)rows * nvs1, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return VJX_OK;

@@ -99,7 +99,7 @@ EXPORTS = [
     "vjx_last_error", "vjx_version", "vjx_device_count", "vjx_create", "vjx_destroy", "vjx_clear_cache",
     "vjx_update_model_data", "vjx_update_sources", "vjx_build_system", "vjx_lu_solve", "vjx_lu_analyze",
     "vjx_lu_stats", "vjx_nr_solve", "vjx_nr_solve_async", "vjx_tran_begin", "vjx_tran_run", "vjx_tran_scalars", "vjx_tran_read",
-    "vjx_tran_set_step_limit", "vjx_tran_run_ms", "vjx_tran_records", "vjx_tran_state", "vjx_time_phase", "vjx_lu_timeline", "vjx_launch_count",
+    "vjx_tran_set_step_limit", "vjx_tran_set_save_list", "vjx_tran_run_ms", "vjx_tran_records", "vjx_tran_state", "vjx_time_phase", "vjx_lu_timeline", "vjx_launch_count",
     "vjx_sizes", "vjx_handle_id", "vjx_handle_from_id",
 ]
 
@@ -142,6 +142,7 @@ def load() -> C.CDLL:
     lib.vjx_tran_run.argtypes = [p, i, C.POINTER(C.c_int), p]
     lib.vjx_tran_scalars.argtypes = [p, p, p]
     lib.vjx_tran_set_step_limit.argtypes = [p, i, p]
+    lib.vjx_tran_set_save_list.argtypes = [p, p, i]
     lib.vjx_tran_run_ms.argtypes = [p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.vjx_tran_read.argtypes = [p, i, i, p, p, p, p]
     lib.vjx_tran_records.argtypes = [p, i, i, p, p]
