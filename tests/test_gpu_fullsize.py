@@ -90,7 +90,7 @@ def test_save_list_filters_the_output_rows_on_the_device(bundles, graph):
     t0, V0, s0 = e.run_transient()
     n = s0["n_steps"]
     assert V0.shape[1] == e.n_external
-    names = [f"p{k}" for k in range(4, 8)] + ["vdd", "a0", "0"]
+    names = [f"p{k}" for k in range(4, 7)] + ["vdd", "a0", "s2_1", "0"]
     e.set_save_list(names)
     t1, V1, s1 = e.run_transient()
     assert s1["n_steps"] == n and np.array_equal(t0, t1) and V1.shape[1] == len(names)

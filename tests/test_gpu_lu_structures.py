@@ -69,7 +69,7 @@ def test_tridiagonal_chain(n):
     _solve_and_check(T, rng)
 
 
-@pytest.mark.parametrize("border", [1, 8, 15, 16, 17, 40, 158, 159, 160, 161, 220])
+@pytest.mark.parametrize("border", [1, 8, 15, 16, 17, 40, 158, 159, 160, 161, 220, 311, 312, 319, 320, 321, 340])
 def test_bordered_matrix_dense_trailing_block(border):
     """A sparse leading part bordered by `border` dense rows and columns: after elimination the trailing
     block is dense, of exactly the size that decides whether / how the dense kernel takes it."""
@@ -84,6 +84,41 @@ def test_bordered_matrix_dense_trailing_block(border):
     P = sp.bmat([[lead, B], [C, D]], format="csr")
     st = _solve_and_check(_dominant(P, rng), rng)
     assert st["n"] == n0 + border
+
+
+@pytest.mark.parametrize("border", [5, 8, 9, 16, 31, 32, 33, 64, 100, 152, 153, 159, 200, 312, 319])
+def test_dense_block_kernels_agree_bit_for_bit(border, monkeypatch):
+    """The blocked dense kernel on 1 / 2 / 4 CTAs (VJX_DT_CLUSTER) and the round-1 one-barrier-per-pivot kernel (0)
+    apply the same operations to every entry in the same order: identical solutions, bit for bit, whatever the
+    number of rows (panel remainders 1..8, back-solve block remainders, y column in the last panel)."""
+    import scipy.sparse as sp
+
+    from vajax_b200.analysis.matrix_sequence import SparseLUSolver
+
+    rng = np.random.default_rng(1000 + border)
+    n0 = 300
+    lead = sp.random(n0, n0, density=0.012, random_state=border)
+    Bm = sp.random(n0, border, density=0.3, random_state=border + 1)
+    Cm = sp.random(border, n0, density=0.3, random_state=border + 2)
+    P = sp.bmat([[lead, Bm], [Cm, sp.csr_matrix(np.ones((border, border)))]], format="csr")
+    A = _dominant(P, rng)
+    A.sort_indices()
+    b = rng.normal(size=A.shape[0])
+    sols = {}
+    for cl in ([0, 1, 2, 4] if border <= 159 else [4, 44]):
+        monkeypatch.setenv("VJX_DT_CLUSTER", str(cl % 40))
+        s = SparseLUSolver(A.indptr, A.indices)
+        try:
+            x1 = s.solve(A.data, b)
+            x2 = s.solve(A.data * 1.0, b)
+            assert np.array_equal(x1, x2)
+            sols[cl] = x1
+        finally:
+            s.close()
+    r = A @ sols[4] - b
+    assert np.max(np.abs(r)) <= 1e-9 * max(1.0, float(np.max(abs(A) @ np.abs(sols[4]) + np.abs(b))))
+    bad = {cl: float(np.max(np.abs(x - sols[4]))) for cl, x in sols.items() if not np.array_equal(x, sols[4])}
+    assert not bad, (border, bad)
 
 
 @pytest.mark.parametrize("n,dens", [(50, 0.2), (300, 0.02), (1500, 0.004), (6000, 0.0008)])

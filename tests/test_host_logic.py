@@ -242,3 +242,48 @@ def test_handle_id_registry_rejects_unknown_ids(lib):
     lib.vjx_handle_id.argtypes = [C.c_void_p]
     assert lib.vjx_handle_from_id(12345) is None
     assert lib.vjx_handle_id(None) == 0
+
+
+def test_ffi_handlers_type_check_against_their_bindings(tmp_path):
+    """vajax_b200/csrc/vjx_ffi.cc (the XLA FFI custom-call handlers, north_star's primary call path) cannot be built for
+    real here - jaxlib's headers are absent - but it is compiled against tests/stubs/xla/ffi/api/ffi.h, a stand-in of
+    the binding DSL that static_asserts every handler is invocable with exactly the context / attribute / operand /
+    result types of its Ffi::Bind() chain, and against include/vajax_b200.h (so the C-ABI calls inside type-check too).
+    Catches signature rot; runs nothing."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "vajax_b200", "csrc", "vjx_ffi.cc")
+    obj = str(tmp_path / "vjx_ffi.o")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror=return-type", "-I", os.path.join(root, "tests", "stubs"),
+                        "-I", "/usr/local/cuda/include", src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run(["g++", "-std=c++17", "-c", "-fPIC", "-I", os.path.join(root, "tests", "stubs"), "-I", "/usr/local/cuda/include",
+                        src, "-o", obj], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    syms = subprocess.run(["nm", "-g", obj], capture_output=True, text=True).stdout
+    for target, arity in (("vjx_ffi_solve_f64", 5), ("vjx_ffi_build_system_f64", 21), ("vjx_ffi_nr_solve_f64", 24)):
+        assert f"{target}_arity" in syms, target
+    for fn in ("vjx_lu_solve", "vjx_build_system", "vjx_nr_solve_async", "vjx_handle_from_id", "vjx_sizes"):
+        assert f"U {fn}" in syms, fn      # resolved against libvajax_b200.so at link time
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/vajax"), reason="needs the reference tree (build container only)")
+def test_reference_adapter_reproduces_the_circuit_description():
+    """vajax_b200.analysis.reference_adapter on the REFERENCE's own prepared objects (CircuitEngine.prepare(),
+    FullMNAStrategy.ensure_setup(), _bcsr_indptr; executed on the NumPy JAX shim): the arrays that go into
+    vjx_circuit_desc equal the reference's (voltage gather indices, stamp indices, CSR pattern: checked inside the
+    adapter) and equal what this repo derives on its own from the flat circuit.  Host only, in a subprocess because
+    the shim shadows `jax` in sys.modules."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "tests"))
+    r = subprocess.run([sys.executable, "check_reference_adapter.py", "rc", "clipper", "ring", "mul3"],
+                       cwd=os.path.join(root, "tests", "golden"), env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 8 and all(ln["arrays_equal"] >= 5 for ln in lines), lines
+    assert {ln["circuit"] for ln in lines} == {"rc", "clipper", "ring", "mul3"}

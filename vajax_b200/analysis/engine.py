@@ -159,6 +159,10 @@ class B200Engine:
         self._prepared = False
         self._keep: List[Any] = []
         self.timings: Dict[str, float] = {}
+        # reference_adapter: parameter / cache split per model type handed over by the caller instead of computed here
+        self._model_data: Optional[Dict[str, dict]] = None
+        # describe(): stop before anything touches the GPU (needs _model_data: the init kernels run on the device)
+        self._host_only = False
 
     # ------------------------------------------------------------------------------------
     def _torch(self):
@@ -228,6 +232,12 @@ class B200Engine:
         for mt, devs in self.by_type.items():
             b = self.bundles[mt]
             pairs = [tuple(p) for p in b["collapsible_pairs"]]
+            given = (self._model_data or {}).get(mt)
+            if given is not None and given.get("collapse_by_device") is not None:
+                # the reference's own decisions (compute_early_collapse_decisions, openvaf_models.py:551-670)
+                per_dev = [tuple(sorted(tuple(p) for p in given["collapse_by_device"][d["name"]])) for d in devs]
+                out[mt] = (per_dev, {k: list(k) for k in set(per_dev)})
+                continue
             names = [p.lower() for p in b["init_param_names"]]
             defaults = {k.lower(): v for k, v in b["param_defaults"].items()}
             if len(names) == 0 or len(pairs) == 0:
@@ -391,23 +401,34 @@ class B200Engine:
                 cols.append(dev_cols[ei])
             else:
                 cols.append(0.0)
-        cache_t, _collapse = self._run_init(mt, cols, n_dev)
-        ncc = cache_t.shape[1]
-        torch = self._torch()
-        if ncc > 0 and n_dev > 1:
-            const_mask = torch.all(cache_t == cache_t[0:1, :], dim=0).cpu().numpy()
-            shared_cache_idx = [int(i) for i in np.where(const_mask)[0]]
-            varying_cache_idx = [int(i) for i in np.where(~const_mask)[0]]
+        given = (self._model_data or {}).get(mt)
+        if given is not None:
+            # parameter / cache split handed over by the caller (reference_adapter: the reference's own
+            # prepare_static_inputs result, openvaf_models.py:839-1058) - no init run, no split of our own
+            shared_idx, varying_idx = list(given["shared_indices"]), list(given["varying_indices"])
+            shared_vals = [float(v) for v in given["shared_params"]]
+            dev_cols = {c: np.asarray(given["device_params"][:, k], dtype=np.float64) for k, c in enumerate(varying_idx)}
+            cache = np.ascontiguousarray(given["cache"], dtype=np.float64)
+            shared_cache_idx, varying_cache_idx = list(given["shared_cache_indices"]), list(given["varying_cache_indices"])
+            limit_param_map = dict(given.get("limit_param_map") or limit_param_map)
         else:
-            shared_cache_idx, varying_cache_idx = [], list(range(ncc))
-        cache = cache_t.cpu().numpy()
+            cache_t, _collapse = self._run_init(mt, cols, n_dev)
+            ncc = cache_t.shape[1]
+            torch = self._torch()
+            if ncc > 0 and n_dev > 1:
+                const_mask = torch.all(cache_t == cache_t[0:1, :], dim=0).cpu().numpy()
+                shared_cache_idx = [int(i) for i in np.where(const_mask)[0]]
+                varying_cache_idx = [int(i) for i in np.where(~const_mask)[0]]
+            else:
+                shared_cache_idx, varying_cache_idx = [], list(range(ncc))
+            cache = cache_t.cpu().numpy()
         # ---- emit + compile the eval kernel for this layout
         layout = emitter.compute_eval_layout(b, shared_idx, varying_idx, shared_cache_idx, varying_cache_idx,
                                              limit_param_map)
         src, meta = emitter.emit_eval_source(b, layout, self.use_device_limiting, n_slices=emitter.default_slices(n_dev),
                                               min_blocks=emitter.default_min_blocks(n_dev))
         use_lim = self.use_device_limiting and not meta.get("limiting_disabled", False)
-        plugin = emitter.compile_plugin(src, f"{mt}_eval")
+        plugin = None if self._host_only else emitter.compile_plugin(src, f"{mt}_eval")
         # ---- node name -> model node index (device independent), then vectorised over instances
         keys_present: Dict[str, int] = {}
         for i in range(len(model_nodes)):
@@ -490,8 +511,9 @@ class B200Engine:
         if self._prepared:
             return self
         t0 = time.perf_counter()
-        lib = vlib.load()
-        self._torch()
+        if not self._host_only:
+            lib = vlib.load()
+            self._torch()
         self._init_plugins: Dict[str, Any] = {}
         self.by_type: Dict[str, List[dict]] = {}
         self.vsources, self.isources = [], []
@@ -538,6 +560,8 @@ class B200Engine:
         self.csr_indices = np.ascontiguousarray((self.unique_linear % n_aug).astype(np.int32))
         self.csr_indptr = np.zeros(n_aug + 1, dtype=np.int32)
         self.csr_indptr[1:] = np.cumsum(np.bincount(urows, minlength=n_aug))
+        if self._host_only:
+            return self
         # ---- create the handle
         cfg = self.adaptive_config()
         o = vlib.Options()
@@ -590,6 +614,27 @@ class B200Engine:
         self.cfg = cfg
         self._prepared = True
         return self
+
+    def describe(self) -> dict:
+        """Host-only: everything ``prepare()`` hands to ``vjx_create`` (the arrays of ``vjx_circuit_desc``,
+        include/vajax_b200.h), without compiling a plugin or touching the GPU.  Needs the parameter / cache split
+        from outside (``_model_data``, see analysis/reference_adapter.py) because the init kernels run on the
+        device.  Used by the CPU tests of the reference adapter."""
+        if self._model_data is None:
+            raise vlib.VjxError("describe() needs externally provided model data (the init kernels run on the GPU)")
+        self._host_only = True
+        try:
+            self.prepare()
+        finally:
+            self._host_only = False
+        models = {mt: {k: m[k] for k in ("n_dev", "R", "J", "num_limit_states", "shared_params", "dev_params", "shared_cache",
+                                         "dev_cache", "vnode1", "vnode2", "res_indices", "jac_row_indices", "jac_col_indices",
+                                         "shared_indices", "varying_indices", "shared_cache_indices", "varying_cache_indices")}
+                  for mt, m in self.models.items()}
+        return dict(n_total=self.n_total, n_unknowns=self.n_unknowns, n_external=self.n_external, n_vs=self.n_vs,
+                    n_is=self.n_is, nse=self.nse, csr_indptr=self.csr_indptr, csr_indices=self.csr_indices,
+                    noi_indices=self.noi_indices, internal_indices=self.internal_indices, vs_p=self.vs_p, vs_n=self.vs_n,
+                    is_p=self.is_p, is_n=self.is_n, total_limit_states=self.total_limit_states, models=models)
 
     # ---- stream plumbing ---------------------------------------------------------------
     def _sarg(self):

@@ -521,13 +521,15 @@ def plan_slices(fn: Function, dae: dict, n_slices: int) -> List[dict]:
 
 
 def default_slices(n_dev: int) -> int:
-    """Slices for a model with ``n_dev`` instances: enough to give every SM sub-partition of a B200 (148 x 4) a few
-    warps, none when the instance count alone fills the machine.  VJX_EVAL_SLICES overrides."""
+    """Slices for a model with ``n_dev`` instances: about two warps per SM sub-partition of a B200 (148 x 4) in
+    total, none when the instance count alone fills the machine.  Measured at c6288 size (314 warps of instances,
+    profiles/r2_eval_variants.txt): 1 slice 125 us, 3 slices 82 us, 6 slices 104 us - the shorter chain of a slice
+    is paid for with more warps sharing an SM's instruction fetch.  VJX_EVAL_SLICES overrides."""
     env = os.environ.get("VJX_EVAL_SLICES")
     if env:
         return max(1, int(env))
     warps = max(1, (n_dev + 31) // 32)
-    return int(max(1, min(6, (4 * 592) // warps)))
+    return int(max(1, min(6, (2 * 592) // warps)))
 
 
 

@@ -1013,6 +1013,310 @@ __global__ void __launch_bounds__(VJX_DT_THREADS, 1) k_lu_dense_tail(LUDev lu, d
 #undef VJX_DT_UPDATE_ROW
 #undef VJX_DT_PUBLISH_ROW
 
+// ------------------------------------------------------------------------------------------
+// Blocked dense trailing block (round 2).  Same arithmetic as k_lu_dense_tail - every entry receives
+// a(i,j) = fma(-l(i,k), u(k,j), a(i,j)) in ascending pivot order with l(i,k) = a(i,k) * (1 / u(k,k)), so the
+// results are bit-identical to it and to the row algorithm - but organised in panels of P = 8 pivots:
+//   1. gather   the panel's columns of this CTA's rows go to shared memory (LpT, transposed), its 8 pivot rows
+//               go to the shared memory of EVERY CTA of the cluster (Up; distributed shared memory),
+//   2. diag     8 lanes of warp 0 factorise the 8 x 8 diagonal block with shuffles (no CTA barrier per pivot),
+//   3. trsm     L21 = A21 U11^-1 (one thread per row) and U12 = L11^-1 A12 (one thread per column, y included),
+//   4. update   rank-8 update of the register tiles: 8 (NR + NC) shared-memory loads for 8 NR NC FMAs.
+// Three barriers per PANEL instead of one per pivot.  The matrix lives in the registers of a cluster of C CTAs
+// (512 threads each): warp gw = 16 * rank + w of the cluster owns rows gw, gw + 16 C, ..., lane l owns columns
+// l, l + 32, ...  Every CTA repeats steps 2 and 3b on identical data (cheaper than another exchange), so one
+// cluster barrier per panel is the only inter-SM synchronisation.  C = 1: up to 159 rows in one CTA; C = 2: the
+// same rows with twice the fp64 pipes; C = 4: up to 319 rows (mul64's 312-row trailing block).
+// The finished U rows (y in column T) go back to lu.dense; the back substitution runs in CTA 0, one thread per
+// row, in blocks of 16 unknowns: the warp holding those rows solves the 16 x 16 diagonal block in registers, the other
+// rows apply the block with 16 FMAs from values they prefetched one block ahead.  Per-row operation order = descending column,
+// as in k_lu_dense_tail.
+#define VJX_DB_THREADS 512
+#define VJX_DB_P 8
+#define VJX_DB_MAX 319
+
+template <int C>
+__device__ __forceinline__ void vjx_db_sync() {
+  if constexpr (C > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ unsigned vjx_cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of `p` (a shared-memory address of this CTA) in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ unsigned vjx_map_shared(const void* p, unsigned rank) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(p), o;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(o) : "r"(a), "r"(rank));
+  return o;
+}
+__device__ __forceinline__ void vjx_st_cluster_f64(unsigned addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+template <int C, int NR, int NC>
+struct VjxDB {
+  static constexpr int NW = 16 * C;            // warps of the cluster = row classes
+  static constexpr int LDS = NC * 32 + 1;      // row stride of Up
+  static constexpr int NRL = NR * 16;          // rows held by one CTA
+  static constexpr int LDL = NRL + 1;          // row stride of LpT
+  static constexpr int TMAX = (NR * NW < NC * 32 ? NR * NW : NC * 32) - 1;
+  static constexpr int NPANEL = (TMAX + VJX_DB_P) / VJX_DB_P;
+  // shared memory (doubles): Up[2][P][LDS] | LpT[2][P][LDL] | invp[2][P] | ys[TMAX + 1] | xs[32]
+  static constexpr int OFF_LPT = 2 * VJX_DB_P * LDS;
+  static constexpr int OFF_INV = OFF_LPT + 2 * VJX_DB_P * LDL;
+  static constexpr int OFF_YS = OFF_INV + 2 * VJX_DB_P;
+  static constexpr int OFF_XS = OFF_YS + TMAX + 1;
+  static constexpr int SMEM_BYTES = (OFF_XS + 32) * 8;
+};
+
+// rank-8 update of register rows >= AA (row AA only when `first_row`), column blocks [B0, B1): at most five column
+// blocks at a time so that the pivot-row values of a step stay in registers next to the tile
+template <int C, int NR, int NC, int AA, int B0, int B1>
+__device__ __forceinline__ void vjx_db_update(double (&r)[NR][NC], const double* Up, const double* LpT, const int np,
+                                              const bool first_row, const int wi, const int lane) {
+  using D = VjxDB<C, NR, NC>;
+  constexpr int P = VJX_DB_P, LDS = D::LDS, LDL = D::LDL;
+  if constexpr (B0 < B1) {
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+      if (m < np) {
+        double u[B1 - B0];
+#pragma unroll
+        for (int b = B0; b < B1; ++b) u[b - B0] = Up[m * LDS + lane + 32 * b];
+        if (first_row) {
+          const double nl = -LpT[m * LDL + AA * 16 + wi];
+#pragma unroll
+          for (int b = B0; b < B1; ++b) r[AA][b] = __fma_rn(nl, u[b - B0], r[AA][b]);
+        }
+#pragma unroll
+        for (int a = AA + 1; a < NR; ++a) {
+          const double nl = -LpT[m * LDL + a * 16 + wi];
+#pragma unroll
+          for (int b = B0; b < B1; ++b) r[a][b] = __fma_rn(nl, u[b - B0], r[a][b]);
+        }
+      }
+    }
+  }
+}
+
+template <int C, int NR, int NC, int A>
+__device__ __forceinline__ void vjx_db_panel(double (&r)[NR][NC], double* sm, const LUDev& lu, const int T, const int crank,
+                                             const int wi, const int lane, bool& bad) {
+  using D = VjxDB<C, NR, NC>;
+  constexpr int P = VJX_DB_P, LDS = D::LDS, LDL = D::LDL, NW = D::NW;
+  constexpr int k0 = P * A;
+  if (k0 >= T) return;
+  constexpr int aA = k0 / NW;                // register row of the pivot rows
+  constexpr int g0 = k0 % NW;                // cluster warp of the first pivot row
+  constexpr int cA = g0 / 16, w0 = g0 % 16;  // owner CTA / first owner warp
+  constexpr int bcol = k0 / 32, l0 = k0 % 32;
+  double* const Up = sm + (A & 1) * P * LDS;
+  double* const LpT = sm + D::OFF_LPT + (A & 1) * P * LDL;
+  double* const invp = sm + D::OFF_INV + (A & 1) * P;
+  const int np = min(P, T - k0);
+  const int gw = crank * 16 + wi;
+  // ---- 1. gather
+  if (lane >= l0 && lane < l0 + P) {
+#pragma unroll
+    for (int a = aA; a < NR; ++a) LpT[(lane - l0) * LDL + a * 16 + wi] = r[a][bcol];
+  }
+  if (crank == cA && wi >= w0 && wi < w0 + P) {
+    const int t = wi - w0;
+    if constexpr (C > 1) {
+#pragma unroll
+      for (int dst = 0; dst < C; ++dst) {
+        const unsigned base = vjx_map_shared(Up + t * LDS, dst);
+#pragma unroll
+        for (int b = bcol; b < NC; ++b) vjx_st_cluster_f64(base + 8u * (unsigned)(lane + 32 * b), r[aA][b]);
+      }
+    } else {
+#pragma unroll
+      for (int b = bcol; b < NC; ++b) Up[t * LDS + lane + 32 * b] = r[aA][b];
+    }
+  }
+  vjx_db_sync<C>();
+  // ---- 2. diagonal block: lane t of warp 0 holds row k0 + t of the 8 x 8 block
+  if (wi == 0) {
+    double a[P];
+    const int t = lane & (P - 1);
+#pragma unroll
+    for (int j = 0; j < P; ++j) a[j] = Up[t * LDS + k0 + j];
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+      if (m < np) {
+        const double piv = __shfl_sync(0xffffffffu, a[m], m);
+        const double inv = 1.0 / piv;
+        if (lane == m) {
+          if (piv == 0.0 || piv != piv) bad = true;
+          invp[m] = inv;
+          if (crank == 0) lu.inv_diag[lu.dense_start + k0 + m] = inv;
+        }
+        const double l = a[m] * inv;
+#pragma unroll
+        for (int j = m + 1; j < P; ++j) {
+          const double u = __shfl_sync(0xffffffffu, a[j], m);
+          if (t > m) a[j] = __fma_rn(-l, u, a[j]);
+        }
+        if (t > m) a[m] = l;
+      }
+    }
+    if (lane < P) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) Up[lane * LDS + k0 + j] = a[j];
+    }
+  }
+  __syncthreads();
+  // ---- 3a. L21: this CTA's rows below the diagonal block, one thread per row (right-looking over the 8 pivots)
+  if (threadIdx.x < D::NRL) {
+    const int lr = threadIdx.x;
+    const int i = crank * 16 + (lr & 15) + NW * (lr >> 4);
+    if (i >= k0 + P && i < T) {
+      double a[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) a[j] = LpT[j * LDL + lr];
+#pragma unroll
+      for (int m = 0; m < P; ++m) {
+        if (m < np) {
+          const double l = a[m] * invp[m];
+          a[m] = l;
+#pragma unroll
+          for (int j = m + 1; j < P; ++j) a[j] = __fma_rn(-l, Up[m * LDS + k0 + j], a[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < P; ++j) LpT[j * LDL + lr] = a[j];
+    }
+  } else {
+    // ---- 3b. U12 (and y, column T): one thread per column right of the block; every CTA computes all of it
+    for (int j = k0 + P + ((int)threadIdx.x - D::NRL); j <= T; j += VJX_DB_THREADS - D::NRL) {
+      double c[P];
+#pragma unroll
+      for (int m = 0; m < P; ++m) c[m] = Up[m * LDS + j];
+#pragma unroll
+      for (int mp = 0; mp < P - 1; ++mp)
+#pragma unroll
+        for (int m = mp + 1; m < P; ++m) c[m] = __fma_rn(-Up[m * LDS + k0 + mp], c[mp], c[m]);
+#pragma unroll
+      for (int m = 1; m < P; ++m) Up[m * LDS + j] = c[m];
+    }
+  }
+  __syncthreads();
+  // the finished U rows (diagonal block included) go back to lu.dense for the back substitution
+  if (crank == 0) {
+    const int ldg = T + 1;
+    for (int q = threadIdx.x; q < np * ldg; q += VJX_DB_THREADS) {
+      const int m = q / ldg, j = q - m * ldg;
+      if (j >= k0 + m) lu.dense[(size_t)(k0 + m) * ldg + j] = Up[m * LDS + j];
+    }
+  }
+  // ---- 4. rank-8 update of the register tiles (rows below the block, columns right of it)
+  constexpr int b0 = (l0 + P == 32) ? bcol + 1 : bcol;
+  vjx_db_update<C, NR, NC, aA, b0, (b0 + 5 < NC ? b0 + 5 : NC)>(r, Up, LpT, np, gw >= g0 + P, wi, lane);
+  if constexpr (b0 + 5 < NC) vjx_db_update<C, NR, NC, aA, b0 + 5, NC>(r, Up, LpT, np, gw >= g0 + P, wi, lane);
+  if constexpr (A + 1 < D::NPANEL) vjx_db_panel<C, NR, NC, A + 1>(r, sm, lu, T, crank, wi, lane, bad);
+}
+
+template <int C, int NR, int NC>
+__global__ void __launch_bounds__(VJX_DB_THREADS, 1) k_lu_dense_blocked(LUDev lu, double* __restrict__ x_out, NRStat* st) {
+  using D = VjxDB<C, NR, NC>;
+  extern __shared__ double vjx_db_smem[];
+  double* const sm = vjx_db_smem;
+  const int T = lu.n_dense, ldg = T + 1;
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = C > 1 ? (int)vjx_cluster_rank() : 0;
+  const int gw = crank * 16 + wi;
+  double r[NR][NC];
+  if (lu.ts && threadIdx.x == 0 && crank == 0) lu.ts[lu.n + 1] = global_ns();
+#pragma unroll
+  for (int a = 0; a < NR; ++a)
+#pragma unroll
+    for (int b = 0; b < NC; ++b) {
+      const int i = gw + D::NW * a, j = lane + 32 * b;
+      r[a][b] = (i < T && j <= T) ? lu.dense[(size_t)i * ldg + j] : 0.0;
+    }
+  bool bad = false;
+  vjx_db_sync<C>();   // every CTA has read the block before CTA 0 starts writing U rows back into it
+  if (lu.ts && threadIdx.x == 0 && crank == 0) lu.ts[lu.n + 2] = global_ns();
+  vjx_db_panel<C, NR, NC, 0>(r, sm, lu, T, crank, wi, lane, bad);
+  if (__syncthreads_or(bad) && threadIdx.x == 0 && crank == 0) atomicOr(&st->error, 2);
+  if constexpr (C > 1) {
+    vjx_db_sync<C>();   // nobody leaves while its shared memory may still be written / read by the others
+    if (crank != 0) return;
+  }
+  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 3] = global_ns();
+  // ---- back substitution, CTA 0: thread t owns row t; blocks of 16 unknowns, last block first
+  double* const ys = sm + D::OFF_YS;
+  double* const xs = sm + D::OFF_XS;
+  const int t = threadIdx.x;
+  const bool row = t < T;
+  const double* const urow = lu.dense + (size_t)(row ? t : 0) * ldg;
+  if (row) {
+    const double yv = urow[T];
+    ys[t] = yv;
+    lu.y[lu.dense_start + t] = yv;
+  }
+  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 4] = global_ns();
+  constexpr int BS = 16;
+  const int nblk = (T + BS - 1) / BS;
+  double un[BS];   // this row's entries in the columns of the block being solved (prefetched one block ahead)
+  {
+    const int k0 = BS * (nblk - 1);
+#pragma unroll
+    for (int m = 0; m < BS; ++m) un[m] = (row && k0 + m < T && k0 + m >= t) ? urow[k0 + m] : 0.0;
+  }
+  __syncthreads();
+  double xmine = 0.0;
+  for (int B = nblk - 1; B >= 0; --B) {
+    const int k0 = BS * B;
+    double uc[BS];
+#pragma unroll
+    for (int m = 0; m < BS; ++m) uc[m] = un[m];
+    if (B > 0) {
+      const int kn = k0 - BS;
+#pragma unroll
+      for (int m = 0; m < BS; ++m) un[m] = (row && kn + m >= t) ? urow[kn + m] : 0.0;
+    }
+    if (wi == (B >> 1)) {
+      // the warp that holds rows k0 .. k0 + 15 (lanes lb .. lb + 15) solves the diagonal block
+      const int lb = (B & 1) * BS;
+      const bool mine = lane >= lb && lane < lb + BS;
+      double yv = (mine && t < T) ? ys[t] : 0.0;
+#pragma unroll
+      for (int m = BS - 1; m >= 0; --m) {
+        if (k0 + m < T) {
+          const int src = lb + m;
+          const double inv = 1.0 / __shfl_sync(0xffffffffu, uc[m], src);
+          const double xk = __shfl_sync(0xffffffffu, yv, src) * inv;
+          if (mine && lane < src) yv = __fma_rn(-uc[m], xk, yv);
+          if (lane == src) xmine = xk;
+        }
+      }
+      if (mine && t < T) xs[lane - lb] = xmine;
+    }
+    __syncthreads();
+    if (row && t < k0) {
+      double yv = ys[t];
+#pragma unroll
+      for (int m = BS - 1; m >= 0; --m)
+        if (k0 + m < T) yv = __fma_rn(-uc[m], xs[m], yv);
+      ys[t] = yv;
+    }
+    __syncthreads();
+  }
+  if (row) {
+    const int i = lu.dense_start + t;
+    st_pub_f64(lu.xp + i, xmine);
+    x_out[lu.perm_c[i]] = xmine;
+    if (lu.ts) lu.ts[i] = global_ns();
+  }
+  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 5] = global_ns();
+}
+
 // Deterministic warp sum: fixed butterfly order.
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1727,6 +2031,7 @@ struct vjx_handle {
   cudaGraphExec_t g_iter = nullptr;    // one NR iteration
   cudaGraphExec_t g_final = nullptr;   // final build + dQdt
   cudaGraphExec_t g_step_pre = nullptr, g_step_post = nullptr;
+  int dense_cluster = 0;               // CTAs of the blocked dense kernel (0 = round-1 single-CTA kernel)
   cudaGraphExec_t g_nrs = nullptr;     // stand-alone NR loop (WHILE node) of vjx_nr_solve_async, on staging buffers
   DevBuf<double> nrs_X, nrs_in;        // staging: X | vsrc, isrc, Q_prev, dQdt_prev, Q_prev2, res_tol_floor
   cudaGraphExec_t g_tran = nullptr;    // whole device-resident loop (WHILE nodes)
@@ -2262,6 +2567,38 @@ static void launch_residual(vjx_handle* h, const BuildPtrs& b, int check, cudaSt
   h->launches++;
 }
 
+
+// Dense trailing block: the blocked kernel on a cluster of C CTAs (h->dense_cluster; 0 = the round-1 kernel).
+template <int C, int NR, int NC>
+static cudaError_t launch_dense_blocked(const LUDev& lud, double* x, NRStat* st, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, 1, 1);
+  cfg.blockDim = dim3(VJX_DB_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = VjxDB<C, NR, NC>::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_lu_dense_blocked<C, NR, NC>, lud, x, st);
+}
+template <int C, int NR, int NC>
+static cudaError_t prepare_dense_blocked() {
+  return cudaFuncSetAttribute(k_lu_dense_blocked<C, NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              VjxDB<C, NR, NC>::SMEM_BYTES);
+}
+static void launch_dense(vjx_handle* h, const LUDev& lud, double* x, cudaStream_t s) {
+  switch (h->dense_cluster) {
+    case 1: launch_dense_blocked<1, 10, 5>(lud, x, h->st.p, s); break;
+    case 2: launch_dense_blocked<2, 5, 5>(lud, x, h->st.p, s); break;
+    case 4: if (lud.n_dense <= 159) launch_dense_blocked<4, 3, 5>(lud, x, h->st.p, s);
+            else launch_dense_blocked<4, 5, 10>(lud, x, h->st.p, s);
+            break;
+    default: k_lu_dense_tail<<<1, VJX_DT_THREADS, VJX_DT_SMEM, s>>>(lud, x, h->st.p);
+  }
+}
+
 static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s);
 
 typedef void (*lu_rows_fn)(LUDev, const double*, const double*, double, const unsigned char*, NRStat*, unsigned*, int, int, int);
@@ -2282,7 +2619,7 @@ static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr,
     h->launches += 1;
   }
   if (lud.n_dense > 0) {
-    k_lu_dense_tail<<<1, VJX_DT_THREADS, VJX_DT_SMEM, s>>>(lud, x, h->st.p);
+    launch_dense(h, lud, x, s);
     h->launches += 1;
   }
 }
@@ -2402,7 +2739,19 @@ static int upload_symbolic(vjx_handle* h) {
   L.n_dense = n_dense;
   L.dense_lstop = h->lu_dense_lstop.p;
   L.dense = h->lu_dense.p;
-  if (n_dense > 0) CK(cudaFuncSetAttribute(k_lu_dense_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, VJX_DT_SMEM));
+  if (n_dense > 0) {
+    CK(cudaFuncSetAttribute(k_lu_dense_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, VJX_DT_SMEM));
+    CK((prepare_dense_blocked<1, 10, 5>()));
+    CK((prepare_dense_blocked<2, 5, 5>()));
+    CK((prepare_dense_blocked<4, 3, 5>()));
+    CK((prepare_dense_blocked<4, 5, 10>()));
+    // which kernel: VJX_DT_CLUSTER = 1 / 2 / 4 CTAs of the blocked kernel (4 takes up to 319 rows), 0 = the
+    // one-barrier-per-pivot kernel of round 1 (default until the blocked one beats it, profiles/r2_dense_notes.md)
+    int c = getenv("VJX_DT_CLUSTER") ? atoi(getenv("VJX_DT_CLUSTER")) : 0;
+    if (c != 0 && c != 1 && c != 2 && c != 4) c = 0;
+    if (n_dense > VJX_DT_MAX) c = 4;
+    h->dense_cluster = c;
+  }
   // back solve: rows of the dense block are solved by k_lu_dense_tail; the chain tail walked by block 0
   // of k_lu_usolve is what is left of [tail_start, n) in front of it
   L.tail_start = std::min(S.tail_start, ds);
@@ -2498,8 +2847,11 @@ static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s) {
   CK(cudaMemcpy(vals.data(), csr_dev, sizeof(double) * h->nse, cudaMemcpyDeviceToHost));
   std::string err;
   double tol = h->o.pivot_tol > 0 ? h->o.pivot_tol : 1e-3;
+  // rows of the dense trailing block: up to 319 with the 4-CTA cluster kernel (mul64's trailing block has 312),
+  // 159 when VJX_DT_CLUSTER pins a smaller configuration
   int dense_cap = VJX_DT_MAX;
-  if (getenv("VJX_DT_ROWS")) dense_cap = std::min(VJX_DT_MAX, atoi(getenv("VJX_DT_ROWS")));
+  if (getenv("VJX_DT_CLUSTER") && atoi(getenv("VJX_DT_CLUSTER")) == 4) dense_cap = VJX_DB_MAX;
+  if (getenv("VJX_DT_ROWS")) dense_cap = std::min(dense_cap, atoi(getenv("VJX_DT_ROWS")));
   if (getenv("VJX_NO_DENSE_TAIL")) dense_cap = 0;
   // The linear solve only ever sees the NOI-enforced matrix (solver_factories.py:1268-1276 precedes every
   // linear_solve): the slots that enforce_noi rewrites to zero are STRUCTURAL zeros.  Leaving them in the
@@ -3176,13 +3528,13 @@ extern "C" int vjx_lu_timeline(vjx_handle* h, int phase, double* ns_out, int* le
   k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
   if (phase == 5) launch_lu_factor(h, h->lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
   lud.ts = ts.p;
-  CK(cudaMemsetAsync(ts.p, 0, sizeof(ull) * ((size_t)n + 8 + VJX_DT_MAX), s));
+  CK(cudaMemsetAsync(ts.p, 0, sizeof(ull) * ((size_t)n + 8 + VJX_DB_MAX), s));
   k_stamp_now<<<1, 1, 0, s>>>(ts.p + n);
   if (phase == 3) launch_lu_factor(h, lud, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
   if (phase == 5) k_lu_usolve<<<h->lu_grid_u, VJX_SOLVE_THREADS, 0, s>>>(lud, h->delta.p, h->st.p);
-  std::vector<ull> hts((size_t)n + 8 + VJX_DT_MAX);
+  std::vector<ull> hts((size_t)n + 8 + VJX_DB_MAX);
   CK(cudaStreamSynchronize(s));
-  CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 8 + VJX_DT_MAX), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hts.data(), ts.p, sizeof(ull) * ((size_t)n + 8 + VJX_DB_MAX), cudaMemcpyDeviceToHost));
   if (phase == 3 && h->lud.n_dense > 0 && getenv("VJX_DT_TRACE")) {
     auto us = [&](int q) { return ((long long)hts[n + q] - (long long)hts[n]) / 1e3; };
     fprintf(stderr, "dense trailing block (%d rows), us since factorisation start: begin %.1f, loaded %.1f, eliminated %.1f, "

@@ -49,6 +49,13 @@ ffi::Error SolveImpl(cudaStream_t stream, int64_t handle, ffi::Buffer<ffi::F64> 
   return Status(vjx_lu_solve(h, data.typed_data(), b.typed_data(), x->typed_data(), stream));
 }
 
+// every operand / result is checked against vjx_sizes before the C-ABI writes through it (a zero-length optional
+// operand is None)
+bool LenIs(const ffi::Buffer<ffi::F64>& b, int n) { return (int)b.element_count() == n; }
+bool OptLenIs(const ffi::Buffer<ffi::F64>& b, int n) { return b.element_count() == 0 || (int)b.element_count() == n; }
+// a result the library writes n elements into (nothing is written when n == 0, any length will do then)
+bool ResLenIs(ffi::ResultBuffer<ffi::F64>& b, int n) { return n <= 0 || (int)b->element_count() == n; }
+
 // ---- S2: build_system(...) -> (csr_data, f, Q, I_vsource, limit_state_out, max_res_contrib)
 //          (mna_builder.py:528-550, result order :1010) ----------------------------------------------------
 ffi::Error BuildSystemImpl(cudaStream_t stream, int64_t handle, int32_t nr_iteration, double integ_c0, double gmin,
@@ -61,10 +68,14 @@ ffi::Error BuildSystemImpl(cudaStream_t stream, int64_t handle, int32_t nr_itera
   vjx_handle* h;
   Sizes sz;
   if (auto e = Resolve(handle, &h, &sz); e.failure()) return e;
-  if ((int)X.element_count() != sz.n_total + sz.n_vs) return ffi::Error::InvalidArgument("X length != n_total + n_vsources");
-  if ((int)Q_prev.element_count() != sz.n_unknowns) return ffi::Error::InvalidArgument("Q_prev length != n_unknowns");
-  if ((int)csr->element_count() != sz.nse || (int)f->element_count() != sz.n_aug)
-    return ffi::Error::InvalidArgument("result shapes: csr_data[nse], f[n_aug]");
+  if (!LenIs(X, sz.n_total + sz.n_vs)) return ffi::Error::InvalidArgument("X length != n_total + n_vsources");
+  if (!OptLenIs(vsrc, sz.n_vs) || !OptLenIs(isrc, sz.n_is)) return ffi::Error::InvalidArgument("vsource_vals / isource_vals length");
+  if (!LenIs(Q_prev, sz.n_unknowns) || !OptLenIs(dQdt_prev, sz.n_unknowns) || !OptLenIs(Q_prev2, sz.n_unknowns))
+    return ffi::Error::InvalidArgument("Q_prev / dQdt_prev / Q_prev2 length != n_unknowns");
+  if (!OptLenIs(limit_in, sz.n_lim)) return ffi::Error::InvalidArgument("limit_state_in length != total limit states");
+  if (!ResLenIs(csr, sz.nse) || !ResLenIs(f, sz.n_aug)) return ffi::Error::InvalidArgument("result shapes: csr_data[nse], f[n_aug]");
+  if (!ResLenIs(Q, sz.n_unknowns) || !ResLenIs(max_res, sz.n_unknowns) || !ResLenIs(Ivs, sz.n_vs) || !ResLenIs(limit_out, sz.n_lim))
+    return ffi::Error::InvalidArgument("result shapes: Q[n_unknowns], I_vsource[n_vs], limit_state_out[n_lim], max_res_contrib[n_unknowns]");
   return Status(vjx_build_system(h, X.typed_data(), OrNull(vsrc), OrNull(isrc), Q_prev.typed_data(), integ_c0, gmin, gshunt,
                                  integ_c1, integ_d1, OrNull(dQdt_prev), integ_c2, OrNull(Q_prev2), OrNull(limit_in),
                                  (int)nr_iteration, csr->typed_data(), f->typed_data(), Q->typed_data(), Ivs->typed_data(),
@@ -72,7 +83,10 @@ ffi::Error BuildSystemImpl(cudaStream_t stream, int64_t handle, int32_t nr_itera
 }
 
 // ---- S3: nr_solve(...) -> (X, iterations, converged, max_f, Q, dQdt, I_vsource, limit_state, max_res_contrib)
-//          (solver_factories.py:604-725).  The three scalars come back as one F64[3] result. --------------------
+//          (solver_factories.py:604-725).  Stream-ordered: vjx_nr_solve_async runs the NR loop as a CUDA-graph WHILE
+//          node on XLA's stream and the DEVICE writes (iterations, converged, max_f, error_flags) into the F64[4]
+//          result - no host read, no synchronisation inside the handler (the very first call on a handle analyses
+//          the first Jacobian and builds the graph, which synchronises once). ------------------------------------
 ffi::Error NrSolveImpl(cudaStream_t stream, int64_t handle, int32_t max_iterations, double integ_c0, double gmin,
                        double gshunt, double integ_c1, double integ_d1, double integ_c2, ffi::Buffer<ffi::F64> X_init,
                        ffi::Buffer<ffi::F64> vsrc, ffi::Buffer<ffi::F64> isrc, ffi::Buffer<ffi::F64> Q_prev,
@@ -83,23 +97,22 @@ ffi::Error NrSolveImpl(cudaStream_t stream, int64_t handle, int32_t max_iteratio
   vjx_handle* h;
   Sizes sz;
   if (auto e = Resolve(handle, &h, &sz); e.failure()) return e;
-  if ((int)X_init.element_count() != sz.n_total + sz.n_vs || (int)X->element_count() != sz.n_total + sz.n_vs)
+  if (!LenIs(X_init, sz.n_total + sz.n_vs) || !ResLenIs(X, sz.n_total + sz.n_vs))
     return ffi::Error::InvalidArgument("X length != n_total + n_vsources");
-  if ((int)scalars->element_count() != 3) return ffi::Error::InvalidArgument("scalars result must be F64[3]");
-  int iters = 0, conv = 0;
-  double max_f = 0.0;
-  // vjx_nr_solve reads the three scalars back on `stream` before it returns (they decide nothing on the device),
-  // so they can be forwarded into the result buffer with an ordinary stream-ordered copy
-  int rc = vjx_nr_solve(h, X_init.typed_data(), OrNull(vsrc), OrNull(isrc), Q_prev.typed_data(), integ_c0, gmin, gshunt,
-                        integ_c1, integ_d1, OrNull(dQdt_prev), integ_c2, OrNull(Q_prev2), OrNull(limit_in),
-                        OrNull(res_tol_floor), (int)max_iterations, X->typed_data(), &iters, &conv, &max_f, Q->typed_data(),
-                        dQdt->typed_data(), Ivs->typed_data(), limit_out->typed_data(), max_res->typed_data(), stream);
-  if (rc != VJX_OK) return Status(rc);
-  const double host[3] = {(double)iters, (double)conv, max_f};
-  if (cudaMemcpyAsync(scalars->typed_data(), host, sizeof(host), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-      cudaStreamSynchronize(stream) != cudaSuccess)
-    return ffi::Error::Internal("vajax_b200: copying the NR scalars failed");
-  return ffi::Error::Success();
+  if (!OptLenIs(vsrc, sz.n_vs) || !OptLenIs(isrc, sz.n_is)) return ffi::Error::InvalidArgument("vsource_vals / isource_vals length");
+  if (!LenIs(Q_prev, sz.n_unknowns) || !OptLenIs(dQdt_prev, sz.n_unknowns) || !OptLenIs(Q_prev2, sz.n_unknowns) ||
+      !OptLenIs(res_tol_floor, sz.n_unknowns))
+    return ffi::Error::InvalidArgument("Q_prev / dQdt_prev / Q_prev2 / res_tol_floor length != n_unknowns");
+  if (!OptLenIs(limit_in, sz.n_lim)) return ffi::Error::InvalidArgument("limit_state_in length != total limit states");
+  if ((int)scalars->element_count() != 4) return ffi::Error::InvalidArgument("scalars result must be F64[4]");
+  if (!ResLenIs(Q, sz.n_unknowns) || !ResLenIs(dQdt, sz.n_unknowns) || !ResLenIs(max_res, sz.n_unknowns) ||
+      !ResLenIs(Ivs, sz.n_vs) || !ResLenIs(limit_out, sz.n_lim))
+    return ffi::Error::InvalidArgument("result shapes: Q / dQdt / max_res_contrib[n_unknowns], I_vsource[n_vs], limit_state[n_lim]");
+  return Status(vjx_nr_solve_async(h, X_init.typed_data(), OrNull(vsrc), OrNull(isrc), Q_prev.typed_data(), integ_c0, gmin,
+                                   gshunt, integ_c1, integ_d1, OrNull(dQdt_prev), integ_c2, OrNull(Q_prev2), OrNull(limit_in),
+                                   OrNull(res_tol_floor), (int)max_iterations, X->typed_data(), scalars->typed_data(),
+                                   Q->typed_data(), dQdt->typed_data(), Ivs->typed_data(), limit_out->typed_data(),
+                                   max_res->typed_data(), stream));
 }
 
 }  // namespace
@@ -157,7 +170,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(vjx_ffi_nr_solve_f64, NrSolveImpl,
                                   .Arg<ffi::Buffer<ffi::F64>>()   // limit_state_in
                                   .Arg<ffi::Buffer<ffi::F64>>()   // res_tol_floor
                                   .Ret<ffi::Buffer<ffi::F64>>()   // X
-                                  .Ret<ffi::Buffer<ffi::F64>>()   // (iterations, converged, max_f)
+                                  .Ret<ffi::Buffer<ffi::F64>>()   // (iterations, converged, max_f, error_flags)
                                   .Ret<ffi::Buffer<ffi::F64>>()   // Q
                                   .Ret<ffi::Buffer<ffi::F64>>()   // dQdt
                                   .Ret<ffi::Buffer<ffi::F64>>()   // I_vsource

@@ -90,3 +90,55 @@ def lu_solve(handle, csr_data, b):
     sz = sizes(handle)
     call = jax.ffi.ffi_call("vjx_ffi_solve_f64", jax.ShapeDtypeStruct((sz["n_aug"],), jnp.float64))
     return call(csr_data, b, handle=np.int64(handle_id(handle)))
+
+
+def _opt(jnp, a):
+    """None -> zero-length operand (the handlers read a zero-length buffer as NULL)."""
+    return jnp.zeros((0,), dtype=jnp.float64) if a is None else a
+
+
+def build_system(handle, X, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0, integ_c1=0.0,
+                 integ_d1=0.0, dQdt_prev=None, integ_c2=0.0, Q_prev2=None, limit_state_in=None, nr_iteration=1):
+    """Seam S2 as a jittable custom call: ``(csr_data, f, Q, I_vsource, limit_state_out, max_res_contrib)``, the
+    reference's ``build_system`` contract (mna_builder.py:528-550,1010) with ``device_arrays`` inside the handle.
+    The scalars are call attributes: they must be Python numbers at trace time (one traced call per coefficient set)."""
+    jax = _jax()
+    import jax.numpy as jnp
+
+    register()
+    sz = sizes(handle)
+    f64 = jnp.float64
+    out = (jax.ShapeDtypeStruct((sz["nse"],), f64), jax.ShapeDtypeStruct((sz["n_aug"],), f64),
+           jax.ShapeDtypeStruct((sz["n_unknowns"],), f64), jax.ShapeDtypeStruct((max(sz["n_vsources"], 1),), f64),
+           jax.ShapeDtypeStruct((max(sz["total_limit_states"], 1),), f64), jax.ShapeDtypeStruct((sz["n_unknowns"],), f64))
+    call = jax.ffi.ffi_call("vjx_ffi_build_system_f64", out)
+    return call(X, _opt(jnp, vsource_vals), _opt(jnp, isource_vals), Q_prev, _opt(jnp, dQdt_prev), _opt(jnp, Q_prev2),
+                _opt(jnp, limit_state_in), handle=np.int64(handle_id(handle)), nr_iteration=np.int32(nr_iteration),
+                integ_c0=float(integ_c0), gmin=float(gmin), gshunt=float(gshunt), integ_c1=float(integ_c1),
+                integ_d1=float(integ_d1), integ_c2=float(integ_c2))
+
+
+def nr_solve(handle, X_init, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0, integ_c1=0.0,
+             integ_d1=0.0, dQdt_prev=None, integ_c2=0.0, Q_prev2=None, limit_state_in=None, res_tol_floor=None,
+             max_iterations=-1):
+    """Seam S3 as a jittable, stream-ordered custom call (``vjx_nr_solve_async``): the reference's 9 results
+    ``(X, iterations, converged, max_f, Q, dQdt, I_vsource, limit_state_out, max_res_contrib)``
+    (solver_factories.py:604-725); the device writes the three scalars, nothing synchronises."""
+    jax = _jax()
+    import jax.numpy as jnp
+
+    register()
+    sz = sizes(handle)
+    f64 = jnp.float64
+    nx, nu = sz["n_total"] + sz["n_vsources"], sz["n_unknowns"]
+    out = (jax.ShapeDtypeStruct((nx,), f64), jax.ShapeDtypeStruct((4,), f64), jax.ShapeDtypeStruct((nu,), f64),
+           jax.ShapeDtypeStruct((nu,), f64), jax.ShapeDtypeStruct((max(sz["n_vsources"], 1),), f64),
+           jax.ShapeDtypeStruct((max(sz["total_limit_states"], 1),), f64), jax.ShapeDtypeStruct((nu,), f64))
+    call = jax.ffi.ffi_call("vjx_ffi_nr_solve_f64", out)
+    X, sc, Q, dQdt, Ivs, lim, mrc = call(
+        X_init, _opt(jnp, vsource_vals), _opt(jnp, isource_vals), Q_prev, _opt(jnp, dQdt_prev), _opt(jnp, Q_prev2),
+        _opt(jnp, limit_state_in), _opt(jnp, res_tol_floor), handle=np.int64(handle_id(handle)),
+        max_iterations=np.int32(max_iterations), integ_c0=float(integ_c0), gmin=float(gmin), gshunt=float(gshunt),
+        integ_c1=float(integ_c1), integ_d1=float(integ_d1), integ_c2=float(integ_c2))
+    return (X, sc[0].astype(jnp.int32), sc[1] > 0.5, sc[2], Q, dQdt, Ivs[:sz["n_vsources"]],
+            lim[:sz["total_limit_states"]], mrc)
