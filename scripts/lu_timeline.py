@@ -15,8 +15,9 @@ from vajax_b200.benchmarks import circuits  # noqa: E402
 from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
-circ = circuits.mul64_circuit(nb) if nb == 64 else circuits.multiplier_circuit(nb)
+bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103", "psp103w")}
+model = sys.argv[2] if len(sys.argv) > 2 else "psp103w"
+circ = circuits.mul64_circuit(nb, mos_model=model) if nb == 64 else circuits.multiplier_circuit(nb, mos_model=model)
 e = B200Engine(circ, bundles, use_device_graph=True).prepare()
 e.run_transient(max_steps=6 if nb == 64 else 12)
 st = e.lu_stats()

@@ -19,14 +19,16 @@ from vajax_b200.benchmarks.circuits import mul64_circuit  # noqa: E402
 from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 
 ROWS = 3   # row 0 = initial condition, then two accepted steps
-bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103")}
-o = OracleEngine(mul64_circuit(64), bundles)
+MODEL = sys.argv[1] if len(sys.argv) > 1 else "psp103"      # psp103 (light surrogate) or psp103w (PSP103-weight)
+OUT = "mul64_first_steps.npz" if MODEL == "psp103" else f"mul64_first_steps_{MODEL}.npz"
+bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103", "psp103w")}
+o = OracleEngine(mul64_circuit(64, mos_model=MODEL), bundles)
 rec = []
 t, V, st = o.run_transient(max_steps=ROWS, record=rec)
 n = st["n_steps"]
 cols = np.arange(0, V.shape[1], 64)
 np.savez_compressed(
-    os.path.join(ROOT, "tests", "golden", "mul64_first_steps.npz"),
+    os.path.join(ROOT, "tests", "golden", OUT),
     times=np.asarray(t[:n]), cols=cols, V_cols=np.asarray(V[:n][:, cols]),
     row_absmax=np.max(np.abs(V[:n]), axis=1), row_sum=np.sum(V[:n], axis=1),
     records=np.array([[r["step"], r["t_next"], r["dt"], r["nr_iters"], float(r["accept"])] for r in rec]),

@@ -58,11 +58,11 @@ CMP = {"feq": "==", "fne": "!=", "flt": "<", "fgt": ">", "fle": "<=", "fge": ">=
        "ieq": "==", "ine": "!=", "ilt": "<", "igt": ">", "ile": "<=", "ige": ">=",
        "beq": "==", "bne": "!=", "seq": "==", "sne": "!="}
 BITWISE = {"iand": "&", "ior": "|", "ixor": "^", "ishl": "<<", "ishr": ">>"}
-UNARY_F = {"exp": "exp", "floor": "floor", "ceil": "ceil", "sin": "sin", "cos": "cos", "tan": "tan",
+UNARY_F = {"exp": "vjx_exp", "floor": "floor", "ceil": "ceil", "sin": "sin", "cos": "cos", "tan": "tan",
            "sinh": "sinh", "cosh": "cosh", "tanh": "tanh", "abs": "fabs", "fabs": "fabs",
            "asin": "asin", "acos": "acos", "atan": "atan", "asinh": "asinh", "acosh": "acosh",
            "atanh": "atanh"}
-BINARY_F = {"pow": "pow", "atan2": "atan2", "hypot": "hypot", "fmin": "vjx_fmin", "fmax": "vjx_fmax"}
+BINARY_F = {"pow": "vjx_pow", "atan2": "atan2", "hypot": "hypot", "fmin": "vjx_fmin", "fmax": "vjx_fmax"}
 TRANSC = {"exp", "ln", "log", "clog2", "sqrt", "pow", "sin", "cos", "tan", "sinh", "cosh", "tanh",
           "asin", "acos", "atan", "asinh", "acosh", "atanh", "atan2", "hypot"}
 
@@ -76,9 +76,17 @@ PRELUDE = r"""
 __device__ __forceinline__ double vjx_fmax(double a, double b) { return (a != a || b != b) ? VJX_NAN : (a > b ? a : b); }
 __device__ __forceinline__ double vjx_fmin(double a, double b) { return (a != a || b != b) ? VJX_NAN : (a < b ? a : b); }
 // safe divide: where(b == 0, 0, a / where(b == 0, 1, b))   (expressions.py:349-374)
-__device__ __forceinline__ double vjx_fdiv(double a, double b) { return b == 0.0 ? 0.0 : a / b; }
-__device__ __forceinline__ double vjx_sqrt(double a) { return sqrt(vjx_fmax(a, 0.0)); }
-__device__ __forceinline__ double vjx_ln(double a) { return log(vjx_fmax(a, 1e-300)); }
+// VJX_MATH_FN: __forceinline__ by default; __noinline__ (VJX_EVAL_NOINLINE_MATH=1) turns the ~700 divisions /
+// roots / logarithms / exponentials of a PSP103-weight model into calls of a few shared routines: a third of the
+// kernel's code is their inlined expansions, and the kernel is bound by instruction fetch, not by the fp64 pipe
+#ifndef VJX_MATH_FN
+#define VJX_MATH_FN __forceinline__
+#endif
+__device__ VJX_MATH_FN double vjx_fdiv(double a, double b) { return b == 0.0 ? 0.0 : a / b; }
+__device__ VJX_MATH_FN double vjx_sqrt(double a) { return sqrt(vjx_fmax(a, 0.0)); }
+__device__ VJX_MATH_FN double vjx_ln(double a) { return log(vjx_fmax(a, 1e-300)); }
+__device__ VJX_MATH_FN double vjx_exp(double a) { return exp(a); }
+__device__ VJX_MATH_FN double vjx_pow(double a, double b) { return pow(a, b); }
 __device__ __forceinline__ double vjx_log10(double a) { return log10(vjx_fmax(a, 1e-300)); }
 __device__ __forceinline__ double vjx_clog2(double a) { return ceil(log2(vjx_fmax(a, 1e-300))); }
 // Python semantics of // and % (sign of the divisor)
@@ -735,7 +743,7 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
             sp_lines.append(f"const double sp{k} = C.simparam_defaults[{k}];")
 
     ns, nsc, nsp = max(1, layout["n_shared"]), max(1, layout["n_shared_cache"]), max(1, len(body.simparams))
-    src: List[str] = [PRELUDE]
+    src: List[str] = (["#define VJX_MATH_FN __noinline__"] if os.environ.get("VJX_EVAL_NOINLINE_MATH") == "1" else []) + [PRELUDE]
     src.append(f"#define NLIM {max(1, n_lim)}")
     src.append(f"struct VjxConst {{ double shared[{ns}]; double shared_cache[{nsc}]; double simparam_defaults[{nsp}]; }};")
     src.append("__constant__ VjxConst C;")

@@ -1074,72 +1074,47 @@ struct VjxDB {
   static constexpr int SMEM_BYTES = (OFF_XS + 32) * 8;
 };
 
-// rank-8 update of register rows >= AA (row AA only when `first_row`), column blocks [B0, B1): at most five column
-// blocks at a time so that the pivot-row values of a step stay in registers next to the tile
-template <int C, int NR, int NC, int AA, int B0, int B1>
-__device__ __forceinline__ void vjx_db_update(double (&r)[NR][NC], const double* Up, const double* LpT, const int np,
-                                              const bool first_row, const int wi, const int lane) {
-  using D = VjxDB<C, NR, NC>;
-  constexpr int P = VJX_DB_P, LDS = D::LDS, LDL = D::LDL;
-  if constexpr (B0 < B1) {
-#pragma unroll
-    for (int m = 0; m < P; ++m) {
-      if (m < np) {
-        double u[B1 - B0];
-#pragma unroll
-        for (int b = B0; b < B1; ++b) u[b - B0] = Up[m * LDS + lane + 32 * b];
-        if (first_row) {
-          const double nl = -LpT[m * LDL + AA * 16 + wi];
-#pragma unroll
-          for (int b = B0; b < B1; ++b) r[AA][b] = __fma_rn(nl, u[b - B0], r[AA][b]);
-        }
-#pragma unroll
-        for (int a = AA + 1; a < NR; ++a) {
-          const double nl = -LpT[m * LDL + a * 16 + wi];
-#pragma unroll
-          for (int b = B0; b < B1; ++b) r[a][b] = __fma_rn(nl, u[b - B0], r[a][b]);
-        }
-      }
-    }
-  }
+// Steps 2 and 3 of a panel and the write-back of its U rows: nothing here touches the register tile, so it is ONE
+// copy of code for all panels (k0 is a run-time value).  Only the gather and the rank-8 update are instantiated per
+// panel (vjx_db_panel<A>), and the update loops over the 8 pivots instead of unrolling them: fully unrolled the kernel
+// was ~0.8 MB of straight-line code executed once and instruction fetch set its speed (ncu: no_instruction 8 stalls
+// per issue); with every register index made run-time instead (predicated selects) it issued 4.4 x the
+// instructions.  profiles/r2_dense_notes.md has the three variants.
+// 1 / x for the pivots of the blocked kernel.  The pivot chain is the critical path of the whole dense phase (one
+// reciprocal -> multiply -> FMA link per pivot, 159 - 319 links), and IEEE division costs it ~250 cycles a link.
+// MUFU.RCP64H (rcp.approx.ftz.f64, 2^-20) and two Newton steps give 1 / x to within an ulp in 4 dependent DFMAs; the
+// result is not the correctly rounded quotient, which nothing downstream requires (the factorisation is held to the
+// residual and to agreement with SuperLU, not to the bits of another kernel).  Zero / NaN / Inf pivots fall through
+// to the plain division so that the error flag logic sees what it always saw.
+__device__ __forceinline__ double vjx_fast_rcp(double x) {
+  const int hi = __double2hiint(x) & 0x7ff00000;
+  if (hi == 0 || hi >= 0x7fd00000 || hi <= 0x00300000) return 1.0 / x;
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = __fma_rn(-x, y, 1.0);
+  y = __fma_rn(y, e, y);
+  e = __fma_rn(-x, y, 1.0);
+  return __fma_rn(y, e, y);
 }
 
-template <int C, int NR, int NC, int A>
-__device__ __forceinline__ void vjx_db_panel(double (&r)[NR][NC], double* sm, const LUDev& lu, const int T, const int crank,
-                                             const int wi, const int lane, bool& bad) {
+// debug probe of the blocked kernel (only when the timeline buffer lu.ts is set): cycles per phase of a panel,
+// accumulated by thread 0 (on the critical path: warp 0 does the diagonal blocks) and by the last thread
+__device__ long long vjx_db_cycles[2][8];
+#define VJX_DB_TICK(slot)                                                          \
+  if (lu.ts && (threadIdx.x == 0 || threadIdx.x == VJX_DB_THREADS - 1)) {         \
+    const long long now_ = clock64();                                            \
+    vjx_db_cycles[threadIdx.x == 0 ? 0 : 1][slot] += now_ - tick_;               \
+    tick_ = now_;                                                                \
+  }
+
+template <int C, int NR, int NC>
+__device__ __noinline__ void vjx_db_middle(double* Up, double* LpT, double* invp, const LUDev& lu, const int T, const int k0,
+                                           const int crank, bool* bad_out) {
   using D = VjxDB<C, NR, NC>;
   constexpr int P = VJX_DB_P, LDS = D::LDS, LDL = D::LDL, NW = D::NW;
-  constexpr int k0 = P * A;
-  if (k0 >= T) return;
-  constexpr int aA = k0 / NW;                // register row of the pivot rows
-  constexpr int g0 = k0 % NW;                // cluster warp of the first pivot row
-  constexpr int cA = g0 / 16, w0 = g0 % 16;  // owner CTA / first owner warp
-  constexpr int bcol = k0 / 32, l0 = k0 % 32;
-  double* const Up = sm + (A & 1) * P * LDS;
-  double* const LpT = sm + D::OFF_LPT + (A & 1) * P * LDL;
-  double* const invp = sm + D::OFF_INV + (A & 1) * P;
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int np = min(P, T - k0);
-  const int gw = crank * 16 + wi;
-  // ---- 1. gather
-  if (lane >= l0 && lane < l0 + P) {
-#pragma unroll
-    for (int a = aA; a < NR; ++a) LpT[(lane - l0) * LDL + a * 16 + wi] = r[a][bcol];
-  }
-  if (crank == cA && wi >= w0 && wi < w0 + P) {
-    const int t = wi - w0;
-    if constexpr (C > 1) {
-#pragma unroll
-      for (int dst = 0; dst < C; ++dst) {
-        const unsigned base = vjx_map_shared(Up + t * LDS, dst);
-#pragma unroll
-        for (int b = bcol; b < NC; ++b) vjx_st_cluster_f64(base + 8u * (unsigned)(lane + 32 * b), r[aA][b]);
-      }
-    } else {
-#pragma unroll
-      for (int b = bcol; b < NC; ++b) Up[t * LDS + lane + 32 * b] = r[aA][b];
-    }
-  }
-  vjx_db_sync<C>();
+  long long tick_ = lu.ts ? clock64() : 0;
   // ---- 2. diagonal block: lane t of warp 0 holds row k0 + t of the 8 x 8 block
   if (wi == 0) {
     double a[P];
@@ -1150,9 +1125,9 @@ __device__ __forceinline__ void vjx_db_panel(double (&r)[NR][NC], double* sm, co
     for (int m = 0; m < P; ++m) {
       if (m < np) {
         const double piv = __shfl_sync(0xffffffffu, a[m], m);
-        const double inv = 1.0 / piv;
+        const double inv = vjx_fast_rcp(piv);
         if (lane == m) {
-          if (piv == 0.0 || piv != piv) bad = true;
+          if (piv == 0.0 || piv != piv) *bad_out = true;
           invp[m] = inv;
           if (crank == 0) lu.inv_diag[lu.dense_start + k0 + m] = inv;
         }
@@ -1168,9 +1143,18 @@ __device__ __forceinline__ void vjx_db_panel(double (&r)[NR][NC], double* sm, co
     if (lane < P) {
 #pragma unroll
       for (int j = 0; j < P; ++j) Up[lane * LDS + k0 + j] = a[j];
+      // the block's part of the finished U rows goes back to lu.dense for the back substitution (the rest: step 3b)
+      if (crank == 0 && lane < np) {
+        double* const drow = lu.dense + (size_t)(k0 + lane) * (T + 1) + k0;
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+          if (j >= lane && k0 + j <= T) drow[j] = a[j];
+      }
     }
   }
+  VJX_DB_TICK(1)
   __syncthreads();
+  VJX_DB_TICK(2)
   // ---- 3a. L21: this CTA's rows below the diagonal block, one thread per row (right-looking over the 8 pivots)
   if (threadIdx.x < D::NRL) {
     const int lr = threadIdx.x;
@@ -1203,21 +1187,86 @@ __device__ __forceinline__ void vjx_db_panel(double (&r)[NR][NC], double* sm, co
         for (int m = mp + 1; m < P; ++m) c[m] = __fma_rn(-Up[m * LDS + k0 + mp], c[mp], c[m]);
 #pragma unroll
       for (int m = 1; m < P; ++m) Up[m * LDS + j] = c[m];
+      if (crank == 0) {   // finished U entries of this column -> lu.dense (consecutive threads, consecutive j)
+        double* const dcol = lu.dense + (size_t)k0 * (T + 1) + j;
+#pragma unroll
+        for (int m = 0; m < P; ++m)
+          if (m < np) dcol[(size_t)m * (T + 1)] = c[m];
+      }
     }
   }
+  VJX_DB_TICK(3)
   __syncthreads();
-  // the finished U rows (diagonal block included) go back to lu.dense for the back substitution
-  if (crank == 0) {
-    const int ldg = T + 1;
-    for (int q = threadIdx.x; q < np * ldg; q += VJX_DB_THREADS) {
-      const int m = q / ldg, j = q - m * ldg;
-      if (j >= k0 + m) lu.dense[(size_t)(k0 + m) * ldg + j] = Up[m * LDS + j];
+  VJX_DB_TICK(4)
+}
+
+template <int C, int NR, int NC, int A>
+__device__ __forceinline__ void vjx_db_panel(double (&r)[NR][NC], double* sm, const LUDev& lu, const int T, const int crank,
+                                             const int wi, const int lane, bool& bad) {
+  using D = VjxDB<C, NR, NC>;
+  constexpr int P = VJX_DB_P, LDS = D::LDS, LDL = D::LDL, NW = D::NW;
+  constexpr int k0 = P * A;
+  if (k0 >= T) return;
+  constexpr int aA = k0 / NW;                // register row of the pivot rows
+  constexpr int g0 = k0 % NW;                // cluster warp of the first pivot row
+  constexpr int cA = g0 / 16, w0 = g0 % 16;  // owner CTA / first owner warp
+  constexpr int bcol = k0 / 32, l0 = k0 % 32;
+  double* const Up = sm + (A & 1) * P * LDS;
+  double* const LpT = sm + D::OFF_LPT + (A & 1) * P * LDL;
+  double* const invp = sm + D::OFF_INV + (A & 1) * P;
+  const int np = min(P, T - k0);
+  const int gw = crank * 16 + wi;
+  long long tick_ = lu.ts ? clock64() : 0;
+  // ---- 1. gather
+  if (lane >= l0 && lane < l0 + P) {
+#pragma unroll
+    for (int a = aA; a < NR; ++a) LpT[(lane - l0) * LDL + a * 16 + wi] = r[a][bcol];
+  }
+  if (crank == cA && wi >= w0 && wi < w0 + P) {
+    const int t = wi - w0;
+    if constexpr (C > 1) {
+#pragma unroll
+      for (int dst = 0; dst < C; ++dst) {
+        const unsigned base = vjx_map_shared(Up + t * LDS, dst);
+#pragma unroll
+        for (int b = bcol; b < NC; ++b) vjx_st_cluster_f64(base + 8u * (unsigned)(lane + 32 * b), r[aA][b]);
+      }
+    } else {
+#pragma unroll
+      for (int b = bcol; b < NC; ++b) Up[t * LDS + lane + 32 * b] = r[aA][b];
     }
   }
-  // ---- 4. rank-8 update of the register tiles (rows below the block, columns right of it)
+  VJX_DB_TICK(6)
+  vjx_db_sync<C>();
+  VJX_DB_TICK(0)
+  vjx_db_middle<C, NR, NC>(Up, LpT, invp, lu, T, k0, crank, &bad);
+  if (lu.ts) tick_ = clock64();
+  // ---- 4. rank-8 update of the register tiles (rows below the block, columns right of it; a finished column inside
+  //         the first live column block is updated with whatever Up holds there - it is never read again)
   constexpr int b0 = (l0 + P == 32) ? bcol + 1 : bcol;
-  vjx_db_update<C, NR, NC, aA, b0, (b0 + 5 < NC ? b0 + 5 : NC)>(r, Up, LpT, np, gw >= g0 + P, wi, lane);
-  if constexpr (b0 + 5 < NC) vjx_db_update<C, NR, NC, aA, b0 + 5, NC>(r, Up, LpT, np, gw >= g0 + P, wi, lane);
+  if constexpr (b0 < NC) {
+    const bool first_row = gw >= g0 + P;
+    const double* lp = LpT + wi;
+    const double* up = Up + lane;
+#pragma unroll 1
+    for (int m = 0; m < np; ++m, lp += LDL, up += LDS) {
+      double u[NC - b0];
+#pragma unroll
+      for (int b = b0; b < NC; ++b) u[b - b0] = up[32 * b];
+      if (first_row) {
+        const double nl = -lp[aA * 16];
+#pragma unroll
+        for (int b = b0; b < NC; ++b) r[aA][b] = __fma_rn(nl, u[b - b0], r[aA][b]);
+      }
+#pragma unroll
+      for (int a = aA + 1; a < NR; ++a) {
+        const double nl = -lp[a * 16];
+#pragma unroll
+        for (int b = b0; b < NC; ++b) r[a][b] = __fma_rn(nl, u[b - b0], r[a][b]);
+      }
+    }
+  }
+  VJX_DB_TICK(7)
   if constexpr (A + 1 < D::NPANEL) vjx_db_panel<C, NR, NC, A + 1>(r, sm, lu, T, crank, wi, lane, bad);
 }
 
@@ -1248,7 +1297,15 @@ __global__ void __launch_bounds__(VJX_DB_THREADS, 1) k_lu_dense_blocked(LUDev lu
     vjx_db_sync<C>();   // nobody leaves while its shared memory may still be written / read by the others
     if (crank != 0) return;
   }
-  if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 3] = global_ns();
+  if (lu.ts && threadIdx.x == 0) {
+    lu.ts[lu.n + 3] = global_ns();
+    for (int w = 0; w < 2; ++w) {
+      printf("dense blocked C=%d T=%d thread %d cycles: wait-gather-sync %lld  diag %lld  sync %lld  trsm %lld  sync %lld  writeback %lld  gather %lld  update %lld\n",
+             C, T, w ? VJX_DB_THREADS - 1 : 0, vjx_db_cycles[w][0], vjx_db_cycles[w][1], vjx_db_cycles[w][2], vjx_db_cycles[w][3],
+             vjx_db_cycles[w][4], vjx_db_cycles[w][5], vjx_db_cycles[w][6], vjx_db_cycles[w][7]);
+      for (int q = 0; q < 8; ++q) vjx_db_cycles[w][q] = 0;
+    }
+  }
   // ---- back substitution, CTA 0: thread t owns row t; blocks of 16 unknowns, last block first
   double* const ys = sm + D::OFF_YS;
   double* const xs = sm + D::OFF_XS;
@@ -1286,12 +1343,12 @@ __global__ void __launch_bounds__(VJX_DB_THREADS, 1) k_lu_dense_blocked(LUDev lu
       const int lb = (B & 1) * BS;
       const bool mine = lane >= lb && lane < lb + BS;
       double yv = (mine && t < T) ? ys[t] : 0.0;
+      const double myinv = (mine && t < T) ? lu.inv_diag[lu.dense_start + t] : 0.0;   // 1 / u(t,t), from the elimination
 #pragma unroll
       for (int m = BS - 1; m >= 0; --m) {
         if (k0 + m < T) {
           const int src = lb + m;
-          const double inv = 1.0 / __shfl_sync(0xffffffffu, uc[m], src);
-          const double xk = __shfl_sync(0xffffffffu, yv, src) * inv;
+          const double xk = __shfl_sync(0xffffffffu, yv * myinv, src);
           if (mine && lane < src) yv = __fma_rn(-uc[m], xk, yv);
           if (lane == src) xmine = xk;
         }
@@ -2037,6 +2094,10 @@ struct vjx_handle {
   cudaGraphExec_t g_tran = nullptr;    // whole device-resident loop (WHILE nodes)
   int g_tran_limit = 0;
   cudaStream_t own_stream = nullptr;
+  // the Jacobian stamp and the residual of an NR iteration both depend on the model kernels only: the residual runs
+  // on a side stream between two events (a parallel branch once captured into the iteration graph)
+  cudaStream_t fork_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   void* pinned = nullptr;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the loop launch inside vjx_tran_run
@@ -2061,6 +2122,9 @@ vjx_handle::~vjx_handle() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (own_stream) cudaStreamDestroy(own_stream);
+  if (fork_stream) cudaStreamDestroy(fork_stream);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
   if (pinned) cudaFreeHost(pinned);
 }
 
@@ -2471,6 +2535,11 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
   CK(h->st.alloc(1));
   CK(h->ts.alloc(1));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  if (!getenv("VJX_NO_FORK")) {
+    CK(cudaStreamCreateWithFlags(&h->fork_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
   CK(cudaHostAlloc(&h->pinned, 4096, cudaHostAllocDefault));
   CK(cudaStreamSynchronize(0));   // allocations are zero-filled on the legacy stream (not a device-wide sync: see vjx_destroy)
   *out = h.release();
@@ -2649,8 +2718,17 @@ static int launch_nr_iteration(vjx_handle* h, const BuildPtrs& b, double* X, cud
   h->launches++;
   int rc = launch_eval(h, b, s);
   if (rc) return rc;
-  launch_stamp(h, h->csr.p, 1, s);
-  launch_residual(h, b, 1, s);
+  if (h->fork_stream) {
+    CK(cudaEventRecord(h->ev_fork, s));
+    CK(cudaStreamWaitEvent(h->fork_stream, h->ev_fork, 0));
+    launch_residual(h, b, 1, h->fork_stream);
+    CK(cudaEventRecord(h->ev_join, h->fork_stream));
+    launch_stamp(h, h->csr.p, 1, s);
+    CK(cudaStreamWaitEvent(s, h->ev_join, 0));
+  } else {
+    launch_stamp(h, h->csr.p, 1, s);
+    launch_residual(h, b, 1, s);
+  }
   launch_lu(h, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
   UpdateArgs ua = make_update_args(h, X, b.limit_in, b.limit_out);
   k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua);
