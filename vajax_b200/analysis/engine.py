@@ -736,7 +736,9 @@ class B200Engine:
 
     # ---- Seam S2 -----------------------------------------------------------------------
     def build_system(self, X, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0, integ_c1=0.0,
-                     integ_d1=0.0, dQdt_prev=None, integ_c2=0.0, Q_prev2=None, limit_state_in=None, nr_iteration=1):
+                     integ_d1=0.0, dQdt_prev=None, integ_c2=0.0, Q_prev2=None, limit_state_in=None, nr_iteration=1,
+                     want=None):
+        """``want``: names among (csr, f, Q, Ivs, lim, mrc) to copy back; the others come back as None."""
         self.prepare()
         torch = self._torch()
         dev = f"cuda:{self.device}"
@@ -752,8 +754,9 @@ class B200Engine:
             self._p(dq), float(integ_c2), self._p(q2), self._p(li), int(nr_iteration),
             self._p(csr), self._p(f), self._p(Q), self._p(Ivs), self._p(lim), self._p(mrc), self._sarg()))
         self._sync()
-        return (csr[:self.nse].cpu().numpy(), f[:self.n_aug].cpu().numpy(), Q[:self.n_unknowns].cpu().numpy(),
-                Ivs[:self.n_vs].cpu().numpy(), lim[:self.total_limit_states].cpu().numpy(), mrc[:self.n_unknowns].cpu().numpy())
+        outs = (("csr", csr[:self.nse]), ("f", f[:self.n_aug]), ("Q", Q[:self.n_unknowns]), ("Ivs", Ivs[:self.n_vs]),
+                ("lim", lim[:self.total_limit_states]), ("mrc", mrc[:self.n_unknowns]))
+        return tuple(t.cpu().numpy() if (want is None or nm in want) else None for nm, t in outs)
 
     # ---- Seam S1 -----------------------------------------------------------------------
     def lu_solve(self, csr_data, b):
@@ -877,16 +880,17 @@ class B200Engine:
         if cfg.tran_fs != 1.0:
             dt = dt * cfg.tran_fs
         nu, nt, nvs = self.n_unknowns, self.n_total, self.n_vs
-        X0 = np.zeros(nt + nvs)
-        X0[:nt] = self.init_mid_rail()
-        vs0, is0 = self.eval_sources(0.0)
         t_setup = time.perf_counter()
+        X0 = np.zeros(nt + nvs)
+        vs0, is0 = self.eval_sources(0.0)
         if self.options.icmode == "uic":
-            X0[:nt] = 0.0
+            # UIC: all-zero state; only Q and the source currents of the initial build are needed on the host side
+            # (the 26 MB of Jacobian values of a mul64-sized circuit stay on the device)
             _, _, Q_init, I_dc, _, _ = self.build_system(X0, vs0, is0, np.zeros(nu), 0.0, self.options.gmin, 0.0, 0.0, 0.0,
-                                                         None, 0.0, None, None, 1)
+                                                         None, 0.0, None, None, 1, want=("Q", "Ivs"))
             dc_mrc = np.zeros(nu)
         else:
+            X0[:nt] = self.init_mid_rail()
             X_dc, _, dc_conv, _, Q_dc, _, I_dc, _, dc_mrc = self.nr_solve(
                 X0, vs0, is0, np.zeros(nu), 0.0, self.options.gmin, 0.0, 0.0, 0.0, None, 0.0, None, None, None)
             X0, Q_init = X_dc, Q_dc
@@ -985,7 +989,9 @@ class B200Engine:
             I_out = np.zeros((max_steps, max(nvs, 1)))
         si = getattr(self, "_save_idx", None)
         if si is None:
-            node_indices = {name: idx for name, idx in self.node_names.items() if 0 < idx < self.n_external}
+            if getattr(self, "_node_indices_all", None) is None:
+                self._node_indices_all = {name: idx for name, idx in self.node_names.items() if 0 < idx < self.n_external}
+            node_indices = self._node_indices_all
         else:   # column of V_out per saved node
             col = {int(n): k for k, n in enumerate(si)}
             node_indices = {name: col[idx] for name, idx in self.node_names.items() if idx in col}

@@ -704,29 +704,39 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
     # 39 % of the kernel's time at mul64 size (profiles/r2_ncu_eval_kernel_mul64_psp103w.txt).
     GROUP = 16
     tail.append("const double c0 = a.ctl[VJX_CTL_C0];")
-    for k, sl in enumerate(slices):
-        tail.append(f"if constexpr (S < 0 || S == {k}) {{")
-        items = [("j", e) for e in sl["jac"]] + ([("r", r) for r in range(R)] if sl["res"] else [])
+
+    def emit_group(items, indent="  "):
         for g0 in range(0, len(items), GROUP):
             grp = items[g0:g0 + GROUP]
-            tail.append("  {")
+            tail.append(indent + "{")
             for kind, e in grp:
                 arr = "jdest" if kind == "j" else "vdest"
-                tail.append(f"    const int p{kind}{e} = __ldg(a.{arr} + (size_t){e} * n + d);")
+                tail.append(f"{indent}  const int p{kind}{e} = __ldg(a.{arr} + (size_t){e} * n + d);")
             for kind, e in grp:
                 if kind == "j":
-                    tail.append(f"    if (pj{e} >= 0) a.jsorted[pj{e}] = vjx_nan0({jac_r[e]} + c0 * {jac_q[e]});")
+                    tail.append(f"{indent}  if (pj{e} >= 0) a.jsorted[pj{e}] = vjx_nan0({jac_r[e]} + c0 * {jac_q[e]});")
                 else:
                     tail.append(
-                        f"    if (pr{e} >= 0) {{ double2* q = reinterpret_cast<double2*>(a.vsorted + (size_t)pr{e} * 4); "
+                        f"{indent}  if (pr{e} >= 0) {{ double2* q = reinterpret_cast<double2*>(a.vsorted + (size_t)pr{e} * 4); "
                         f"q[0] = make_double2(vjx_nan0({res_r[e]}), vjx_nan0({res_q[e]})); q[1] = make_double2(vjx_nan0({lim_r[e]}), vjx_nan0({lim_q[e]})); }}")
-            tail.append("  }")
+            tail.append(indent + "}")
+
+    # S = -1: every output; S = k >= 0: the outputs of slice k; S = -2: the residual-side outputs only (the build at the
+    # converged X that nr_solve ends with needs Q, the currents and the limit states, no Jacobian:
+    # solver_factories.py:689-713) - the derivative paths fall to dead-code elimination
+    for k, sl in enumerate(slices):
+        if sl["jac"]:
+            tail.append(f"if constexpr (S == -1 || S == {k}) {{")
+            emit_group([("j", e) for e in sl["jac"]])
+            tail.append("}")
         if sl["res"]:
+            tail.append(f"if constexpr (S == -1 || S == -2 || S == {k}) {{")
+            emit_group([("r", r) for r in range(R)])
             for li in range(n_lim):
                 if li not in body.limit_store:
                     raise ValueError(f"Limit state {li} was registered (LoadLimit) but no StoreLimit found.")
                 tail.append(f"  if (a.limit_out) a.limit_out[(size_t)d * NLIM + {li}] = {body.as_f(body.limit_store[li])};")
-        tail.append("}")
+            tail.append("}")
 
     # ---- simparams prologue
     sp_lines = []
@@ -769,10 +779,19 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
             src.append(f"    case {k}: vjx_eval_body<{k}>(a, d, n); break;")
         src.append("  }")
     src.append("}")
+    src.append(f"extern \"C\" __global__ void {lb} vjx_eval_kernel_res(VjxEvalArgs a) {{")
+    src.append("  const int d = blockIdx.x * blockDim.x + threadIdx.x;")
+    src.append("  const int n = a.n_dev;")
+    src.append("  if (d >= n) return;")
+    src.append("  vjx_eval_body<-2>(a, d, n);")
+    src.append("}")
     src.append(f"""
 extern "C" int vjx_model_eval(const VjxEvalArgs* a, cudaStream_t s) {{
   if (a->n_dev <= 0) return 0;
-  vjx_eval_kernel<<<dim3((a->n_dev + {tb - 1}) / {tb}, {K}), {tb}, 0, s>>>(*a);
+  if (a->jsorted == nullptr)   // residual-side outputs only
+    vjx_eval_kernel_res<<<dim3((a->n_dev + {tb - 1}) / {tb}, 1), {tb}, 0, s>>>(*a);
+  else
+    vjx_eval_kernel<<<dim3((a->n_dev + {tb - 1}) / {tb}, {K}), {tb}, 0, s>>>(*a);
   return (int)cudaGetLastError();
 }}
 extern "C" int vjx_model_set_const(const double* sh, int ns, const double* sc, int nsc,

@@ -1115,22 +1115,24 @@ __device__ __noinline__ void vjx_db_middle(double* Up, double* LpT, double* invp
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int np = min(P, T - k0);
   long long tick_ = lu.ts ? clock64() : 0;
-  // ---- 2. diagonal block: lane t of warp 0 holds row k0 + t of the 8 x 8 block
+  // ---- 2. diagonal block: lane t of warp 0 holds row k0 + t of the 8 x 8 block.  Nothing inside the pivot loop
+  //         diverges or touches memory: every lane computes every reciprocal (same value), the stores happen once
+  //         after the loop.  (With "if (lane == m) { store 1/pivot }" inside, each pivot paid a divergent region whose
+  //         store addresses were loaded from the argument block: ~570 cycles per pivot instead of the chain's ~150.)
   if (wi == 0) {
-    double a[P];
+    double a[P], invs[P];
     const int t = lane & (P - 1);
+    bool anybad = false;
 #pragma unroll
     for (int j = 0; j < P; ++j) a[j] = Up[t * LDS + k0 + j];
 #pragma unroll
     for (int m = 0; m < P; ++m) {
+      invs[m] = 0.0;
       if (m < np) {
         const double piv = __shfl_sync(0xffffffffu, a[m], m);
         const double inv = vjx_fast_rcp(piv);
-        if (lane == m) {
-          if (piv == 0.0 || piv != piv) *bad_out = true;
-          invp[m] = inv;
-          if (crank == 0) lu.inv_diag[lu.dense_start + k0 + m] = inv;
-        }
+        anybad |= (piv == 0.0) | (piv != piv);
+        invs[m] = inv;
         const double l = a[m] * inv;
 #pragma unroll
         for (int j = m + 1; j < P; ++j) {
@@ -1141,10 +1143,16 @@ __device__ __noinline__ void vjx_db_middle(double* Up, double* LpT, double* invp
       }
     }
     if (lane < P) {
+      double myinv = invs[0];
+#pragma unroll
+      for (int m = 1; m < P; ++m) myinv = (lane == m) ? invs[m] : myinv;
+      invp[lane] = myinv;
 #pragma unroll
       for (int j = 0; j < P; ++j) Up[lane * LDS + k0 + j] = a[j];
+      if (anybad && lane == 0) *bad_out = true;
       // the block's part of the finished U rows goes back to lu.dense for the back substitution (the rest: step 3b)
       if (crank == 0 && lane < np) {
+        lu.inv_diag[lu.dense_start + k0 + lane] = myinv;
         double* const drow = lu.dense + (size_t)(k0 + lane) * (T + 1) + k0;
 #pragma unroll
         for (int j = 0; j < P; ++j)
@@ -1317,6 +1325,7 @@ __global__ void __launch_bounds__(VJX_DB_THREADS, 1) k_lu_dense_blocked(LUDev lu
     ys[t] = yv;
     lu.y[lu.dense_start + t] = yv;
   }
+  const double myinv = row ? lu.inv_diag[lu.dense_start + t] : 0.0;   // 1 / u(t,t), written by the elimination
   if (lu.ts && threadIdx.x == 0) lu.ts[lu.n + 4] = global_ns();
   constexpr int BS = 16;
   const int nblk = (T + BS - 1) / BS;
@@ -1343,7 +1352,6 @@ __global__ void __launch_bounds__(VJX_DB_THREADS, 1) k_lu_dense_blocked(LUDev lu
       const int lb = (B & 1) * BS;
       const bool mine = lane >= lb && lane < lb + BS;
       double yv = (mine && t < T) ? ys[t] : 0.0;
-      const double myinv = (mine && t < T) ? lu.inv_diag[lu.dense_start + t] : 0.0;   // 1 / u(t,t), from the elimination
 #pragma unroll
       for (int m = BS - 1; m >= 0; --m) {
         if (k0 + m < T) {
@@ -2088,6 +2096,7 @@ struct vjx_handle {
   cudaGraphExec_t g_iter = nullptr;    // one NR iteration
   cudaGraphExec_t g_final = nullptr;   // final build + dQdt
   cudaGraphExec_t g_step_pre = nullptr, g_step_post = nullptr;
+  bool full_final_eval = false;        // VJX_FULL_FINAL_EVAL=1: the build at the converged X runs the full model kernel
   int dense_cluster = 0;               // CTAs of the blocked dense kernel (0 = round-1 single-CTA kernel)
   cudaGraphExec_t g_nrs = nullptr;     // stand-alone NR loop (WHILE node) of vjx_nr_solve_async, on staging buffers
   DevBuf<double> nrs_X, nrs_in;        // staging: X | vsrc, isrc, Q_prev, dQdt_prev, Q_prev2, res_tol_floor
@@ -2535,6 +2544,7 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
   CK(h->st.alloc(1));
   CK(h->ts.alloc(1));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->full_final_eval = getenv("VJX_FULL_FINAL_EVAL") != nullptr;
   if (!getenv("VJX_NO_FORK")) {
     CK(cudaStreamCreateWithFlags(&h->fork_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -2605,7 +2615,7 @@ static int launch_eval(vjx_handle* h, const BuildPtrs& b, cudaStream_t s) {
     a.limit_in = (ms->n_lim > 0 && b.limit_in) ? b.limit_in + ms->limit_offset : nullptr;
     a.limit_out = (ms->n_lim > 0 && b.limit_out) ? b.limit_out + ms->limit_offset : nullptr;
     a.jdest = ms->jdest.p;
-    a.jsorted = h->jsorted.p;
+    a.jsorted = (b.csr || h->full_final_eval) ? h->jsorted.p : nullptr;   // no Jacobian wanted: residual-side kernel
     a.vdest = ms->vdest.p;
     a.vsorted = h->vsorted.p;
     int rc = ms->eval(&a, s);

@@ -37,7 +37,8 @@ struct VjxEvalArgs {
   // Scatter destinations: each contribution is written once, directly at its position in
   // the slot-sorted contribution arrays (no per-model intermediate tensors).
   const int* jdest;          // SoA (J, n_dev): index into jsorted, -1 = masked (ground)
-  double* jsorted;           // slot-sorted Jacobian contributions: jr + c0*jc
+  double* jsorted;           // slot-sorted Jacobian contributions: jr + c0*jc; NULL = the caller needs no Jacobian
+                             //   (residual-side outputs only: the build at the converged X)
   const int* vdest;          // SoA (R, n_dev): record index into vsorted, -1 = masked
   double* vsorted;           // row-sorted records of 4 doubles: res_resist, res_react(Q),
                              //   lim_rhs_resist, lim_rhs_react
