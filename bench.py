@@ -285,12 +285,23 @@ def run_b200(args, rank, world, local_rank):
     # a c6288-sized circuit is latency-bound and leaves most of the GPU idle
     sweep_ms, sweep_steps = 0.0, 0
     if n_corners > 1 and not args.no_graph:
-        for e in engines:
+        # engines configured for concurrency (run_corners(concurrent > 2) does the same): one output slice and 4 CTAs
+        # per SM for the model kernels, so that the corners' launches overlap instead of queueing
+        sweep_engines = []
+        for gid in corner_ids:
+            circ, _ = make_circuit(args.workload, args.nbits, corner=gid, model=args.model)
+            sweep_engines.append(B200Engine(circ, bundles, device=local_rank, use_device_graph=True, stream="own",
+                                            eval_slices=int(os.environ.get("VJX_SWEEP_SLICES", "1")),
+                                            eval_min_blocks=int(os.environ.get("VJX_SWEEP_MINBLOCKS", "4"))).prepare())
+        for e in sweep_engines:   # warm-up: LU analysis, graph build
+            e.tran_begin(max_steps=1 + W)
+            e.tran_run()
+        for e in sweep_engines:
             e.tran_begin(max_steps=rows)
         barrier()
         ev_s, ev_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev_s.record()
-        ths = [threading.Thread(target=e.tran_run, kwargs=dict(step_limit=rows)) for e in engines]
+        ths = [threading.Thread(target=e.tran_run, kwargs=dict(step_limit=rows)) for e in sweep_engines]
         for th in ths:
             th.start()
         for th in ths:
@@ -299,11 +310,13 @@ def run_b200(args, rank, world, local_rank):
         ev_e.record()
         torch.cuda.synchronize()
         sweep_ms = ev_s.elapsed_time(ev_e)
-        for e in engines:
+        for e in sweep_engines:
             sc = e.tran_scalars()
             sweep_steps += sc["step_idx"] - 1
             if sc["error_flags"]:
                 raise SystemExit(f"bench.py: device error flags {sc['error_flags']} in the concurrent sweep")
+        for e in sweep_engines:
+            e.close()
         barrier()
     clocks = sampler.stop()
     # ---- e2e through the public API with host buffers (H2D of the initial state, D2H of the waveforms)

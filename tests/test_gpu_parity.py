@@ -225,3 +225,30 @@ def test_init_kernel_against_reference(mt, bundles):
     if ref.size:
         assert np.max(np.abs(cache - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-13
     assert np.array_equal(col.cpu().numpy().astype(np.float64), units[f"model_{mt}_collapse"])
+
+
+def test_model_kernel_variants_are_bit_identical(bundles, monkeypatch):
+    """Output slices (1 / 3 / 6), register budgets (launch bounds), the residual-only kernel of the build at the converged
+    X (vs. the full kernel, VJX_FULL_FINAL_EVAL) and the parallel stamp / residual branches (vs. the chain, VJX_NO_FORK)
+    are scheduling choices: every output is computed by the same sequence of fp64 operations, so the transient is the
+    same bit for bit."""
+    from vajax_b200.analysis.engine import B200Engine
+
+    circ = CIRCUITS["mul2w"]()
+    ref = None
+    for kw, env in (({}, {}), (dict(eval_slices=1), {}), (dict(eval_slices=3), {}), (dict(eval_slices=6, eval_min_blocks=3), {}),
+                    (dict(eval_slices=1, eval_min_blocks=5), {}), ({}, {"VJX_FULL_FINAL_EVAL": "1"}), ({}, {"VJX_NO_FORK": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for graph in (False, True):
+            e = B200Engine(circ, bundles, use_device_graph=graph, **kw).prepare()
+            t, V, st = e.run_transient()
+            rec = e.step_records()
+            e.close()
+            if ref is None:
+                ref = (t, V, st["n_steps"], st["total_nr_iterations"], rec)
+            else:
+                assert st["n_steps"] == ref[2] and st["total_nr_iterations"] == ref[3], (kw, env, graph)
+                assert np.array_equal(t, ref[0]) and np.array_equal(V, ref[1]) and np.array_equal(rec, ref[4]), (kw, env, graph)
+        for k in env:
+            monkeypatch.delenv(k)

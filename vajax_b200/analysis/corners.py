@@ -232,6 +232,11 @@ def run_corners(circuit: dict, bundles: Dict[str, dict], corners: Sequence[Corne
         kw = dict(engine_kwargs)
         if concurrent > 1:
             kw.setdefault("stream", "own")
+        if concurrent > 2 and engine_factory.__name__ == "B200Engine":
+            # several corners in flight: one slice and a small register footprint per model-kernel launch, so that the
+            # launches of different corners share the SMs instead of queueing behind each other (bit-identical results)
+            kw.setdefault("eval_slices", 1)
+            kw.setdefault("eval_min_blocks", 4)
         eng = engine_factory(apply_corner(circuit, corners[i]), bundles, device=device, **kw)
         times, V, st = eng.run_transient(max_steps=max_steps)
         n = int(st["n_steps"])

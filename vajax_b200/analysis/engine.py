@@ -134,10 +134,16 @@ class _Plugin:
 
 class B200Engine:
     def __init__(self, circuit: dict, bundles: Dict[str, dict], use_device_limiting: bool = False,
-                 device: int = 0, use_device_graph: bool = False, pivot_tol: float = 1e-3, stream=None):
+                 device: int = 0, use_device_graph: bool = False, pivot_tol: float = 1e-3, stream=None,
+                 eval_slices: Optional[int] = None, eval_min_blocks: Optional[int] = None):
         """``stream``: None = the default CUDA stream; "own" = a private non-blocking stream, so that several
         engines (corners of a sweep) can run their device-resident loops concurrently on one GPU; or a
-        ``torch.cuda.Stream``."""
+        ``torch.cuda.Stream``.  ``eval_slices`` / ``eval_min_blocks``: output slices and resident CTAs per SM of the
+        model kernels (None = by instance count, cuda_emitter.default_slices / default_min_blocks).  A single
+        c6288-sized transient wants the shortest chain (3 slices); a sweep with several corners in flight wants the
+        smallest footprint per launch (1 slice, 4 CTAs per SM) so that the corners' model kernels overlap."""
+        self.eval_slices = eval_slices
+        self.eval_min_blocks = eval_min_blocks
         self.circuit = circuit
         self.devices = circuit["devices"]
         self.num_nodes = int(circuit["num_nodes"])
@@ -425,8 +431,9 @@ class B200Engine:
         # ---- emit + compile the eval kernel for this layout
         layout = emitter.compute_eval_layout(b, shared_idx, varying_idx, shared_cache_idx, varying_cache_idx,
                                              limit_param_map)
-        src, meta = emitter.emit_eval_source(b, layout, self.use_device_limiting, n_slices=emitter.default_slices(n_dev),
-                                              min_blocks=emitter.default_min_blocks(n_dev))
+        src, meta = emitter.emit_eval_source(b, layout, self.use_device_limiting, n_slices=emitter.default_slices(n_dev) if self.eval_slices is None else int(self.eval_slices),
+                                              min_blocks=(emitter.default_min_blocks(n_dev) if self.eval_min_blocks is None
+                                                          else int(self.eval_min_blocks)))
         use_lim = self.use_device_limiting and not meta.get("limiting_disabled", False)
         plugin = None if self._host_only else emitter.compile_plugin(src, f"{mt}_eval")
         # ---- node name -> model node index (device independent), then vectorised over instances

@@ -577,12 +577,13 @@ def compute_eval_layout(bundle: dict, shared_indices, varying_indices, shared_ca
 def default_min_blocks(n_dev: int) -> int:
     """Resident CTAs per SM asked of ptxas (``__launch_bounds__`` second argument; 0 = unconstrained).  A model
     kernel that fills the machine several times over (mul64: 2,082 CTAs) is bound by how many warps an SM
-    sub-partition can switch between: 4 CTAs of 128 threads (128 registers, some spills) beat 2 CTAs at 255
-    registers (1.21 against 1.45 ms, profiles/r2_eval_variants.txt).  VJX_EVAL_MINBLOCKS overrides."""
+    sub-partition can switch between: 5 CTAs of 128 threads (102 registers, spills into L1) beat 2 CTAs at 255
+    registers - mul64, psp103w: 2 CTAs 1.24 ms, 3: 1.27, 4: 1.17, **5: 0.99**, 6: 1.16, 8: 1.04
+    (profiles/r2_eval_variants.txt).  VJX_EVAL_MINBLOCKS overrides."""
     env = os.environ.get("VJX_EVAL_MINBLOCKS")
     if env:
         return max(0, int(env))
-    return 4 if (n_dev + 127) // 128 > 4 * 148 else 0
+    return 5 if (n_dev + 127) // 128 > 4 * 148 else 0
 
 
 def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = False, n_slices: int = 1,
