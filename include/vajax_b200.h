@@ -134,6 +134,10 @@ int vjx_lu_analyze(vjx_handle* h, const double* csr_data_dev, vjx_stream stream)
  * [3]=levels(U), [4]=max row length, [5]=n, [6]=peeled singleton pivots, [7]=core size,
  * [8]=longest L part of a row, [9]=entries of the scatter program */
 int vjx_lu_stats(vjx_handle* h, double* out10);
+/* Sweep tuning (no reference counterpart: the reference runs corners one after the other, engine.py:2235-2320):
+ * the persistent factorisation / back-solve kernels of this handle take 1/div of the GPU's CTA slots so that several
+ * handles in flight on one GPU share the SMs.  Results do not depend on it.  Call before the first solve. */
+int vjx_lu_set_grid_div(vjx_handle* h, int div);
 
 /* ---- Seam S3: nr_solve (vajax/analysis/solver_factories.py:604-725) ---------------------- */
 int vjx_nr_solve(vjx_handle* h, const double* X_init_dev, const double* vsrc_dev, const double* isrc_dev,

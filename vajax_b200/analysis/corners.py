@@ -15,6 +15,8 @@ corner gets its own parameter / init-cache upload.
 
 from __future__ import annotations
 
+import os
+
 import copy
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence
@@ -237,6 +239,8 @@ def run_corners(circuit: dict, bundles: Dict[str, dict], corners: Sequence[Corne
             # launches of different corners share the SMs instead of queueing behind each other (bit-identical results)
             kw.setdefault("eval_slices", 1)
             kw.setdefault("eval_min_blocks", 4)
+            if os.environ.get("VJX_SWEEP_LU_DIV"):
+                kw.setdefault("lu_grid_div", int(os.environ["VJX_SWEEP_LU_DIV"]))
         eng = engine_factory(apply_corner(circuit, corners[i]), bundles, device=device, **kw)
         times, V, st = eng.run_transient(max_steps=max_steps)
         n = int(st["n_steps"])

@@ -135,7 +135,8 @@ class _Plugin:
 class B200Engine:
     def __init__(self, circuit: dict, bundles: Dict[str, dict], use_device_limiting: bool = False,
                  device: int = 0, use_device_graph: bool = False, pivot_tol: float = 1e-3, stream=None,
-                 eval_slices: Optional[int] = None, eval_min_blocks: Optional[int] = None):
+                 eval_slices: Optional[int] = None, eval_min_blocks: Optional[int] = None,
+                 lu_grid_div: Optional[int] = None):
         """``stream``: None = the default CUDA stream; "own" = a private non-blocking stream, so that several
         engines (corners of a sweep) can run their device-resident loops concurrently on one GPU; or a
         ``torch.cuda.Stream``.  ``eval_slices`` / ``eval_min_blocks``: output slices and resident CTAs per SM of the
@@ -144,6 +145,7 @@ class B200Engine:
         smallest footprint per launch (1 slice, 4 CTAs per SM) so that the corners' model kernels overlap."""
         self.eval_slices = eval_slices
         self.eval_min_blocks = eval_min_blocks
+        self.lu_grid_div = lu_grid_div   # sweep tuning: persistent LU kernels take 1/div of the CTA slots (vjx_lu_set_grid_div)
         self.circuit = circuit
         self.devices = circuit["devices"]
         self.num_nodes = int(circuit["num_nodes"])
@@ -616,6 +618,8 @@ class B200Engine:
         self._vsd, self._isd = vsd, isd
         t1 = time.perf_counter()
         vlib.check(lib.vjx_create(C.byref(cd), self.device, C.byref(self.handle)))
+        if self.lu_grid_div:
+            vlib.check(lib.vjx_lu_set_grid_div(self.handle, int(self.lu_grid_div)))
         self.timings["create"] = time.perf_counter() - t1
         self.timings["prepare"] = time.perf_counter() - t0
         self.cfg = cfg

@@ -2068,6 +2068,7 @@ struct vjx_handle {
   DevBuf<double> pwl_t, pwl_v, vsrc_val, isrc_val;
   // LU
   bool lu_ready = false;
+  int lu_grid_div = 0;   // > 1: persistent LU kernels take 1 / lu_grid_div of the SM slots (vjx_lu_set_grid_div)
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_init, lu_kub, lu_order_u, lu_perm_r, lu_perm_c;
   long long ffi_id = 0;           // id handed out by vjx_handle_id (0 = none)
@@ -2878,6 +2879,10 @@ static int upload_symbolic(vjx_handle* h) {
     h->lu_nseg = 0;
     int bounds[3] = {n_nol, n_cut, n};
     int max_grid = 1;
+    // The row and back-solve kernels are persistent (tickets + polling) and by default sized to fill the GPU, which is
+    // right for one transient; with several corners of a sweep in flight on one GPU each of them holding every SM slot
+    // while it polls serialises the corners.  lu_grid_div > 1 shrinks their grids (tickets make any grid size safe).
+    const int grid_div = std::max(1, h->lu_grid_div > 0 ? h->lu_grid_div : (getenv("VJX_LU_GRID_DIV") ? atoi(getenv("VJX_LU_GRID_DIV")) : 1));
     for (int sgi = 0; sgi < 2; ++sgi) {
       const int t0 = bounds[sgi], t1 = bounds[sgi + 1];
       if (t1 <= t0) continue;
@@ -2904,7 +2909,7 @@ static int upload_symbolic(vjx_handle* h) {
       h->lu_seg_t0[s_i] = t0;
       h->lu_seg_t1[s_i] = t1;
       h->lu_seg_rowbuf[s_i] = rowbuf;
-      h->lu_seg_grid[s_i] = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ,
+      h->lu_seg_grid[s_i] = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ / grid_div,
                                                      ((long long)(t1 - t0) + VJX_FACTOR_WARPS - 1) / VJX_FACTOR_WARPS));
       max_grid = std::max(max_grid, h->lu_seg_grid[s_i]);
     }
@@ -2921,7 +2926,8 @@ static int upload_symbolic(vjx_handle* h) {
   // back solve: one block per SM slot, minus room for the long-row blocks; block 0 is dedicated to the
   // chain tail, the other blocks take the tickets
   const int wps = VJX_SOLVE_THREADS / 32;
-  int grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_u - n_long_u, ((long long)n + wps - 1) / wps));
+  const int grid_div_u = std::max(1, h->lu_grid_div > 0 ? h->lu_grid_div : (getenv("VJX_LU_GRID_DIV") ? atoi(getenv("VJX_LU_GRID_DIV")) : 1));
+  int grid_s = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * occ_u / grid_div_u - n_long_u, ((long long)n + wps - 1) / wps));
   if (L.tail_start < n && grid_s < 2) grid_s = 2;
   h->lu_grid_u = grid_s + n_long_u;
   h->lu_ready = true;
@@ -3444,6 +3450,16 @@ extern "C" int vjx_tran_set_save_list(vjx_handle* h, const int* node_idx_host, i
   h->n_out = n_save;
   if (h->g_tran) { cudaGraphExecDestroy(h->g_tran); h->g_tran = nullptr; }   // kernel arguments change
   h->max_steps = -1;                                                         // force re-allocation of V_out
+  return VJX_OK;
+}
+
+// Sweep tuning: the persistent LU kernels (tickets + polling) of a handle take 1 / div of the GPU's CTA slots, so that
+// several handles in flight on one GPU share the SMs.  Any grid size is safe (tickets); results do not depend on it.
+// Must be called before the first factorisation / analysis of the handle.
+extern "C" int vjx_lu_set_grid_div(vjx_handle* h, int div) {
+  if (!h || div < 1) return fail(VJX_ERR_INVALID, "bad grid divisor");
+  if (h->lu_ready) return fail(VJX_ERR_INVALID, "vjx_lu_set_grid_div: the LU of this handle is already analysed");
+  h->lu_grid_div = div;
   return VJX_OK;
 }
 
