@@ -228,7 +228,7 @@ def test_init_kernel_against_reference(mt, bundles):
 
 
 def test_model_kernel_variants_are_bit_identical(bundles, monkeypatch):
-    """Output slices (1 / 3 / 6), register budgets (launch bounds), the residual-only kernel of the build at the converged
+    """Output slices (1 / 3 / 6), register budgets (launch bounds), lock-step barriers, the LU grid divisor, the residual-only kernel of the build at the converged
     X (vs. the full kernel, VJX_FULL_FINAL_EVAL) and the parallel stamp / residual branches (vs. the chain, VJX_NO_FORK)
     are scheduling choices: every output is computed by the same sequence of fp64 operations, so the transient is the
     same bit for bit."""
@@ -237,7 +237,8 @@ def test_model_kernel_variants_are_bit_identical(bundles, monkeypatch):
     circ = CIRCUITS["mul2w"]()
     ref = None
     for kw, env in (({}, {}), (dict(eval_slices=1), {}), (dict(eval_slices=3), {}), (dict(eval_slices=6, eval_min_blocks=3), {}),
-                    (dict(eval_slices=1, eval_min_blocks=5), {}), ({}, {"VJX_FULL_FINAL_EVAL": "1"}), ({}, {"VJX_NO_FORK": "1"})):
+                    (dict(eval_slices=1, eval_min_blocks=5), {}), ({}, {"VJX_FULL_FINAL_EVAL": "1"}), ({}, {"VJX_NO_FORK": "1"}),
+                    ({}, {"VJX_EVAL_LOCKSTEP": "200"}), (dict(eval_slices=1, eval_min_blocks=4, lu_grid_div=4), {"VJX_EVAL_LOCKSTEP": "500"})):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         for graph in (False, True):

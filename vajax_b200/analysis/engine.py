@@ -872,8 +872,18 @@ class B200Engine:
             V[self.noi_indices] = 0.0
         return V
 
+    def dc_operating_point(self, config=None, X_init=None, trace: Optional[list] = None):
+        """DC operating point with the continuation chain (gdev -> gshunt -> src) behind plain Newton: SURVEY row N2,
+        reference vajax/analysis/dc_operating_point.py:128-242 + homotopy.py.  Every solve is one ``vjx_nr_solve``;
+        the solution vector stays on the device between solves.  Returns ``(X, info)`` (analysis/dc_op.py)."""
+        from . import dc_op
+
+        self.prepare()
+        return dc_op.compute_dc_operating_point(self, config, X_init=X_init, trace=trace)
+
     # ---- FullMNAStrategy.run (full_mna.py:780-1196) --------------------------------------
-    def tran_begin(self, t_stop: Optional[float] = None, dt: Optional[float] = None, max_steps: Optional[int] = None):
+    def tran_begin(self, t_stop: Optional[float] = None, dt: Optional[float] = None, max_steps: Optional[int] = None,
+                   dc_homotopy: bool = False):
         """Initial condition (UIC or DC operating point, full_mna.py:882-957) and device state
         allocation; host arrays go host->device here."""
         self.prepare()
@@ -904,6 +914,15 @@ class B200Engine:
             X0[:nt] = self.init_mid_rail()
             X_dc, _, dc_conv, _, Q_dc, _, I_dc, _, dc_mrc = self.nr_solve(
                 X0, vs0, is0, np.zeros(nu), 0.0, self.options.gmin, 0.0, 0.0, 0.0, None, 0.0, None, None, None)
+            if not dc_conv and dc_homotopy:
+                # not what FullMNAStrategy.run does (it starts from the unconverged vector, full_mna.py:940-957):
+                # opt-in continuation from the mid-rail start, then one more solve for Q / the source currents
+                from . import dc_op
+
+                r = dc_op.run_homotopy_chain(dc_op.device_solver(self), X0, np.asarray(vs0, dtype=np.float64),
+                                             np.asarray(is0, dtype=np.float64), np.zeros(nu), dc_op.HomotopyConfig.from_options(self.options))
+                X_dc, _, dc_conv, _, Q_dc, _, I_dc, _, dc_mrc = self.nr_solve(
+                    r.V, vs0, is0, np.zeros(nu), 0.0, self.options.gmin, 0.0, 0.0, 0.0, None, 0.0, None, None, None)
             X0, Q_init = X_dc, Q_dc
         dX0, dQ, dI, dM = self._dev(X0), self._dev(Q_init), self._dev(I_dc if nvs else np.zeros(1)), self._dev(dc_mrc)
         vlib.check(lib.vjx_tran_begin(self.handle, self._p(dX0), self._p(dQ), self._p(dI), self._p(dM), t_stop, dt,

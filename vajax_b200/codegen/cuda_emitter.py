@@ -388,7 +388,7 @@ class _Body:
         return "f", "0.0"
 
     # ---- whole body
-    def emit(self, indent: str = "  ") -> List[str]:
+    def emit(self, indent: str = "  ", lockstep: int = 0) -> List[str]:
         fn = self.fn
         order = fn.topo_order()
         reachable = set(order)
@@ -420,10 +420,37 @@ class _Body:
                     else:
                         e = self.num(val, t)
                     phi_assign[pred].append(f"{ins.result} = {e};")
+        # Lock-step barriers (lockstep = M > 0): the body is straight-line code several times the size of the
+        # instruction cache, executed once per thread, so warps of a CTA that drift apart each fetch it from L2 on
+        # their own.  A block through which every entry -> exit path passes (no edge of the acyclic CFG jumps over
+        # it) is executed exactly once by every thread, so a CTA barrier is legal there and inside it; one every
+        # ~M statements keeps the CTA's warps on the same cache lines.  The kernel then must not return early
+        # (emit_eval_source clamps the instance index and predicates the stores instead).
+        cut = set()
+        if lockstep > 0:
+            pos = {b: i for i, b in enumerate(order)}
+            reach = 0
+            for i, b in enumerate(order):
+                if reach <= i:
+                    cut.add(b)
+                su = fn._succ_of(b)
+                reach = max([reach] + [pos[x] for x in su] + ([len(order)] if not su else []))
         out: List[str] = []
+        since = 0
+        self.n_barriers = 0
         for b in order:
             out.append(f"L_{b}: ;")
-            out.extend(indent + s for s in body[b])
+            if b in cut:
+                for st in body[b]:
+                    if since >= lockstep:
+                        out.append(indent + "__syncthreads();")
+                        self.n_barriers += 1
+                        since = 0
+                    out.append(indent + st)
+                    since += 1
+            else:
+                out.extend(indent + s for s in body[b])
+                since += len(body[b])
             out.extend(indent + s for s in phi_assign[b])
             term = fn.blocks[b][-1] if fn.blocks[b] else None
             if term is None or term.opcode == "exit":
@@ -587,7 +614,7 @@ def default_min_blocks(n_dev: int) -> int:
 
 
 def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = False, n_slices: int = 1,
-                     min_blocks: int = 0) -> Tuple[str, dict]:
+                     min_blocks: int = 0, lockstep: Optional[int] = None) -> Tuple[str, dict]:
     fn = parse_function("eval", bundle["mir_data"], bundle.get("str_constants"))
     dae = bundle["dae_data"]
     param_idx_to_val = {p[0]: f"v{p[1]}" for p in bundle["all_func_params"]}
@@ -628,7 +655,8 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
         else:
             head.append(f"{var} = a.dev_cache[(size_t){src[1]} * n + d];")
 
-    code = body.emit()
+    lockstep = int(os.environ.get("VJX_EVAL_LOCKSTEP", "0")) if lockstep is None else int(lockstep)
+    code = body.emit(lockstep=lockstep)
 
     def outv(ref: str) -> str:
         v = _mir_var(ref)
@@ -693,7 +721,7 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
     if use_limit_functions and n_lim > 0 and not body.limit_raw:
         # inline limiting without BuiltinLimit: the reference disables limiting for the model
         # (openvaf_models.py:972-990) - signal it to the caller.
-        src2, meta2 = emit_eval_source(bundle, layout, use_limit_functions=False, n_slices=n_slices, min_blocks=min_blocks)
+        src2, meta2 = emit_eval_source(bundle, layout, use_limit_functions=False, n_slices=n_slices, min_blocks=min_blocks, lockstep=lockstep)
         meta2["limiting_disabled"] = True
         return src2, meta2
 
@@ -712,7 +740,7 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
             tail.append(indent + "{")
             for kind, e in grp:
                 arr = "jdest" if kind == "j" else "vdest"
-                tail.append(f"{indent}  const int p{kind}{e} = __ldg(a.{arr} + (size_t){e} * n + d);")
+                tail.append(f"{indent}  const int p{kind}{e} = {'live ? ' if lockstep > 0 else ''}__ldg(a.{arr} + (size_t){e} * n + d){' : -1' if lockstep > 0 else ''};")
             for kind, e in grp:
                 if kind == "j":
                     tail.append(f"{indent}  if (pj{e} >= 0) a.jsorted[pj{e}] = vjx_nan0({jac_r[e]} + c0 * {jac_q[e]});")
@@ -736,7 +764,7 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
             for li in range(n_lim):
                 if li not in body.limit_store:
                     raise ValueError(f"Limit state {li} was registered (LoadLimit) but no StoreLimit found.")
-                tail.append(f"  if (a.limit_out) a.limit_out[(size_t)d * NLIM + {li}] = {body.as_f(body.limit_store[li])};")
+                tail.append(f"  if ({'live && ' if lockstep > 0 else ''}a.limit_out) a.limit_out[(size_t)d * NLIM + {li}] = {body.as_f(body.limit_store[li])};")
             tail.append("}")
 
     # ---- simparams prologue
@@ -759,7 +787,7 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
     src.append(f"struct VjxConst {{ double shared[{ns}]; double shared_cache[{nsc}]; double simparam_defaults[{nsp}]; }};")
     src.append("__constant__ VjxConst C;")
     # the body once, as a template: S < 0 stores every output, S = k only the outputs of slice k
-    src.append("template <int S> __device__ __forceinline__ void vjx_eval_body(const VjxEvalArgs& a, const int d, const int n) {")
+    src.append("template <int S> __device__ __forceinline__ void vjx_eval_body(const VjxEvalArgs& a, const int d, const int n, const bool live) {")
     src.extend("  " + s for s in body.decls())
     src.extend("  " + s for s in sp_lines)
     src.extend("  " + s for s in head)
@@ -769,22 +797,23 @@ def emit_eval_source(bundle: dict, layout: dict, use_limit_functions: bool = Fal
     tb = int(os.environ.get("VJX_EVAL_BLOCK", "128"))
     lb = f"__launch_bounds__({tb}, {int(min_blocks)})" if min_blocks else f"__launch_bounds__({tb})"
     src.append(f"extern \"C\" __global__ void {lb} vjx_eval_kernel(VjxEvalArgs a) {{")
-    src.append("  const int d = blockIdx.x * blockDim.x + threadIdx.x;")
-    src.append("  const int n = a.n_dev;")
-    src.append("  if (d >= n) return;")
+    entry = (["  const int d0 = blockIdx.x * blockDim.x + threadIdx.x;", "  const int n = a.n_dev;",
+              "  const bool live = d0 < n;", "  const int d = live ? d0 : n - 1;   // no early return: the body holds CTA barriers"]
+             if lockstep > 0 else
+             ["  const int d = blockIdx.x * blockDim.x + threadIdx.x;", "  const int n = a.n_dev;", "  if (d >= n) return;",
+              "  const bool live = true;"])
+    src.extend(entry)
     if K == 1:
-        src.append("  vjx_eval_body<-1>(a, d, n);")
+        src.append("  vjx_eval_body<-1>(a, d, n, live);")
     else:
         src.append("  switch (blockIdx.y) {")
         for k in range(K):
-            src.append(f"    case {k}: vjx_eval_body<{k}>(a, d, n); break;")
+            src.append(f"    case {k}: vjx_eval_body<{k}>(a, d, n, live); break;")
         src.append("  }")
     src.append("}")
     src.append(f"extern \"C\" __global__ void {lb} vjx_eval_kernel_res(VjxEvalArgs a) {{")
-    src.append("  const int d = blockIdx.x * blockDim.x + threadIdx.x;")
-    src.append("  const int n = a.n_dev;")
-    src.append("  if (d >= n) return;")
-    src.append("  vjx_eval_body<-2>(a, d, n);")
+    src.extend(entry)
+    src.append("  vjx_eval_body<-2>(a, d, n, live);")
     src.append("}")
     src.append(f"""
 extern "C" int vjx_model_eval(const VjxEvalArgs* a, cudaStream_t s) {{
@@ -815,7 +844,7 @@ extern "C" int vjx_model_abi_version() {{ return 1; }}
         "limit_metadata": {"limit_count": n_lim, "raw_operands": dict(body.limit_raw),
                            "store_operands": dict(body.limit_store), "limited_branches": limited},
         "flops_static": dict(body.flops),
-        "n_slices": K, "slice_costs": [sl["cost"] for sl in slices],
+        "n_slices": K, "slice_costs": [sl["cost"] for sl in slices], "lockstep": lockstep, "n_barriers": getattr(body, "n_barriers", 0),
         "warnings": list(body.warnings),
         "use_limit_functions": bool(use_limit_functions),
         "node_names": [r["node_name"] for r in dae["residuals"]],
