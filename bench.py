@@ -292,7 +292,8 @@ def run_b200(args, rank, world, local_rank):
             circ, _ = make_circuit(args.workload, args.nbits, corner=gid, model=args.model)
             sweep_engines.append(B200Engine(circ, bundles, device=local_rank, use_device_graph=True, stream="own",
                                             eval_slices=int(os.environ.get("VJX_SWEEP_SLICES", "1")),
-                                            eval_min_blocks=int(os.environ.get("VJX_SWEEP_MINBLOCKS", "4"))).prepare())
+                                            eval_min_blocks=int(os.environ.get("VJX_SWEEP_MINBLOCKS", "4")),
+                                            lu_grid_div=int(os.environ.get("VJX_SWEEP_LU_DIV", max(1, min(8, len(corner_ids) // 2))))).prepare())
         for e in sweep_engines:   # warm-up: LU analysis, graph build
             e.tran_begin(max_steps=1 + W)
             e.tran_run()

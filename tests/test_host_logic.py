@@ -119,7 +119,9 @@ def test_symbolic_peels_supply_rails(lib):
     rc, x, st = _probe(lib, A, b)
     assert rc == 0 and st["n_single"] >= 2 and st["n_core"] <= n_int
     assert np.max(np.abs(A @ x - b)) < 1e-9 * np.max(np.abs(b))
-    assert st["max_l_len"] < 10  # the 200-long rail row never becomes an L row
+    # the 200-long rail row never becomes an L row (the depth-aware ordering eliminates the 200-ring like a cyclic
+    # reduction: ~log2(200) levels, L parts of up to ~2 log2(200) entries instead of a 200-level chain)
+    assert st["max_l_len"] < 32
 
 
 def test_symbolic_rejects_structurally_singular(lib):

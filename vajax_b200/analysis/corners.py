@@ -239,8 +239,10 @@ def run_corners(circuit: dict, bundles: Dict[str, dict], corners: Sequence[Corne
             # launches of different corners share the SMs instead of queueing behind each other (bit-identical results)
             kw.setdefault("eval_slices", 1)
             kw.setdefault("eval_min_blocks", 4)
-            if os.environ.get("VJX_SWEEP_LU_DIV"):
-                kw.setdefault("lu_grid_div", int(os.environ["VJX_SWEEP_LU_DIV"]))
+            # ... and the persistent LU kernels of one corner take 2 / concurrent of the CTA slots instead of all of them
+            # (8 corners in flight, c6288 / psp103w: 2.94 k -> 3.33 k steps/s; 16 in flight: 3.83 k;
+            # gpurun_out/r2_t_sweep.txt).  VJX_SWEEP_LU_DIV overrides.
+            kw.setdefault("lu_grid_div", int(os.environ.get("VJX_SWEEP_LU_DIV", max(1, min(8, concurrent // 2)))))
         eng = engine_factory(apply_corner(circuit, corners[i]), bundles, device=device, **kw)
         times, V, st = eng.run_transient(max_steps=max_steps)
         n = int(st["n_steps"])

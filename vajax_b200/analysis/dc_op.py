@@ -206,10 +206,19 @@ def run_homotopy_chain(nr_solve: Callable, V_init, vsource_vals, isource_vals, Q
     return HomotopyResult(False, X, "chain_failed", solve.iterations, solve.solves)
 
 
-def device_solver(engine) -> Callable:
+def device_solver(engine, reanalyze: bool = True) -> Callable:
     """``nr_solve`` for the continuation on a ``B200Engine``: the solution vector of one solve is handed to the
-    next as a device tensor; only (iterations, converged, max|f|) cross to the host per solve."""
+    next as a device tensor; only (iterations, converged, max|f|) cross to the host per solve.
+
+    ``reanalyze``: the GPU LU keeps the pivot order of its analysis (fixed pattern, no pivoting in the numeric
+    kernels), and a continuation moves gmin / gshunt over ten decades: a pivot that was 1e-3 S at the first solve is
+    1e-12 S at the last.  With a stale order the ring oscillator's solves drift to |X| ~ 1e30 while still reporting
+    convergence (the reference's UMFPACK / cuDSS pivot anew at every factorisation).  So every solve of the
+    continuation starts with a new analysis at its own first Jacobian (``B200Engine.lu_reanalyze_at``: one build +
+    the host analysis, milliseconds for the circuits that need a DC continuation)."""
     def nr_solve(X, vs, isrc, Q_prev, c0, gmin, gshunt, c1, d1, dQdt_prev, c2, Q_prev2):
+        if reanalyze:
+            engine.lu_reanalyze_at(X, vs, isrc, Q_prev, c0, gmin, gshunt)
         return engine.nr_solve(X, vs, isrc, Q_prev, c0, gmin, gshunt, c1, d1, dQdt_prev, c2, Q_prev2, None, None,
                                return_device=True)
     return nr_solve

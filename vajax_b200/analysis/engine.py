@@ -769,6 +769,23 @@ class B200Engine:
                 ("lim", lim[:self.total_limit_states]), ("mrc", mrc[:self.n_unknowns]))
         return tuple(t.cpu().numpy() if (want is None or nm in want) else None for nm, t in outs)
 
+    def lu_reanalyze_at(self, X, vsource_vals, isource_vals, Q_prev, integ_c0, gmin=1e-12, gshunt=0.0):
+        """New LU analysis (ordering + pivot sequence, ``vjx_lu_analyze``) from the Jacobian at the given point; the
+        Jacobian stays on the device.  The pivot order of a handle is fixed at its first factorisation
+        (north_star: "pivot order fixed at the DC operating point"), which holds along a transient but not along a
+        continuation that moves gmin / gshunt over ten decades (analysis/dc_op.py re-analyses at every solve)."""
+        self.prepare()
+        torch = self._torch()
+        csr = torch.zeros(max(self.nse, 1), dtype=torch.float64, device=f"cuda:{self.device}")
+        a = [self._dev(X), self._dev(vsource_vals), self._dev(isource_vals), self._dev(Q_prev)]
+        lib = vlib.load()
+        vlib.check(lib.vjx_build_system(
+            self.handle, self._p(a[0]), self._p(a[1]) if self.n_vs else None, self._p(a[2]) if self.n_is else None,
+            self._p(a[3]), float(integ_c0), float(gmin), float(gshunt), 0.0, 0.0, None, 0.0, None, None, 0,
+            self._p(csr), None, None, None, None, None, self._sarg()))
+        vlib.check(lib.vjx_lu_analyze(self.handle, self._p(csr), self._sarg()))
+        self._sync()
+
     # ---- Seam S1 -----------------------------------------------------------------------
     def lu_solve(self, csr_data, b):
         self.prepare()

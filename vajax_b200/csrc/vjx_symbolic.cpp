@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
+#include <set>
 
 // ---------------------------------------------------------------------------------------------
 // Approximate minimum degree on the quotient graph (Amestoy/Davis/Duff style bound, no
@@ -129,6 +131,99 @@ void vjx_amd_order(int n, const int* indptr, const int* indices, std::vector<int
   }
   std::sort(dense.begin(), dense.end(), [&](int a, int b) {
     if (adjv[a].size() != adjv[b].size()) return adjv[a].size() < adjv[b].size();
+    return a < b;
+  });
+  for (int v : dense) perm.push_back(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Minimum degree with dependency-depth tie-breaking (exact external degrees on explicit elimination
+// graphs).  Among the vertices of minimum degree the one whose row would sit lowest in the dependency
+// DAG of the factor is eliminated first: pend[v] = 1 + max level of the eliminated vertices whose clique
+// holds v, which is exactly the level the numeric kernels would give row v.  Minimum degree alone does
+// not care in which order it takes equal-degree vertices, and a first-in / last-out bucket (the AMD
+// above) grows long single-row chains out of that freedom: on the c6288-shaped core the factor has the
+// same fill (+1 %) but 105 dependency levels instead of 158 and a trailing chain of 48 single-row
+// levels instead of 118 (scripts/ordering_study.py, profiles/r2_ordering_notes.md).
+// Vertices above the dense threshold are ordered last, as in vjx_amd_order.
+// ---------------------------------------------------------------------------------------------
+void vjx_mdh_order(int n, const int* indptr, const int* indices, std::vector<int>& perm) {
+  perm.clear();
+  perm.reserve(n);
+  if (n == 0) return;
+  std::vector<std::vector<int>> adj(n);
+  {
+    std::vector<int> cnt(n, 0);
+    for (int i = 0; i < n; ++i)
+      for (int p = indptr[i]; p < indptr[i + 1]; ++p) {
+        int j = indices[p];
+        if (j != i && j >= 0 && j < n) { cnt[i]++; cnt[j]++; }
+      }
+    for (int i = 0; i < n; ++i) adj[i].reserve(cnt[i]);
+    for (int i = 0; i < n; ++i)
+      for (int p = indptr[i]; p < indptr[i + 1]; ++p) {
+        int j = indices[p];
+        if (j != i && j >= 0 && j < n) { adj[i].push_back(j); adj[j].push_back(i); }
+      }
+    for (int i = 0; i < n; ++i) {
+      auto& a = adj[i];
+      std::sort(a.begin(), a.end());
+      a.erase(std::unique(a.begin(), a.end()), a.end());
+    }
+  }
+  const int dense_thr = std::max(16, (int)(10.0 * std::sqrt((double)n)));
+  std::vector<char> state(n, 0);   // 0 alive, 1 eliminated, 3 dense (deferred)
+  std::vector<int> dense;
+  for (int i = 0; i < n; ++i)
+    if ((int)adj[i].size() > dense_thr) { state[i] = 3; dense.push_back(i); }
+  if (!dense.empty())
+    for (int i = 0; i < n; ++i) {
+      if (state[i] == 3) continue;
+      auto& a = adj[i];
+      a.erase(std::remove_if(a.begin(), a.end(), [&](int v) { return state[v] == 3; }), a.end());
+    }
+  std::vector<int> pend(n, 0);
+  struct Key {
+    int deg, pend, v;
+    bool operator<(const Key& o) const {
+      if (deg != o.deg) return deg < o.deg;
+      if (pend != o.pend) return pend < o.pend;
+      return v < o.v;
+    }
+  };
+  std::set<Key> heap;
+  for (int i = 0; i < n; ++i)
+    if (state[i] == 0) heap.insert(Key{(int)adj[i].size(), 0, i});
+  std::vector<int> merged;
+  while (!heap.empty()) {
+    const Key k = *heap.begin();
+    heap.erase(heap.begin());
+    const int p = k.v;
+    state[p] = 1;
+    perm.push_back(p);
+    std::vector<int> clique;
+    clique.swap(adj[p]);   // sorted, alive vertices only (eliminated ones are removed from every list below)
+    for (int u : clique) {
+      heap.erase(Key{(int)adj[u].size(), pend[u], u});
+      // adj[u] <- (adj[u] U clique) \ {u, p}
+      merged.clear();
+      merged.reserve(adj[u].size() + clique.size());
+      size_t a = 0, b = 0;
+      const auto& au = adj[u];
+      while (a < au.size() || b < clique.size()) {
+        int x;
+        if (b >= clique.size() || (a < au.size() && au[a] < clique[b])) x = au[a++];
+        else if (a >= au.size() || clique[b] < au[a]) x = clique[b++];
+        else { x = au[a]; ++a; ++b; }
+        if (x != u && x != p) merged.push_back(x);
+      }
+      adj[u].swap(merged);
+      pend[u] = std::max(pend[u], k.pend + 1);
+      heap.insert(Key{(int)adj[u].size(), pend[u], u});
+    }
+  }
+  std::sort(dense.begin(), dense.end(), [&](int a, int b) {
+    if (adj[a].size() != adj[b].size()) return adj[a].size() < adj[b].size();
     return a < b;
   });
   for (int v : dense) perm.push_back(v);
@@ -274,7 +369,11 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
       lip[a + 1] = (int)lix.size();
     }
     std::vector<int> pl;
-    vjx_amd_order(nc, lip.data(), lix.data(), pl);
+    // ordering of the core: minimum degree with dependency-depth tie-breaking (default), VJX_ORDER=amd for the
+    // approximate-minimum-degree ordering of round 1
+    const char* ord = getenv("VJX_ORDER");
+    if (ord && std::strcmp(ord, "amd") == 0) vjx_amd_order(nc, lip.data(), lix.data(), pl);
+    else vjx_mdh_order(nc, lip.data(), lix.data(), pl);
     if ((int)pl.size() != nc) { err = "ordering failed"; return -1; }
     for (int a = 0; a < nc; ++a) q.push_back(core_cols[pl[a]]);
   }

@@ -71,6 +71,9 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
 
 // Approximate minimum degree ordering on the pattern of A + A^T. perm[k] = k-th pivot.
 void vjx_amd_order(int n, const int* indptr, const int* indices, std::vector<int>& perm);
+// Exact minimum degree, ties broken by the dependency level the row would get (lowest first): same fill, a
+// markedly lower dependency DAG (the default ordering of the core; VJX_ORDER=amd selects the one above).
+void vjx_mdh_order(int n, const int* indptr, const int* indices, std::vector<int>& perm);
 
 // Host emulation of the GPU numeric algorithm (diagnostics for CPU-only tests of the symbolic
 // structures; never used by the product path): refactor + solve, returns max-norm residual.
