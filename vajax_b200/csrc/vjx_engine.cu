@@ -2945,7 +2945,7 @@ static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s) {
   // 159 when VJX_DT_CLUSTER pins a smaller configuration
   int dense_cap = VJX_DT_MAX;
   if (getenv("VJX_DT_CLUSTER") && atoi(getenv("VJX_DT_CLUSTER")) == 4) dense_cap = VJX_DB_MAX;
-  if (getenv("VJX_DT_ROWS")) dense_cap = std::min(dense_cap, atoi(getenv("VJX_DT_ROWS")));
+  if (getenv("VJX_DT_ROWS")) dense_cap = -std::min(dense_cap, std::max(atoi(getenv("VJX_DT_ROWS")), 1));   // < 0: forced size
   if (getenv("VJX_NO_DENSE_TAIL")) dense_cap = 0;
   // The linear solve only ever sees the NOI-enforced matrix (solver_factories.py:1268-1276 precedes every
   // linear_solve): the slots that enforce_noi rewrites to zero are STRUCTURAL zeros.  Leaving them in the

@@ -574,8 +574,24 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
   }
   // --- dense trailing block and execution order of the L parts (see vjx_symbolic.h)
   {
+    // dense_cap < 0: exactly the longest suffix of rows with an L part, up to |dense_cap| (VJX_DT_ROWS).
+    // dense_cap > 0: the block is the *chain* at the end of the elimination order - the suffix of rows that are alone
+    // in their dependency level (each waits for the one before it: a global-memory link per row in k_lu_rows, a
+    // barrier per row inside the block), rounded up to a whole panel of 16.  Rows in front of the chain have
+    // company in their level and cost less as ordinary rows than as rows of the block, whose L parts all finish
+    // late (c6288 / psp103w with the minimum-degree + depth ordering, chain of 48: 159 rows 163 us, 64 rows 147 us,
+    // 48 rows 143 us, 32 rows 146 us per refactorisation; gpurun_out/r2_w_variants.txt).
+    const bool forced = dense_cap < 0;
+    if (forced) dense_cap = -dense_cap;
     int nd = 0;
     while (nd < dense_cap && nd < n && S.lu_diag[n - 1 - nd] > S.lu_ptr[n - 1 - nd]) ++nd;
+    if (!forced && nd >= 16) {
+      std::vector<int> cl(S.n_levels_l, 0);
+      for (int i = 0; i < n; ++i) cl[S.level_l[i]]++;
+      int nc = 0;
+      while (nc < nd && cl[S.level_l[n - 1 - nc]] == 1) ++nc;
+      if (nc >= 16) nd = std::min(nd, (nc + 15) / 16 * 16);
+    }
     if (nd < 16) nd = 0;
     S.n_dense = nd;
     const int ds = n - nd;

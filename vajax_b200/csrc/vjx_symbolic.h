@@ -63,8 +63,9 @@ struct VjxSymbolic {
 };
 
 // Returns 0 on success; <0 and fills err otherwise.
-// dense_cap: upper bound on the rows of the dense trailing block (0 = none); out.n_dense is the longest
-// suffix of rows that all have an L part, up to that cap.
+// dense_cap: upper bound on the rows of the dense trailing block (0 = none).  > 0: out.n_dense is the chain of
+// single-row dependency levels at the end of the order (whole panels of 16, within the longest suffix of rows
+// that all have an L part); < 0: that longest suffix itself, up to |dense_cap|.
 int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const double* values,
                          double pivot_tol, bool build_update_stream, VjxSymbolic& out, std::string& err,
                          int dense_cap = 0);
