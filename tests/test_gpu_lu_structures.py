@@ -86,6 +86,26 @@ def test_bordered_matrix_dense_trailing_block(border):
     assert st["n"] == n0 + border
 
 
+@pytest.mark.parametrize("hv_min,border", [(1, 8), (4, 40), (8, 159), (16, 220), (48, 340)])
+def test_heavy_row_blocks_solve_the_same_system(hv_min, border, monkeypatch):
+    """The opt-in heavy-row path of k_lu_rows (VJX_HV_MIN: rows with that many k-steps are walked depth group by
+    depth group by three warps of a block, the fourth keeps taking ordinary rows) on bordered matrices - heavy rows in
+    front of and inside the dense trailing block: same residual / SuperLU bar as the default path, and the solution
+    of the default path up to the order of the sums."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(border)
+    n0 = 400
+    lead = sp.random(n0, n0, density=0.01, random_state=border)
+    B = sp.random(n0, border, density=0.3, random_state=border + 1)
+    C = sp.random(border, n0, density=0.3, random_state=border + 2)
+    D = sp.csr_matrix(np.ones((border, border)))
+    P = _dominant(sp.bmat([[lead, B], [C, D]], format="csr"), rng)
+    monkeypatch.setenv("VJX_HV_MIN", str(hv_min))
+    st = _solve_and_check(P, np.random.default_rng(7))
+    assert st["n"] == n0 + border
+
+
 @pytest.mark.parametrize("border", [5, 8, 9, 16, 31, 32, 33, 64, 100, 152, 153, 159, 200, 312, 319])
 def test_dense_block_kernels_agree_bit_for_bit(border, monkeypatch):
     """The blocked dense kernel on 1 / 2 / 4 CTAs (VJX_DT_CLUSTER) and the round-1 one-barrier-per-pivot kernel (0)

@@ -101,6 +101,28 @@ def test_symbolic_analysis_against_superlu(lib, n_nodes, n_vs, seed):
     assert st["nnz_lu"] >= A.nnz and st["n"] == A.shape[0]
 
 
+@pytest.mark.parametrize("n_nodes,n_vs,seed,hv_min,dense_cap", [
+    (40, 3, 2, 1, 0), (40, 3, 2, 4, 159), (400, 12, 3, 1, 0), (400, 12, 3, 4, 0), (400, 12, 3, 4, 159),
+    (400, 12, 3, 16, 48), (3000, 40, 4, 8, 159)])
+def test_heavy_row_program_against_superlu(lib, monkeypatch, n_nodes, n_vs, seed, hv_min, dense_cap):
+    """The heavy-row program (k-steps regrouped by dependency depth and target position, vjx_build_heavy) walked by
+    the host emulation of the thread block that executes it on the GPU: same solution as SuperLU, with every row that
+    has at least hv_min k-steps going through the program, with and without a dense trailing block."""
+    import scipy.sparse.linalg as spla
+
+    A = _mna_like(n_nodes, n_vs, seed)
+    b = np.random.default_rng(seed).normal(size=A.shape[0])
+    rc0, x0, st0 = _probe(lib, A, b)
+    monkeypatch.setenv("VJX_PROBE_HV_MIN", str(hv_min))
+    monkeypatch.setenv("VJX_PROBE_DENSE_CAP", str(dense_cap))
+    rc, x, st = _probe(lib, A, b)
+    assert rc == 0 and rc0 == 0
+    xr = spla.splu(A.tocsc()).solve(b)
+    assert np.max(np.abs(x - xr)) <= 1e-9 * max(1.0, np.max(np.abs(xr)))
+    # same factorisation up to the order of the sums
+    assert np.max(np.abs(x - x0)) <= 1e-10 * max(1.0, np.max(np.abs(x0)))
+
+
 def test_symbolic_peels_supply_rails(lib):
     """A rail node pinned by a vsource and touched by every device must leave the core: the branch
     row is a row singleton, the branch-current column a column singleton."""

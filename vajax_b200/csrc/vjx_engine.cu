@@ -67,7 +67,33 @@ struct NRStat {
   ull lim_ref_bits;
   unsigned epoch;    // count of NR iterations started (diagnostics)
   unsigned ticket_f, ticket_l, ticket_u;   // row tickets: k_lu_rows launch 1 / launch 2, k_lu_usolve
+  unsigned ticket_hf, ticket_hl, pad1;      // heavy-row tickets of the two k_lu_rows launches
 };
+
+// State every NR iteration starts from: per-iteration reductions cleared, LU row tickets reset.  Inside the NR loop
+// this is done by the kernels that are launched anyway (the loop's entry - k_nr_begin / k_pre_step - for the first
+// iteration, k_nr_update / k_nr_reduce_update at the end of an iteration for the next one); k_iter_begin is the
+// stand-alone form for the single builds and solves outside the loop.
+__device__ __forceinline__ void nr_clear_delta(NRStat* st) {
+  st->bad_delta = 0;
+  st->max_dv_bits = 0ULL;
+  st->lim_delta_bits = 0ULL;
+  st->lim_ref_bits = 0ULL;
+}
+__device__ __forceinline__ void nr_clear_tickets(NRStat* st) {
+  st->epoch += 1u;
+  st->ticket_f = 0u;
+  st->ticket_l = 0u;
+  st->ticket_u = 0u;
+  st->ticket_hf = 0u;
+  st->ticket_hl = 0u;
+}
+__device__ __forceinline__ void nr_clear_iter(NRStat* st) {
+  st->bad_res = 0;
+  st->max_f_bits = 0ULL;
+  nr_clear_delta(st);
+  nr_clear_tickets(st);
+}
 
 struct TranScalars {
   double t, dt, t_stop, max_dt, min_dt_used, max_dt_used;
@@ -108,6 +134,11 @@ struct LUDev {
   const long long* upd_ptr;    // [nnz+1] start of each L entry's scatter list
   const int* upd_pos;          // position inside row i of each column of U(k,:)
   long long n_upd_prefetch;    // entries of upd_pos k_lu_load prefetches into L2 (0: the description is larger than L2)
+  // heavy rows (vjx_symbolic.h, Heavy): walked depth by depth by a whole thread block
+  const int* hv_prog;
+  const long long* hv_off;
+  const int* hv_rows;
+  const unsigned char* hv_flag; // per position of order_f: the row is a heavy row (the warps skip it)
   unsigned long long* ts;      // optional per-row completion timestamps (globaltimer, debug probe)
   double* val;
   double* inv_diag;
@@ -530,6 +561,8 @@ __global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restr
   const long long nt = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const double sent = bits_f64(VJX_SENTINEL);
+  // (the reductions of the Newton update that follows this solve: their last reader was the previous k_nr_update)
+  if (t0 == 0) nr_clear_delta(st);
   // When the static description of the factorisation fits in L2, pull it there now, with full-grid coalesced
   // prefetches: the row kernels read it inside dependency chains, where a miss to HBM costs a k-step its
   // whole latency budget (first NR iteration after anything evicted it; free when it is resident already).
@@ -594,11 +627,210 @@ __global__ void __launch_bounds__(256) k_lu_load(LUDev lu, const double* __restr
 #endif
 extern __shared__ double vjx_lu_smem[];
 
-template <int UG, bool PIPE, int RC>
+// Heavy rows: the first n_hv_cta thread blocks of a k_lu_rows launch take the rows with many k-steps, one row per
+// BLOCK, and walk them group by group (vjx_symbolic.h, Heavy): the k-steps of one dependency depth are independent,
+// so every warp forms their multipliers at once (lane s: l_s = w[kpos_s] / U(k_s,k_s), redundantly in each warp - no
+// hand-over between warps), then the warps share the group's records: a lane owns one position of the row and applies
+// its <= 4 contributions -l_slot * U in ascending k, l_slot by shuffle.  One barrier per group instead of ~550
+// cycles of dependent latency per k-step.  The row lives in the block's whole shared memory (all four warps'
+// working vectors); L entries go straight to global memory (w[kpos] stays the undivided value the other warps still
+// read).  The program text is read through L1 (read-only path) and touched a few KB ahead, the U values / pivots
+// of the next record / group are requested before the current one is applied.  Readiness is the sentinel protocol
+// of the other rows: polling is convergent per warp.
+#define VJX_HV_PF_INTS 6144
+#define VJX_HV_WARPS 3   // of the block's 4: the last warp keeps taking ordinary rows, so a launch makes progress even
+                         // if only its heavy-row blocks are resident (several handles sharing the GPU)
+__device__ __forceinline__ void hv_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * VJX_HV_WARPS) : "memory"); }
+// Pulls a line of the program into L1 ahead of its use: a real read-only load whose value is folded into a checksum
+// one call later (ptxas deletes a load nobody consumes; the deferred use never waits for it).
+__device__ __forceinline__ void hv_touch(const int* p, unsigned& acc, unsigned& last) {
+  acc ^= last;
+  last = (unsigned)__ldg(p);
+}
+
+struct HvRec {
+  int pos, R;
+  int e[4];
+  ull u[4];
+};
+
+__device__ __forceinline__ void hv_fetch(const LUDev& lu, const int* G, int r, int lane, HvRec& o) {
+  const int info = __ldg(G + VJX_HV_GRP_INTS + r);
+  const int* Rp = G + (info & 0x0fffffff);
+  o.R = info >> 28;
+  o.pos = __ldg(Rp + lane);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o.e[j] = -1;
+    o.u[j] = 0ULL;
+    if (j < o.R) {
+      o.e[j] = __ldg(Rp + 32 + 32 * j + lane);
+      if (o.e[j] != -1) o.u[j] = ld_poll_u64(lu.val + (((unsigned)o.e[j]) >> 5));
+    }
+  }
+}
+
+__device__ __forceinline__ void lu_heavy_role(const LUDev& lu, const double* __restrict__ csr, const double* __restrict__ b,
+                                              double scale, const unsigned char* __restrict__ zero_mask, NRStat* st,
+                                              unsigned* ticket_h, int hv_begin, int hv_end) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* const w = vjx_lu_smem;
+  __shared__ unsigned s_tk;
+  unsigned pf_acc = 0u, pf_last = 0u;
+  while (true) {
+    hv_bar();
+    if (tid == 0) s_tk = atomicAdd(ticket_h, 1u);
+    hv_bar();
+    const unsigned tk = s_tk;
+    if (tk >= (unsigned)(hv_end - hv_begin)) {
+      if ((pf_acc ^ pf_last) == 0x9e3779b9u && tk == 0xffffffffu) atomicOr(&st->error, 16);   // (keeps the touches alive)
+      break;
+    }
+    const int hidx = hv_begin + (int)tk;
+    const int i = lu.hv_rows[hidx];
+    const int rb = lu.ptr[i], dg = lu.diag[i], re = lu.ptr[i + 1];
+    const int* P = lu.hv_prog + lu.hv_off[hidx];
+    const int* const Pend = lu.hv_prog + lu.hv_off[hidx + 1];
+    const int* pf = P;
+    {
+      const int* lim = P + VJX_HV_PF_INTS < Pend ? P + VJX_HV_PF_INTS : Pend;
+      for (const int* q = pf + tid * 32; q < lim; q += 32 * 32 * VJX_HV_WARPS) hv_touch(q, pf_acc, pf_last);
+      pf = lim;
+    }
+    for (int p = rb + tid; p < re; p += 32 * VJX_HV_WARPS) {
+      const int sidx = lu.src[p];
+      w[p - rb] = sidx >= 0 ? csr[sidx] : 0.0;
+    }
+    double yacc = 0.0, l = 0.0;
+    int nrec = 0, keep = 0, gints = 0, kpos = -1, kk = 0;
+    ull inv_b = 0ULL, y_b = 0ULL;
+    HvRec la;
+    la.pos = -1; la.R = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { la.e[j] = -1; la.u[j] = 0ULL; }
+    if (P < Pend) {
+      nrec = __ldg(P); keep = __ldg(P + 1); gints = __ldg(P + 3);
+      kpos = __ldg(P + 4 + lane); kk = __ldg(P + 36 + lane);
+      if (kpos >= 0) { inv_b = ld_poll_u64(lu.inv_diag + kk); y_b = ld_poll_u64(lu.y + kk); }
+      if (warp < nrec) hv_fetch(lu, P, warp, lane, la);
+    }
+    hv_bar();
+    while (P < Pend) {
+      {
+        const int* lim = P + VJX_HV_PF_INTS < Pend ? P + VJX_HV_PF_INTS : Pend;
+        for (const int* q = pf + tid * 32; q < lim; q += 32 * 32 * VJX_HV_WARPS) hv_touch(q, pf_acc, pf_last);
+        if (lim > pf) pf = lim;
+      }
+      if (!keep) {
+        unsigned spins = 0;
+        while (true) {
+          bool ok = true;
+          if (kpos >= 0) {
+            if (inv_b == VJX_SENTINEL) { inv_b = ld_poll_u64(lu.inv_diag + kk); ok = false; }
+            if (y_b == VJX_SENTINEL) { y_b = ld_poll_u64(lu.y + kk); ok = false; }
+          }
+          if (!__all_sync(0xffffffffu, ok)) {
+            // still waiting for a row of this group: refresh, in the same round trip, the U values of the record that
+            // is applied next (a row publishes its U part before its pivot: they are there when the pivot is)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (la.e[j] != -1 && la.u[j] == VJX_SENTINEL) la.u[j] = ld_poll_u64(lu.val + (((unsigned)la.e[j]) >> 5));
+            if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+            continue;
+          }
+          break;
+        }
+        l = 0.0;
+        if (kpos >= 0) {
+          l = w[kpos] * bits_f64(inv_b);
+          if (warp == 0) {
+            lu.val[rb + kpos] = l;
+            yacc = __fma_rn(-l, bits_f64(y_b), yacc);
+          }
+        }
+      }
+      // header of the next group: its pivots / y are requested now, one group ahead
+      const int* Pn = P + gints;
+      int nrec_n = 0, keep_n = 0, gints_n = 0, kpos_n = -1, kk_n = 0;
+      ull inv_n = 0ULL, y_n = 0ULL;
+      if (Pn < Pend) {
+        nrec_n = __ldg(Pn); keep_n = __ldg(Pn + 1); gints_n = __ldg(Pn + 3);
+        kpos_n = __ldg(Pn + 4 + lane); kk_n = __ldg(Pn + 36 + lane);
+        if (kpos_n >= 0) { inv_n = ld_poll_u64(lu.inv_diag + kk_n); y_n = ld_poll_u64(lu.y + kk_n); }
+      }
+      for (int r = warp; r < nrec; r += VJX_HV_WARPS) {
+        HvRec c = la;
+        if (r + VJX_HV_WARPS < nrec) hv_fetch(lu, P, r + VJX_HV_WARPS, lane, la);
+        else if (Pn < Pend && warp < nrec_n) hv_fetch(lu, Pn, warp, lane, la);
+        unsigned spins = 0;
+        while (true) {
+          bool ok = true;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c.e[j] != -1 && c.u[j] == VJX_SENTINEL) { c.u[j] = ld_poll_u64(lu.val + (((unsigned)c.e[j]) >> 5)); ok = false; }
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+        }
+        double acc = c.pos >= 0 ? w[c.pos] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < c.R) {   // warp-uniform
+            const double lv = __shfl_sync(0xffffffffu, l, c.e[j] & 31);
+            if (c.e[j] != -1) acc = __fma_rn(-lv, bits_f64(c.u[j]), acc);
+          }
+        }
+        if (c.pos >= 0) w[c.pos] = acc;
+      }
+      if (warp >= nrec && Pn < Pend && warp < nrec_n) hv_fetch(lu, Pn, warp, lane, la);
+      hv_bar();
+      P = Pn; nrec = nrec_n; keep = keep_n; gints = gints_n; kpos = kpos_n; kk = kk_n; inv_b = inv_n; y_b = y_n;
+    }
+    // y of the row: the lanes' partial sums in lane order (fixed), on top of the right-hand side
+    double ysum = 0.0;
+    if (warp == 0) {
+      if (lane == 0) {
+        const int r = lu.perm_r[i];
+        ysum = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
+      }
+      for (int sl = 0; sl < 32; ++sl) {
+        const double ys = __shfl_sync(0xffffffffu, yacc, sl);
+        if (lane == 0) ysum += ys;
+      }
+    }
+    if (i >= lu.dense_start) {
+      const int lend = lu.dense_lstop[i - lu.dense_start];
+      double* srow = lu.dense + (size_t)(i - lu.dense_start) * (lu.n_dense + 1);
+      for (int p = lend + tid; p < re; p += 32 * VJX_HV_WARPS) srow[lu.col[p] - lu.dense_start] = w[p - rb];
+      if (tid == 0) {
+        srow[lu.n_dense] = ysum;
+        if (lu.ts) lu.ts[lu.n + 8 + (i - lu.dense_start)] = global_ns();
+      }
+    } else {
+      const double d = w[dg - rb];
+      for (int p = dg + 1 + tid; p < re; p += 32 * VJX_HV_WARPS) st_pub_f64(lu.val + p, w[p - rb]);
+      if (tid == 0) {
+        if (d == 0.0 || d != d) atomicOr(&st->error, 2);
+        st_pub_f64(lu.y + i, ysum);
+        st_pub_f64(lu.inv_diag + i, 1.0 / d);
+        lu.val[dg] = d;
+        if (lu.ts) lu.ts[i] = global_ns();
+      }
+    }
+  }
+}
+
+template <int UG, bool PIPE, int RC, bool HV>
 __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, const double* __restrict__ csr,
                                                                     const double* __restrict__ b, double scale,
                                                                     const unsigned char* __restrict__ zero_mask, NRStat* st,
-                                                                    unsigned* ticket, int t_begin, int t_end, int rowbuf) {
+                                                                    unsigned* ticket, int t_begin, int t_end, int rowbuf,
+                                                                    int n_hv_cta, int hv_begin, int hv_end, unsigned* ticket_h) {
+  if constexpr (HV) {   // (a launch without heavy rows keeps its register count: the wide launch lives on occupancy)
+    if ((int)blockIdx.x < n_hv_cta && (threadIdx.x >> 5) < VJX_HV_WARPS) {
+      lu_heavy_role(lu, csr, b, scale, zero_mask, st, ticket_h, hv_begin, hv_end);
+      return;
+    }
+  }
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   double* const wsm = vjx_lu_smem + (size_t)warp * rowbuf;
@@ -607,6 +839,7 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
     if (lane == 0) tk = atomicAdd(ticket, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= (unsigned)(t_end - t_begin)) break;
+    if (lu.hv_flag[t_begin + tk]) continue;   // taken by a heavy-row block
     const int i = lu.order_f[t_begin + tk];
     const int rb = lu.ptr[i], dg = lu.diag[i], re = lu.ptr[i + 1];
     double* w = (re - rb) <= rowbuf ? wsm : lu.scratch + ((size_t)blockIdx.x * VJX_FACTOR_WARPS + warp) * lu.max_lrow;
@@ -1544,22 +1777,10 @@ __global__ void k_nr_begin(NRStat* st, double* ctl, int max_iter, int reset_iter
   st->max_iter = max_iter;
   st->cont = 1;
   st->error = 0;   // a watchdog bit of an earlier call must not fail this one
+  nr_clear_iter(st);
 }
 
-// Runs at the head of every NR iteration: clears the per-iteration reductions and resets the LU row
-// tickets.
-__global__ void k_iter_begin(NRStat* st) {
-  st->bad_res = 0;
-  st->bad_delta = 0;
-  st->max_f_bits = 0ULL;
-  st->max_dv_bits = 0ULL;
-  st->lim_delta_bits = 0ULL;
-  st->lim_ref_bits = 0ULL;
-  st->epoch += 1u;
-  st->ticket_f = 0u;
-  st->ticket_l = 0u;
-  st->ticket_u = 0u;
-}
+__global__ void k_iter_begin(NRStat* st) { nr_clear_iter(st); }
 
 struct UpdateArgs {
   int n_unknowns, n_vs, n_total, n_lim;
@@ -1642,6 +1863,93 @@ __global__ void k_nr_update(UpdateArgs a, double* ctl, double* limit_state, cuda
     int cont = (!conv && (it + 1) < st->max_iter) ? 1 : 0;
     st->cont = cont;
     if (use_handle) cudaGraphSetConditional(handle, cont);
+    // state of the next iteration (the residual's reductions of the LAST iteration stay readable: max_f of the solve;
+    // max_dv / the limit reductions are still being read by the other blocks of this launch: k_lu_load clears them)
+    if (cont) { st->bad_res = 0; st->max_f_bits = 0ULL; }
+    nr_clear_tickets(st);
+  }
+}
+
+// k_delta_reduce + k_nr_update as ONE block (circuits up to VJX_NRU_MAX unknowns: the reductions stay in shared
+// memory, no second launch; same values, same convergence logic).
+#define VJX_NRU_THREADS 1024
+#define VJX_NRU_MAX 65536
+__global__ void __launch_bounds__(VJX_NRU_THREADS) k_nr_reduce_update(UpdateArgs a, double* ctl, double* limit_state,
+                                                                      cudaGraphConditionalHandle handle, int use_handle) {
+  __shared__ double s_mv[32], s_ld[32], s_lr[32];
+  __shared__ int s_bad[32];
+  const int n_aug = a.n_unknowns + a.n_vs;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  int bad = 0;
+  double mv = 0.0, ld = 0.0, lr = 0.0;
+  for (int i = tid; i < n_aug; i += VJX_NRU_THREADS) {
+    const double d = a.delta[i];
+    double cd = (i < a.n_unknowns) ? d * a.damping : d;
+    const double xr = a.X[i + 1];
+    const double tol = fmax(fabs(xr) * a.reltol, (i < a.n_unknowns) ? a.vntol : a.abstol);
+    if (!a.delta_mask[i]) cd = 0.0;
+    if (!(fabs(cd) < tol)) bad = 1;
+    if (i < a.n_unknowns) {
+      const double ad = fabs(d);
+      mv = (ad != ad || mv != mv) ? qnan : fmax(mv, ad);
+    }
+  }
+  for (int i = tid; i < a.n_lim; i += VJX_NRU_THREADS) {
+    ld = fmax(ld, fabs(a.limit_out[i] - a.limit_in[i]));
+    lr = fmax(lr, fabs(a.limit_in[i]));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    const double t = __shfl_xor_sync(0xffffffffu, mv, o);
+    mv = (mv != mv || t != t) ? qnan : fmax(mv, t);
+    ld = fmax(ld, __shfl_xor_sync(0xffffffffu, ld, o));
+    lr = fmax(lr, __shfl_xor_sync(0xffffffffu, lr, o));
+  }
+  if (lane == 0) { s_bad[wp] = bad; s_mv[wp] = mv; s_ld[wp] = ld; s_lr[wp] = lr; }
+  __syncthreads();
+  bad = 0; mv = 0.0; ld = 0.0; lr = 0.0;
+  for (int q = 0; q < VJX_NRU_THREADS / 32; ++q) {
+    bad |= s_bad[q];
+    const double t = s_mv[q];
+    mv = (mv != mv || t != t) ? qnan : fmax(mv, t);
+    ld = fmax(ld, s_ld[q]);
+    lr = fmax(lr, s_lr[q]);
+  }
+  // (max |dV| as the two-kernel path reads it back: a NaN anywhere is the canonical quiet NaN)
+  const double scale = fmin(1.0, a.max_step / fmax(mv, 1e-30));
+  for (int i = tid; i < n_aug; i += VJX_NRU_THREADS) {
+    const double d = a.delta[i];
+    double x = a.X[i + 1];
+    if (i < a.n_unknowns) {
+      x = x + d * scale * a.damping;
+      if (a.is_noi[i + 1]) x = 0.0;
+    } else {
+      x = x + d;
+    }
+    a.X[i + 1] = x;
+  }
+  for (int i = tid; i < a.n_lim; i += VJX_NRU_THREADS) limit_state[i] = a.limit_out[i];
+  if (tid == 0) {
+    NRStat* st = a.st;
+    st->bad_delta = bad;
+    st->max_dv_bits = (mv != mv) ? 0x7ff8000000000000ULL : (mv > 0.0 ? (ull)__double_as_longlong(mv) : 0ULL);
+    st->lim_delta_bits = ld > 0.0 ? (ull)__double_as_longlong(ld) : 0ULL;
+    st->lim_ref_bits = lr > 0.0 ? (ull)__double_as_longlong(lr) : 0ULL;
+    const int it = st->iter;
+    bool conv = (st->bad_res == 0) && (it == 0 || bad == 0);
+    if (a.n_lim > 0) {
+      const double lref = fmax(lr * a.reltol, a.vntol);
+      conv = conv && (ld < lref) && (it >= 1);
+    }
+    st->converged = conv ? 1 : 0;
+    st->iter = it + 1;
+    ctl[VJX_CTL_ITER] = (double)(it + 1);
+    const int cont = (!conv && (it + 1) < st->max_iter) ? 1 : 0;
+    st->cont = cont;
+    if (use_handle) cudaGraphSetConditional(handle, cont);
+    if (cont) { st->bad_res = 0; st->max_f_bits = 0ULL; }
+    nr_clear_tickets(st);
   }
 }
 
@@ -1784,6 +2092,7 @@ __global__ void k_pre_step(StepArgs a, cudaGraphConditionalHandle nr_handle, int
     a.st->converged = 0;
     a.st->max_iter = a.o.tran_itl;
     a.st->cont = 1;
+    nr_clear_iter(a.st);
     s->attempts += 1;
     if (use_handle) cudaGraphSetConditional(nr_handle, 1);
   }
@@ -2080,6 +2389,11 @@ struct vjx_handle {
   // small working vector and many warps per SM, then the narrow high levels with long rows)
   int lu_nseg = 0, lu_seg_t0[2] = {0, 0}, lu_seg_t1[2] = {0, 0}, lu_seg_rowbuf[2] = {0, 0}, lu_seg_grid[2] = {0, 0};
   DevBuf<int> lu_order_f, lu_long_u;
+  // heavy rows of each launch: blocks [0, lu_seg_hv_cta) walk rows lu_hv_rows[lu_seg_hv0 .. lu_seg_hv1)
+  int lu_seg_hv_cta[2] = {0, 0}, lu_seg_hv0[2] = {0, 0}, lu_seg_hv1[2] = {0, 0};
+  DevBuf<int> lu_hv_prog, lu_hv_rows;
+  DevBuf<long long> lu_hv_off;
+  DevBuf<unsigned char> lu_hv_flag;
   int lu_grid_u = 0;
   DevBuf<long long> lu_upd_ptr;
   DevBuf<int> lu_upd_pos;
@@ -2107,7 +2421,7 @@ struct vjx_handle {
   // the Jacobian stamp and the residual of an NR iteration both depend on the model kernels only: the residual runs
   // on a side stream between two events (a parallel branch once captured into the iteration graph)
   cudaStream_t fork_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
   void* pinned = nullptr;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the loop launch inside vjx_tran_run
@@ -2135,6 +2449,8 @@ vjx_handle::~vjx_handle() {
   if (fork_stream) cudaStreamDestroy(fork_stream);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
+  if (ev_fork2) cudaEventDestroy(ev_fork2);
+  if (ev_join2) cudaEventDestroy(ev_join2);
   if (pinned) cudaFreeHost(pinned);
 }
 
@@ -2550,6 +2866,10 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
     CK(cudaStreamCreateWithFlags(&h->fork_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    if (!getenv("VJX_NO_EVAL_FORK")) {
+      CK(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
+    }
   }
   CK(cudaHostAlloc(&h->pinned, 4096, cudaHostAllocDefault));
   CK(cudaStreamSynchronize(0));   // allocations are zero-filled on the legacy stream (not a device-wide sync: see vjx_destroy)
@@ -2604,7 +2924,21 @@ static int launch_eval(vjx_handle* h, const BuildPtrs& b, cudaStream_t s) {
     k_isrc<<<(2 * h->n_is + 127) / 128, 128, 0, s>>>(2 * h->n_is, h->isrc_dest.p, b.isrc, h->vsorted.p);
     h->launches++;
   }
-  for (ModelState* ms : h->models) {
+  // The model with the most work runs on the caller's stream, the others (a handful of resistors or diodes beside ten
+  // thousand MOSFETs: launches of a few microseconds each) on the side stream beside it - a parallel branch of the
+  // captured iteration graph, like the residual beside the stamp.  They write disjoint parts of jsorted / vsorted.
+  size_t main_m = 0;
+  for (size_t m = 1; m < h->models.size(); ++m)
+    if ((double)h->models[m]->n_dev * (h->models[m]->J + h->models[m]->R + 1) >
+        (double)h->models[main_m]->n_dev * (h->models[main_m]->J + h->models[main_m]->R + 1)) main_m = m;
+  const bool side = h->fork_stream && h->ev_fork2 && h->models.size() > 1;
+  if (side) {
+    CK(cudaEventRecord(h->ev_fork2, s));
+    CK(cudaStreamWaitEvent(h->fork_stream, h->ev_fork2, 0));
+  }
+  for (size_t m = 0; m < h->models.size(); ++m) {
+    ModelState* ms = h->models[m];
+    cudaStream_t ms_stream = (side && m != main_m) ? h->fork_stream : s;
     VjxEvalArgs a;
     a.n_dev = ms->n_dev;
     a.V = b.X;
@@ -2619,9 +2953,13 @@ static int launch_eval(vjx_handle* h, const BuildPtrs& b, cudaStream_t s) {
     a.jsorted = (b.csr || h->full_final_eval) ? h->jsorted.p : nullptr;   // no Jacobian wanted: residual-side kernel
     a.vdest = ms->vdest.p;
     a.vsorted = h->vsorted.p;
-    int rc = ms->eval(&a, s);
+    int rc = ms->eval(&a, ms_stream);
     if (rc != 0) return fail(VJX_ERR_CUDA, "model eval launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     h->launches++;
+  }
+  if (side) {
+    CK(cudaEventRecord(h->ev_join2, h->fork_stream));
+    CK(cudaStreamWaitEvent(s, h->ev_join2, 0));
   }
   return VJX_OK;
 }
@@ -2681,10 +3019,12 @@ static void launch_dense(vjx_handle* h, const LUDev& lud, double* x, cudaStream_
 
 static int ensure_lu(vjx_handle* h, const double* csr_dev, cudaStream_t s);
 
-typedef void (*lu_rows_fn)(LUDev, const double*, const double*, double, const unsigned char*, NRStat*, unsigned*, int, int, int);
-static lu_rows_fn lu_rows_kernel(int rowbuf, bool two_launches) {
-  if (rowbuf > 1024) return k_lu_rows<VJX_UG, true, 1>;
-  return two_launches ? k_lu_rows<VJX_UG, false, 1> : k_lu_rows<VJX_UG, false, 2>;
+typedef void (*lu_rows_fn)(LUDev, const double*, const double*, double, const unsigned char*, NRStat*, unsigned*, int, int, int,
+                           int, int, int, unsigned*);
+static lu_rows_fn lu_rows_kernel(int rowbuf, bool two_launches, bool heavy) {
+  if (rowbuf > 1024) return heavy ? k_lu_rows<VJX_UG, true, 1, true> : k_lu_rows<VJX_UG, true, 1, false>;
+  if (two_launches) return heavy ? k_lu_rows<VJX_UG, false, 1, true> : k_lu_rows<VJX_UG, false, 1, false>;
+  return heavy ? k_lu_rows<VJX_UG, false, 2, true> : k_lu_rows<VJX_UG, false, 2, false>;
 }
 
 static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr, const double* b, double scale,
@@ -2692,10 +3032,11 @@ static void launch_lu_factor(vjx_handle* h, const LUDev& lud, const double* csr,
   k_lu_load<<<h->lu_grid_load, 256, 0, s>>>(lud, csr, b, scale, zero_mask, h->st.p);
   h->launches += 1;
   for (int g = 0; g < h->lu_nseg; ++g) {
-    auto kfn = lu_rows_kernel(h->lu_seg_rowbuf[g], h->lu_nseg > 1 || h->lu_seg_rowbuf[g] > 1024);
+    auto kfn = lu_rows_kernel(h->lu_seg_rowbuf[g], h->lu_nseg > 1 || h->lu_seg_rowbuf[g] > 1024, h->lu_seg_hv_cta[g] > 0);
     kfn<<<h->lu_seg_grid[g], 32 * VJX_FACTOR_WARPS, h->lu_seg_rowbuf[g] * VJX_FACTOR_WARPS * sizeof(double), s>>>(
         lud, csr, b, scale, zero_mask, h->st.p, g == 0 ? &h->st.p->ticket_f : &h->st.p->ticket_l, h->lu_seg_t0[g],
-        h->lu_seg_t1[g], h->lu_seg_rowbuf[g]);
+        h->lu_seg_t1[g], h->lu_seg_rowbuf[g], h->lu_seg_hv_cta[g], h->lu_seg_hv0[g], h->lu_seg_hv1[g],
+        g == 0 ? &h->st.p->ticket_hf : &h->st.p->ticket_hl);
     h->launches += 1;
   }
   if (lud.n_dense > 0) {
@@ -2725,8 +3066,7 @@ static UpdateArgs make_update_args(vjx_handle* h, double* X, const double* limit
 // One NR iteration on (X, limit_w): reference _nr_body_common.
 static int launch_nr_iteration(vjx_handle* h, const BuildPtrs& b, double* X, cudaGraphConditionalHandle handle,
                                int use_handle, cudaStream_t s) {
-  k_iter_begin<<<1, 1, 0, s>>>(h->st.p);
-  h->launches++;
+  // (no k_iter_begin: the loop's entry kernel / the previous iteration's update left the state cleared)
   int rc = launch_eval(h, b, s);
   if (rc) return rc;
   if (h->fork_stream) {
@@ -2742,9 +3082,16 @@ static int launch_nr_iteration(vjx_handle* h, const BuildPtrs& b, double* X, cud
   }
   launch_lu(h, h->csr.p, h->f.p, -1.0, h->noi_row_mask.p, h->delta.p, s);
   UpdateArgs ua = make_update_args(h, X, b.limit_in, b.limit_out);
-  k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua);
-  k_nr_update<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua, h->ctl.p, h->limit_w.p, handle, use_handle);
-  h->launches += 2;
+  // (opt-in: one launch less, 7.6 instead of 8.6 us timed alone, but the c6288 step got 5 % SLOWER with it -
+  // 0.804 against 0.762 ms over 200 steps, gpurun_out/r2_z_variants.txt - so the two-kernel form stays the default)
+  if (std::max(h->n_aug, h->total_lim) <= VJX_NRU_MAX && getenv("VJX_NRU_MERGE")) {
+    k_nr_reduce_update<<<1, VJX_NRU_THREADS, 0, s>>>(ua, h->ctl.p, h->limit_w.p, handle, use_handle);
+    h->launches += 1;
+  } else {
+    k_delta_reduce<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua);
+    k_nr_update<<<grid_for(h, std::max(h->n_aug, h->total_lim)), 256, 0, s>>>(ua, h->ctl.p, h->limit_w.p, handle, use_handle);
+    h->launches += 2;
+  }
   return VJX_OK;
 }
 
@@ -2900,8 +3247,10 @@ static int upload_symbolic(vjx_handle* h) {
       // ring slots of 2 chunks (64 U entries per prefetched step) cost 24 registers: worth it when one launch
       // holds everything and the heaviest rows set its duration (c6288: rows phase 113 -> 108 us), not when the
       // wide launch lives on occupancy (mul64: 1.54 -> 1.62 ms)
-      auto kfn = lu_rows_kernel(rowbuf, n_cut < n);
+      auto kfn = lu_rows_kernel(rowbuf, n_cut < n, false);
       CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kRowbufCap * VJX_FACTOR_WARPS * (int)sizeof(double)));
+      CK(cudaFuncSetAttribute(lu_rows_kernel(rowbuf, n_cut < n, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kRowbufCap * VJX_FACTOR_WARPS * (int)sizeof(double)));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 32 * VJX_FACTOR_WARPS, smem));
       occ = std::max(1, occ);
@@ -2917,6 +3266,67 @@ static int upload_symbolic(vjx_handle* h) {
     if (max_lrow > 0) {
       CK(h->lu_scratch.alloc((size_t)max_grid * VJX_FACTOR_WARPS * (size_t)max_lrow));
       L.scratch = h->lu_scratch.p;
+    }
+    // Heavy rows (vjx_symbolic.h, Heavy): rows with at least VJX_HV_MIN k-steps of their own that fit the block's
+    // shared memory go to the first blocks of their launch, one row per block.  The program costs ~4 bytes per
+    // contribution / fill: the threshold doubles until it fits VJX_HV_MAX_MB (default 192).  OFF by default
+    // (VJX_HV_MIN unset or 0): measured slower than the k-sequential warps on both benchmark circuits - c6288
+    // 203 vs 144 us, mul64 2.0 vs 1.5 ms per refactorisation - because after the minimum-degree + depth ordering the
+    // rows phase is bound by the chain of dependency levels (~1.9 us per level through L2), not by the k-steps of a
+    // row, and a block with a barrier per group crosses a level later than a warp does (profiles/r2_heavy_rows.md).
+    {
+      int hv_min = getenv("VJX_HV_MIN") ? atoi(getenv("VJX_HV_MIN")) : 0;
+      const double max_mb = getenv("VJX_HV_MAX_MB") ? atof(getenv("VJX_HV_MAX_MB")) : 192.0;
+      std::vector<unsigned char> flag((size_t)std::max(n, 1), 0);
+      std::vector<int> rows_all;
+      int seg_n[2] = {0, 0};
+      while (true) {
+        rows_all.clear();
+        for (int g = 0; g < h->lu_nseg; ++g) {
+          if (g + 1 < h->lu_nseg) { seg_n[g] = 0; continue; }   // (the wide launch of two keeps to warps)
+          std::vector<int> r = vjx_select_heavy(S, h->lu_seg_t0[g], h->lu_seg_t1[g], hv_min, VJX_HV_WARPS * h->lu_seg_rowbuf[g]);
+          seg_n[g] = (int)r.size();
+          rows_all.insert(rows_all.end(), r.begin(), r.end());
+        }
+        vjx_build_heavy(S, rows_all);
+        if (rows_all.empty() || 4e-6 * (double)S.heavy.prog.size() <= max_mb) break;
+        hv_min *= 2;
+      }
+      std::vector<int> pos_of_row((size_t)n, -1);
+      for (int t = 0; t < n; ++t) pos_of_row[S.order_f[t]] = t;
+      for (int i : rows_all) flag[(size_t)pos_of_row[i]] = 1;
+      int o = 0;
+      for (int g = 0; g < 2; ++g) {
+        h->lu_seg_hv0[g] = o;
+        h->lu_seg_hv1[g] = o + (g < h->lu_nseg ? seg_n[g] : 0);
+        o = h->lu_seg_hv1[g];
+        h->lu_seg_hv_cta[g] = 0;
+        if (g >= h->lu_nseg || seg_n[g] == 0) continue;
+        // every heavy row a block of its own while that leaves two thirds of the resident blocks to the other rows
+        // (the heavy variant of the kernel needs more registers: its own occupancy sizes the launch)
+        int occ_hv = 1;
+        auto kfn = lu_rows_kernel(h->lu_seg_rowbuf[g], h->lu_nseg > 1 || h->lu_seg_rowbuf[g] > 1024, true);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_hv, kfn, 32 * VJX_FACTOR_WARPS,
+                                                         h->lu_seg_rowbuf[g] * VJX_FACTOR_WARPS * (int)sizeof(double)));
+        const int cap = std::max(1, h->sm_count * std::max(1, occ_hv) / grid_div);
+        h->lu_seg_grid[g] = std::max(1, std::min(h->lu_seg_grid[g], cap));
+        h->lu_seg_hv_cta[g] = std::max(1, std::min(seg_n[g], h->lu_seg_grid[g] / 3));
+      }
+      std::vector<int> prog(S.heavy.prog), rows(rows_all);
+      std::vector<long long> off(S.heavy.off);
+      if (prog.empty()) prog.push_back(0);
+      if (rows.empty()) rows.push_back(0);
+      CK(h->lu_hv_prog.upload(prog));
+      CK(h->lu_hv_rows.upload(rows));
+      CK(h->lu_hv_off.upload(off));
+      CK(h->lu_hv_flag.upload(flag));
+      L.hv_prog = h->lu_hv_prog.p; L.hv_off = h->lu_hv_off.p; L.hv_rows = h->lu_hv_rows.p; L.hv_flag = h->lu_hv_flag.p;
+      if (getenv("VJX_HV_VERBOSE"))
+        fprintf(stderr, "[vjx] heavy rows %zu (min k-steps %d): k-steps %d groups %d records %d fill %.2f program %.1f MB; blocks %d + %d\n",
+                rows_all.size(), hv_min, S.heavy.n_ksteps, S.heavy.n_groups, S.heavy.n_records,
+                S.heavy.n_slots ? (double)S.heavy.n_contrib / (double)S.heavy.n_slots : 0.0, 4e-6 * (double)S.heavy.prog.size(),
+                h->lu_seg_hv_cta[0], h->lu_seg_hv_cta[1]);
+      S.heavy.prog.clear(); S.heavy.prog.shrink_to_fit();
     }
   }
   int occ_u = 1;

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <numeric>
@@ -668,12 +669,168 @@ int vjx_symbolic_analyze(int n, const int* indptr, const int* indices, const dou
   return 0;
 }
 
+int vjx_row_lend(const VjxSymbolic& S, int i) {
+  const int ds = S.n - S.n_dense;
+  const int dg = S.lu_diag[i];
+  if (i < ds) return dg;
+  int p = S.lu_ptr[i];
+  while (p < dg && S.lu_col[p] < ds) ++p;   // columns of the dense block are stored last (execution order)
+  return p;
+}
+
+std::vector<int> vjx_select_heavy(const VjxSymbolic& S, int t0, int t1, int min_ksteps, int max_len) {
+  std::vector<int> rows;
+  if (min_ksteps <= 0 || S.upd_ptr.empty() || S.nnz_lu >= (int64_t)(1 << 26)) return rows;
+  for (int t = t0; t < t1; ++t) {
+    const int i = S.order_f[t];
+    if (S.lu_ptr[i + 1] - S.lu_ptr[i] > max_len) continue;
+    if (vjx_row_lend(S, i) - S.lu_ptr[i] >= min_ksteps) rows.push_back(i);
+  }
+  return rows;
+}
+
+void vjx_build_heavy(VjxSymbolic& S, const std::vector<int>& rows) {
+  VjxSymbolic::Heavy& H = S.heavy;
+  H = VjxSymbolic::Heavy();
+  H.rows = rows;
+  H.off.assign(rows.size() + 1, 0);
+  struct Contrib { int pos, slot, q; };
+  std::vector<Contrib> cs;
+  std::vector<int> tstart, torder;
+  for (size_t r = 0; r < rows.size(); ++r) {
+    const int i = rows[r];
+    const int rb = S.lu_ptr[i], lend = vjx_row_lend(S, i);
+    H.off[r] = (long long)H.prog.size();
+    int p0 = rb;
+    while (p0 < lend) {
+      const int d0 = S.depth[S.lu_col[p0]];
+      int p1 = p0 + 1;
+      while (p1 < lend && p1 - p0 < 32 && S.depth[S.lu_col[p1]] == d0) ++p1;
+      // contributions of the group's k-steps, regrouped by target position (ascending k per position)
+      cs.clear();
+      for (int p = p0; p < p1; ++p) {
+        const int k = S.lu_col[p];
+        const int ub = S.lu_diag[k] + 1, ue = S.lu_ptr[k + 1];
+        const int64_t mb = S.upd_ptr[(size_t)p];
+        for (int q = ub; q < ue; ++q) cs.push_back({S.upd_pos[(size_t)(mb + (q - ub))], p - p0, q});
+      }
+      std::stable_sort(cs.begin(), cs.end(), [](const Contrib& a, const Contrib& b) {
+        return a.pos != b.pos ? a.pos < b.pos : a.slot < b.slot;
+      });
+      tstart.clear();
+      for (size_t c = 0; c < cs.size(); ++c)
+        if (c == 0 || cs[c].pos != cs[c - 1].pos) tstart.push_back((int)c);
+      tstart.push_back((int)cs.size());
+      const int nt = (int)tstart.size() - 1;
+      H.n_contrib += (long long)cs.size();
+      H.n_ksteps += p1 - p0;
+      for (int round = 0;; ++round) {
+        torder.clear();
+        for (int t = 0; t < nt; ++t)
+          if (tstart[t + 1] - tstart[t] > 4 * round) torder.push_back(t);
+        if (torder.empty() && round > 0) break;
+        // positions with many contributions left first: lanes of one record then have similar counts
+        std::stable_sort(torder.begin(), torder.end(), [&](int a, int b) {
+          const int ca = std::min(4, tstart[a + 1] - tstart[a] - 4 * round), cb = std::min(4, tstart[b + 1] - tstart[b] - 4 * round);
+          return ca > cb;
+        });
+        const int nrec = ((int)torder.size() + 31) / 32;
+        // record r: pos[32] (lane 0 also carries the record's depth R in bits 24+), then R rows of 32 entries;
+        // R = contributions the record's first lane still has (the largest count of the record), at most 4
+        const size_t g0 = H.prog.size();
+        size_t gi = VJX_HV_GRP_INTS + (size_t)nrec;
+        H.prog.resize(g0 + gi, -1);
+        H.prog[g0 + 0] = nrec; H.prog[g0 + 1] = round > 0 ? 1 : 0; H.prog[g0 + 2] = round > 0 ? 0 : p1 - p0;
+        if (round == 0)
+          for (int p = p0; p < p1; ++p) { H.prog[g0 + 4 + (p - p0)] = p - rb; H.prog[g0 + 36 + (p - p0)] = S.lu_col[p]; }
+        for (int rr = 0; rr < nrec; ++rr) {
+          const int t0 = torder[(size_t)rr * 32];
+          const int R = std::min(4, tstart[t0 + 1] - tstart[t0] - 4 * round);
+          H.prog[g0 + VJX_HV_GRP_INTS + rr] = (int)gi | (R << 28);
+          H.prog.resize(g0 + gi + 32 * (size_t)(1 + R), -1);
+          int* Rp = H.prog.data() + g0 + gi;
+          for (int lane = 0; lane < 32 && (size_t)rr * 32 + lane < torder.size(); ++lane) {
+            const int t = torder[(size_t)rr * 32 + lane];
+            Rp[lane] = cs[tstart[t]].pos;
+            for (int j = 0; j < R; ++j) {
+              const int c = tstart[t] + 4 * round + j;
+              if (c < tstart[t + 1]) Rp[32 + 32 * j + lane] = cs[c].slot | (cs[c].q << 5);
+            }
+          }
+          gi += 32 * (size_t)(1 + R);
+          H.n_slots += 32 * R;
+        }
+        H.prog[g0 + 3] = (int)gi;
+        H.n_groups++;
+        H.n_records += nrec;
+        if (torder.empty()) break;
+      }
+      p0 = p1;
+    }
+  }
+  H.off[rows.size()] = (long long)H.prog.size();
+}
+
+// One heavy row exactly as the thread block of k_lu_rows walks it (host emulation for the CPU tests).
+static void heavy_row_emulate(const VjxSymbolic& S, size_t r, const double* values, std::vector<double>& v,
+                              const std::vector<double>& inv) {
+  const int i = S.heavy.rows[r];
+  const int rb = S.lu_ptr[i], dg = S.lu_diag[i], re = S.lu_ptr[i + 1], lend = vjx_row_lend(S, i);
+  std::vector<double> w(re - rb);
+  for (int pp = rb; pp < re; ++pp) w[pp - rb] = S.lu_src[pp] >= 0 ? values[S.lu_src[pp]] : 0.0;
+  const int* P = S.heavy.prog.data() + S.heavy.off[r];
+  const int* Pend = S.heavy.prog.data() + S.heavy.off[r + 1];
+  double l[32] = {0};
+  while (P < Pend) {
+    const int nrec = P[0], keep = P[1];
+    if (!keep)
+      for (int s = 0; s < 32; ++s) {
+        const int kpos = P[4 + s];
+        l[s] = kpos >= 0 ? w[kpos] * inv[P[36 + s]] : 0.0;
+        if (kpos >= 0) v[rb + kpos] = l[s];
+      }
+    for (int rr = 0; rr < nrec; ++rr) {
+      const int info = P[VJX_HV_GRP_INTS + rr];
+      const int* R = P + (info & 0x0fffffff);
+      const int depth = info >> 28;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int pos = R[lane];
+        if (pos < 0) continue;
+        double acc = w[pos];
+        for (int j = 0; j < depth; ++j) {
+          const int e = R[32 + 32 * j + lane];
+          if (e != -1) acc -= l[e & 31] * v[(size_t)(((unsigned)e) >> 5)];
+        }
+        w[pos] = acc;
+      }
+    }
+    P += P[3];
+  }
+  // the k-steps inside the dense block (dense rows only), in stored order
+  for (int pp = lend; pp < dg; ++pp) {
+    const int k = S.lu_col[pp];
+    const double lk = w[pp - rb] * inv[k];
+    const int ub = S.lu_diag[k] + 1, ue = S.lu_ptr[k + 1];
+    const int64_t mb = S.upd_ptr[(size_t)pp];
+    for (int q = ub; q < ue; ++q) w[S.upd_pos[(size_t)(mb + (q - ub))]] -= lk * v[q];
+    v[pp] = lk;
+  }
+  for (int pp = dg; pp < re; ++pp) v[pp] = w[pp - rb];
+}
+
 double vjx_symbolic_selfcheck(const VjxSymbolic& S, int n, const int* indptr, const int* indices,
                               const double* values, const double* b, double* x_out) {
   std::vector<double> v((size_t)S.nnz_lu, 0.0), inv(n, 0.0), y(n, 0.0), xp(n, 0.0);
+  std::vector<int> hv_of(n, -1);
+  for (size_t r = 0; r < S.heavy.rows.size(); ++r) hv_of[S.heavy.rows[r]] = (int)r;
   for (int t = 0; t < n; ++t) {
     const int i = S.order_f[t];
     const int rb = S.lu_ptr[i], dg = S.lu_diag[i], re = S.lu_ptr[i + 1];
+    if (hv_of[i] >= 0) {
+      heavy_row_emulate(S, (size_t)hv_of[i], values, v, inv);
+      inv[i] = 1.0 / v[dg];
+      continue;
+    }
     double* w = v.data() + rb;
     for (int pp = rb; pp < re; ++pp) w[pp - rb] = S.lu_src[pp] >= 0 ? values[S.lu_src[pp]] : 0.0;
     for (int pp = rb; pp < dg; ++pp) {
@@ -724,8 +881,11 @@ extern "C" int vjx_symbolic_probe(int n, const int* indptr, const int* indices, 
                                   double pivot_tol, const double* b, double* x_out, double* stats8 /* [12] */) {
   VjxSymbolic S;
   std::string err;
-  int rc = vjx_symbolic_analyze(n, indptr, indices, values, pivot_tol, true, S, err);
+  const int dcap = getenv("VJX_PROBE_DENSE_CAP") ? atoi(getenv("VJX_PROBE_DENSE_CAP")) : 0;
+  int rc = vjx_symbolic_analyze(n, indptr, indices, values, pivot_tol, true, S, err, dcap);
   if (rc != 0) return rc;
+  if (getenv("VJX_PROBE_HV_MIN"))   // CPU tests of the heavy-row program: build it and let the emulation walk it
+    vjx_build_heavy(S, vjx_select_heavy(S, 0, n, atoi(getenv("VJX_PROBE_HV_MIN")), 1 << 30));
   double r = vjx_symbolic_selfcheck(S, n, indptr, indices, values, b, x_out);
   if (stats8) {
     stats8[0] = (double)S.nnz_lu;
@@ -741,6 +901,10 @@ extern "C" int vjx_symbolic_probe(int n, const int* indptr, const int* indices, 
     stats8[10] = S.max_l_len;
     stats8[11] = S.n - S.tail_start;
   }
+  if (getenv("VJX_PROBE_HV_MIN") && getenv("VJX_PROBE_VERBOSE"))
+    fprintf(stderr, "heavy rows %zu  k-steps %d  groups %d  records %d  contributions %lld  fill %.3f  program %.1f MB\n",
+            S.heavy.rows.size(), S.heavy.n_ksteps, S.heavy.n_groups, S.heavy.n_records, S.heavy.n_contrib,
+            S.heavy.n_slots ? (double)S.heavy.n_contrib / (double)S.heavy.n_slots : 0.0, 4e-6 * (double)S.heavy.prog.size());
   return 0;
 }
 

@@ -60,7 +60,34 @@ struct VjxSymbolic {
   int n_core = 0;                 // unknowns left for AMD + Gilbert-Peierls
   double flops = 0.0;             // 2 * sum_k nnz(L(:,k)) * nnz(U(k,:)) + nnz(L)
   int64_t nnz_lu = 0;
+  // Heavy rows (vjx_build_heavy): rows with many k-steps are not walked k-step by k-step by one warp but depth by
+  // depth by a whole thread block.  The k-steps of a row that have the same dependency depth are independent of
+  // each other (U(k1,k2) = 0), so their multipliers l = w[k] / U(k,k) are formed together (one lane each, at most
+  // 32 per group) and their updates are regrouped BY TARGET POSITION: a lane owns a position of the row and applies
+  // the contributions -l_s * U(k_s, j) to it in ascending k - no two lanes touch the same word, no atomics, the
+  // order of every sum is fixed at analysis time.  Program of one row = a sequence of group blocks (all ints):
+  //   [nrec, keep, nk, ints]  kpos[32]  k[32]  info[nrec]  then nrec records of  pos[32]  ent[R][32]
+  // kpos / pos: position inside the row (-1: idle lane); ent = slot | (index into the LU values << 5), -1: none;
+  // info = offset of the record from the start of its group | R << 28, R <= 4 the largest number of contributions
+  // a lane of the record has (positions are sorted by that count, so a record's lanes have similar counts).  A
+  // position with more than 4 contributions in its group continues in a `keep` block (same multipliers, no new
+  // k-steps) behind a barrier.
+  struct Heavy {
+    std::vector<int> rows;           // heavy rows (permuted index) in factorisation order
+    std::vector<long long> off;      // [rows.size() + 1] start of each row's program in prog
+    std::vector<int> prog;
+    long long n_contrib = 0, n_slots = 0;
+    int n_groups = 0, n_records = 0, n_ksteps = 0;
+  } heavy;
 };
+
+// Builds S.heavy for the given rows (permuted indices, in factorisation order).  Needs the scatter program.
+void vjx_build_heavy(VjxSymbolic& S, const std::vector<int>& rows);
+// End of the part of row i's L entries that k_lu_rows executes itself (the rest belongs to the dense block).
+int vjx_row_lend(const VjxSymbolic& S, int i);
+// Rows with at least min_ksteps such k-steps and at most max_len entries, in factorisation order.
+std::vector<int> vjx_select_heavy(const VjxSymbolic& S, int t0, int t1, int min_ksteps, int max_len);
+#define VJX_HV_GRP_INTS 68
 
 // Returns 0 on success; <0 and fills err otherwise.
 // dense_cap: upper bound on the rows of the dense trailing block (0 = none).  > 0: out.n_dense is the chain of
