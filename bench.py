@@ -193,7 +193,7 @@ PHASES = [("device_eval", 0), ("jacobian_stamp", 1), ("residual", 2), ("lu_facto
 def launches_per(eng, n_lu):
     nm = len(eng.models)
     isrc = 1 if eng.n_is > 0 else 0
-    per_iter = 1 + isrc + nm + 1 + 1 + n_lu + 2
+    per_iter = isrc + nm + 1 + 1 + n_lu + 2   # models, stamp, residual, LU launches, k_delta_reduce + k_nr_update (no k_iter_begin since round 2)
     per_attempt = 2 + (isrc + nm + 1 + 1 + 1 + 1 + 1 + 1)
     return per_iter, per_attempt
 

@@ -131,6 +131,7 @@ struct LUDev {
   int tail_start;              // rows [tail_start, n): chain tail of the back solve, one thread block
   const int* long_u;           // rows with a very long U part: one thread block each (last blocks of the grid)
   int n_long_u, n_bulk_u;      // order_u holds n_bulk_u rows
+  int n_flat_u;                // ... the first n_flat_u of them have no U part (x = y / pivot, no dependency)
   const long long* upd_ptr;    // [nnz+1] start of each L entry's scatter list
   const int* upd_pos;          // position inside row i of each column of U(k,:)
   long long n_upd_prefetch;    // entries of upd_pos k_lu_load prefetches into L2 (0: the description is larger than L2)
@@ -1739,12 +1740,27 @@ __global__ void __launch_bounds__(VJX_SOLVE_THREADS) k_lu_usolve(LUDev lu, doubl
     }
     return;
   }
+  // Rows without a U part (the peeled singletons: 20 k of c6288's 25 k rows, 533 k of mul64's 666 k) are x = y / pivot
+  // with everything known when this kernel starts: one thread each, before the tickets.  Handed out by ticket, one
+  // row per warp, they kept every warp busy for the first 18 us of c6288's back solve while the rows of the
+  // dependency chain waited for a ticket (profiles/r2_ab timeline).  Same value: (y - 0) * (1 / pivot).
+  {
+    const int first = n_tail > 0 ? 1 : 0;
+    const int nb = (int)gridDim.x - lu.n_long_u - first;
+    for (int t = ((int)blockIdx.x - first) * (int)blockDim.x + (int)threadIdx.x; t < lu.n_flat_u; t += nb * (int)blockDim.x) {
+      const int i = lu.order_u[t];
+      const double xi = lu.y[i] * lu.inv_diag[i];
+      st_pub_f64(lu.xp + i, xi);
+      x_out[lu.perm_c[i]] = xi;
+      if (lu.ts) lu.ts[i] = global_ns();
+    }
+  }
   while (true) {
     unsigned tk = 0;
     if (lane == 0) tk = atomicAdd(&st->ticket_u, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= (unsigned)lu.n_bulk_u) break;
-    const int i = lu.order_u[tk];
+    if (tk >= (unsigned)(lu.n_bulk_u - lu.n_flat_u)) break;
+    const int i = lu.order_u[lu.n_flat_u + tk];
     const int ub = lu.diag[i] + 1, re = lu.ptr[i + 1];
     double yi = 0.0, di = 0.0;
     int pc = 0;
@@ -3192,7 +3208,13 @@ static int upload_symbolic(vjx_handle* h) {
   // of k_lu_usolve is what is left of [tail_start, n) in front of it
   L.tail_start = std::min(S.tail_start, ds);
   std::vector<int> bulk_u, lg;
-  for (int i : S.order_u) if (i < L.tail_start) bulk_u.push_back(i);
+  // rows without a U part first (one thread each at the start of k_lu_usolve), then the others in level order
+  L.n_flat_u = 0;
+  if (!getenv("VJX_NO_FLAT_U")) {
+    for (int i : S.order_u) if (i < L.tail_start && S.lu_ptr[i + 1] - S.lu_diag[i] - 1 == 0) bulk_u.push_back(i);
+    L.n_flat_u = (int)bulk_u.size();
+  }
+  for (int i : S.order_u) if (i < L.tail_start && (L.n_flat_u == 0 || S.lu_ptr[i + 1] - S.lu_diag[i] - 1 > 0)) bulk_u.push_back(i);
   for (int i : S.long_u) if (i < L.tail_start) lg.push_back(i);
   const int n_long_u = (int)lg.size();
   {
