@@ -106,6 +106,40 @@ def test_heavy_row_blocks_solve_the_same_system(hv_min, border, monkeypatch):
     assert st["n"] == n0 + border
 
 
+@pytest.mark.parametrize("work,border", [(1, 8), (1, 40), (64, 159), (1, 220), (2000, 340)])
+def test_block_rows_are_bit_identical_to_warp_rows(work, border, monkeypatch):
+    """lu_block_row_role (VJX_BR_WORK: rows whose scatter program has that many entries are updated by three warps
+    of a block, one barrier per k-step) applies the same fused multiply-adds to every position in the same order as
+    the warp path: identical solutions bit for bit, with rows in front of and inside the dense trailing block and U
+    rows longer than one pass of 96 threads (border 220 / 340)."""
+    import scipy.sparse as sp
+
+    from vajax_b200.analysis.matrix_sequence import SparseLUSolver
+
+    rng = np.random.default_rng(border)
+    n0 = 400
+    lead = sp.random(n0, n0, density=0.01, random_state=border)
+    B = sp.random(n0, border, density=0.3, random_state=border + 1)
+    C = sp.random(border, n0, density=0.3, random_state=border + 2)
+    D = sp.csr_matrix(np.ones((border, border)))
+    P = sp.csr_matrix(_dominant(sp.bmat([[lead, B], [C, D]], format="csr"), rng))
+    P.sort_indices()
+    b = np.random.default_rng(3).normal(size=P.shape[0])
+    xs = []
+    for mode in (None, work):
+        if mode is not None:
+            monkeypatch.setenv("VJX_BR_WORK", str(mode))
+        sol = SparseLUSolver(P.indptr, P.indices)
+        try:
+            xs.append(np.array(sol.solve(P.data, b)))
+            xs.append(np.array(sol.solve(P.data * 1.25, b)))   # second factorisation on the same handle
+        finally:
+            sol.close()
+    assert np.array_equal(xs[0], xs[2]) and np.array_equal(xs[1], xs[3])
+    r = P @ xs[2] - b
+    assert np.max(np.abs(r)) <= 1e-9 * max(1.0, float(np.max(abs(P) @ np.abs(xs[2]) + np.abs(b))))
+
+
 @pytest.mark.parametrize("border", [5, 8, 9, 16, 31, 32, 33, 64, 100, 152, 153, 159, 200, 312, 319])
 def test_dense_block_kernels_agree_bit_for_bit(border, monkeypatch):
     """The blocked dense kernel on 1 / 2 / 4 CTAs (VJX_DT_CLUSTER) and the round-1 one-barrier-per-pivot kernel (0)

@@ -820,6 +820,151 @@ __device__ __forceinline__ void lu_heavy_role(const LUDev& lu, const double* __r
   }
 }
 
+// Block rows: the same k-sequential row update as the warps below - every position receives the same fused
+// multiply-adds in the same order, so the values are bit-identical - but by three warps of a block: the entries of
+// U(k,:) are spread over 96 threads (a 1,000-entry U row of mul64's trailing part is 11 per thread, requested together,
+// instead of 32 chunks walked by one warp) with one named barrier per k-step.  The next two k-steps' pivot, y and
+// first U value per thread are in flight while the current step is applied; a step whose row is not finished polls
+// pivot and U values in the same round trip, exactly like the warp path.  For rows whose work (entries of their
+// scatter program) is at least VJX_BR_WORK; same block layout / fourth warp / tickets as the heavy-row path above.
+struct BrStep {
+  int k, ub, ue, pos;
+  long long mb;
+  ull inv, y, u;
+};
+
+__device__ __forceinline__ void br_meta(const LUDev& lu, int p, int lend, BrStep& o) {
+  o.k = -1; o.ub = 0; o.ue = 0; o.mb = 0; o.pos = -1; o.inv = 0ULL; o.y = 0ULL; o.u = 0ULL;
+  if (p < lend) {
+    o.k = __ldg(lu.col + p);
+    o.ub = __ldg(lu.kub + p);
+    o.mb = __ldg(lu.upd_ptr + p);
+    o.ue = o.ub + (int)(__ldg(lu.upd_ptr + p + 1) - o.mb);
+  }
+}
+__device__ __forceinline__ void br_request(const LUDev& lu, int tid, BrStep& o) {
+  if (o.k >= 0) {
+    o.inv = ld_poll_u64(lu.inv_diag + o.k);
+    if (tid == 0) o.y = ld_poll_u64(lu.y + o.k);
+    if (o.ub + tid < o.ue) {
+      o.pos = __ldg(lu.upd_pos + o.mb + tid);
+      o.u = ld_poll_u64(lu.val + o.ub + tid);
+    }
+  }
+}
+
+__device__ __forceinline__ void lu_block_row_role(const LUDev& lu, const double* __restrict__ csr, const double* __restrict__ b,
+                                                  double scale, const unsigned char* __restrict__ zero_mask, NRStat* st,
+                                                  unsigned* ticket_h, int hv_begin, int hv_end) {
+  constexpr int NT = 32 * VJX_HV_WARPS;
+  const int tid = threadIdx.x;
+  double* const w = vjx_lu_smem;
+  __shared__ unsigned s_tk;
+  while (true) {
+    hv_bar();
+    if (tid == 0) s_tk = atomicAdd(ticket_h, 1u);
+    hv_bar();
+    const unsigned tk = s_tk;
+    if (tk >= (unsigned)(hv_end - hv_begin)) break;
+    const int i = lu.hv_rows[hv_begin + (int)tk];
+    const int rb = lu.ptr[i], dg = lu.diag[i], re = lu.ptr[i + 1];
+    const bool dense_row = i >= lu.dense_start;
+    const int lend = dense_row ? lu.dense_lstop[i - lu.dense_start] : dg;
+    BrStep c, n1, n2, n3;
+    br_meta(lu, rb, lend, c);
+    br_meta(lu, rb + 1, lend, n1);
+    br_meta(lu, rb + 2, lend, n2);
+    br_request(lu, tid, c);
+    br_request(lu, tid, n1);
+    for (int p = rb + tid; p < re; p += NT) {
+      const int sidx = lu.src[p];
+      w[p - rb] = sidx >= 0 ? csr[sidx] : 0.0;
+    }
+    double ysum = 0.0;
+    if (tid == 0) {
+      const int r = lu.perm_r[i];
+      ysum = (zero_mask && zero_mask[r]) ? 0.0 : scale * b[r];
+    }
+    hv_bar();
+    for (int p = rb; p < lend; ++p) {
+      br_request(lu, tid, n2);
+      br_meta(lu, p + 3, lend, n3);
+      // pivot (and y, thread 0) of row k: convergent per warp; the own first U value rides along
+      {
+        unsigned spins = 0;
+        while (true) {
+          bool ok = true;
+          if (c.inv == VJX_SENTINEL) { c.inv = ld_poll_u64(lu.inv_diag + c.k); ok = false; }
+          if (tid == 0 && c.y == VJX_SENTINEL) { c.y = ld_poll_u64(lu.y + c.k); ok = false; }
+          if (c.pos >= 0 && c.u == VJX_SENTINEL) c.u = ld_poll_u64(lu.val + c.ub + tid);
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+        }
+      }
+      const double l = w[p - rb] * bits_f64(c.inv);
+      // first entry of this thread
+      if (c.ub + (tid & ~31) < c.ue) {   // warp-uniform: this warp has entries in the first pass
+        unsigned spins = 0;
+        while (true) {
+          bool ok = true;
+          if (c.pos >= 0 && c.u == VJX_SENTINEL) { c.u = ld_poll_u64(lu.val + c.ub + tid); ok = false; }
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+        }
+        if (c.pos >= 0) w[c.pos] = __fma_rn(-l, bits_f64(c.u), w[c.pos]);
+      }
+      // rest of a long U(k,:): 6 entries per thread requested together
+      for (int q0 = c.ub + NT; q0 < c.ue; q0 += 6 * NT) {
+        if (q0 + (tid & ~31) >= c.ue) break;   // warp-uniform
+        ull u6[6];
+        int pos6[6];
+#pragma unroll
+        for (int g = 0; g < 6; ++g) {
+          u6[g] = 0ULL; pos6[g] = -1;
+          const int q = q0 + g * NT + tid;
+          if (q < c.ue) { pos6[g] = __ldg(lu.upd_pos + c.mb + (q - c.ub)); u6[g] = ld_poll_u64(lu.val + q); }
+        }
+        unsigned spins = 0;
+        while (true) {
+          bool ok = true;
+#pragma unroll
+          for (int g = 0; g < 6; ++g)
+            if (pos6[g] >= 0 && u6[g] == VJX_SENTINEL) { u6[g] = ld_poll_u64(lu.val + q0 + g * NT + tid); ok = false; }
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
+        }
+#pragma unroll
+        for (int g = 0; g < 6; ++g)
+          if (pos6[g] >= 0) w[pos6[g]] = __fma_rn(-l, bits_f64(u6[g]), w[pos6[g]]);
+      }
+      if (tid == 0) {
+        lu.val[p] = l;
+        ysum = __fma_rn(-l, bits_f64(c.y), ysum);
+      }
+      hv_bar();
+      c = n1; n1 = n2; n2 = n3;
+    }
+    if (dense_row) {
+      double* srow = lu.dense + (size_t)(i - lu.dense_start) * (lu.n_dense + 1);
+      for (int p = lend + tid; p < re; p += NT) srow[lu.col[p] - lu.dense_start] = w[p - rb];
+      if (tid == 0) {
+        srow[lu.n_dense] = ysum;
+        if (lu.ts) lu.ts[lu.n + 8 + (i - lu.dense_start)] = global_ns();
+      }
+    } else {
+      const double d = w[dg - rb];
+      for (int p = dg + 1 + tid; p < re; p += NT) st_pub_f64(lu.val + p, w[p - rb]);
+      if (tid == 0) {
+        if (d == 0.0 || d != d) atomicOr(&st->error, 2);
+        st_pub_f64(lu.y + i, ysum);
+        st_pub_f64(lu.inv_diag + i, 1.0 / d);
+        lu.val[dg] = d;
+        if (lu.ts) lu.ts[i] = global_ns();
+      }
+    }
+  }
+}
+
 template <int UG, bool PIPE, int RC, bool HV>
 __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, const double* __restrict__ csr,
                                                                     const double* __restrict__ b, double scale,
@@ -828,7 +973,8 @@ __global__ void __launch_bounds__(32 * VJX_FACTOR_WARPS) k_lu_rows(LUDev lu, con
                                                                     int n_hv_cta, int hv_begin, int hv_end, unsigned* ticket_h) {
   if constexpr (HV) {   // (a launch without heavy rows keeps its register count: the wide launch lives on occupancy)
     if ((int)blockIdx.x < n_hv_cta && (threadIdx.x >> 5) < VJX_HV_WARPS) {
-      lu_heavy_role(lu, csr, b, scale, zero_mask, st, ticket_h, hv_begin, hv_end);
+      if (lu.hv_prog) lu_heavy_role(lu, csr, b, scale, zero_mask, st, ticket_h, hv_begin, hv_end);
+      else lu_block_row_role(lu, csr, b, scale, zero_mask, st, ticket_h, hv_begin, hv_end);
       return;
     }
   }
@@ -3302,14 +3448,28 @@ static int upload_symbolic(vjx_handle* h) {
       std::vector<unsigned char> flag((size_t)std::max(n, 1), 0);
       std::vector<int> rows_all;
       int seg_n[2] = {0, 0};
+      // Block rows (lu_block_row_role): the same blocks, k-sequential, no program; rows whose scatter program has at
+      // least VJX_BR_WORK entries.  Takes precedence over the heavy-row path when both are asked for.
+      const long long br_work = getenv("VJX_BR_WORK") ? atoll(getenv("VJX_BR_WORK")) : 0;
       while (true) {
         rows_all.clear();
         for (int g = 0; g < h->lu_nseg; ++g) {
           if (g + 1 < h->lu_nseg) { seg_n[g] = 0; continue; }   // (the wide launch of two keeps to warps)
-          std::vector<int> r = vjx_select_heavy(S, h->lu_seg_t0[g], h->lu_seg_t1[g], hv_min, VJX_HV_WARPS * h->lu_seg_rowbuf[g]);
+          std::vector<int> r;
+          if (br_work > 0) {
+            for (int t = h->lu_seg_t0[g]; t < h->lu_seg_t1[g]; ++t) {
+              const int i = S.order_f[t];
+              if (S.lu_ptr[i + 1] - S.lu_ptr[i] > VJX_HV_WARPS * h->lu_seg_rowbuf[g]) continue;
+              const int le = vjx_row_lend(S, i);
+              if (le > S.lu_ptr[i] && (long long)(S.upd_ptr[(size_t)le] - S.upd_ptr[(size_t)S.lu_ptr[i]]) >= br_work) r.push_back(i);
+            }
+          } else {
+            r = vjx_select_heavy(S, h->lu_seg_t0[g], h->lu_seg_t1[g], hv_min, VJX_HV_WARPS * h->lu_seg_rowbuf[g]);
+          }
           seg_n[g] = (int)r.size();
           rows_all.insert(rows_all.end(), r.begin(), r.end());
         }
+        if (br_work > 0) { S.heavy = VjxSymbolic::Heavy(); break; }
         vjx_build_heavy(S, rows_all);
         if (rows_all.empty() || 4e-6 * (double)S.heavy.prog.size() <= max_mb) break;
         hv_min *= 2;
@@ -3336,13 +3496,18 @@ static int upload_symbolic(vjx_handle* h) {
       }
       std::vector<int> prog(S.heavy.prog), rows(rows_all);
       std::vector<long long> off(S.heavy.off);
+      const bool block_rows = br_work > 0;
       if (prog.empty()) prog.push_back(0);
       if (rows.empty()) rows.push_back(0);
+      if (off.empty()) off.push_back(0);
       CK(h->lu_hv_prog.upload(prog));
       CK(h->lu_hv_rows.upload(rows));
       CK(h->lu_hv_off.upload(off));
       CK(h->lu_hv_flag.upload(flag));
-      L.hv_prog = h->lu_hv_prog.p; L.hv_off = h->lu_hv_off.p; L.hv_rows = h->lu_hv_rows.p; L.hv_flag = h->lu_hv_flag.p;
+      L.hv_prog = block_rows ? nullptr : h->lu_hv_prog.p;   // no program: the blocks run lu_block_row_role
+      L.hv_off = h->lu_hv_off.p; L.hv_rows = h->lu_hv_rows.p; L.hv_flag = h->lu_hv_flag.p;
+      if (getenv("VJX_HV_VERBOSE") && block_rows)
+        fprintf(stderr, "[vjx] block rows %zu (work >= %lld); blocks %d + %d\n", rows_all.size(), br_work, h->lu_seg_hv_cta[0], h->lu_seg_hv_cta[1]);
       if (getenv("VJX_HV_VERBOSE"))
         fprintf(stderr, "[vjx] heavy rows %zu (min k-steps %d): k-steps %d groups %d records %d fill %.2f program %.1f MB; blocks %d + %d\n",
                 rows_all.size(), hv_min, S.heavy.n_ksteps, S.heavy.n_groups, S.heavy.n_records,
