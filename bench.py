@@ -486,7 +486,10 @@ def mul64_record(args, local_rank, peak):
 
 
 def cpu_baseline(args, sample_steps: int, threads_note: str = "") -> dict:
-    """The oracle port (NumPy MIR interpreter + SciPy SuperLU) on the host cores, bounded sample."""
+    """The oracle port (NumPy MIR interpreter + SciPy SuperLU) on the host cores, bounded sample.
+    One thread: splitting the interpreter's (n,) arrays into instance chunks on a thread pool was tried (round 2) and is
+    5 x SLOWER on the 8-core build container (5.0 s against 1.07 s per step) - 6.4 k interpreted instructions per
+    evaluation hold the GIL for their dispatch, the NumPy loops of a 1.2 k-element chunk are shorter than that."""
     from oracle.engine import OracleEngine
 
     circ, _ = make_circuit(args.workload, args.nbits, model=args.model)
