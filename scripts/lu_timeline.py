@@ -43,6 +43,11 @@ for phase, name in ((3, "factor+fwd"), (5, "usolve")):
         if m.any():
             print(f"   levels {lo:4d}-{hi - 1:4d}: rows {m.sum():6d}  done {ns[m].min() / 1e3:8.1f} .. {ns[m].max() / 1e3:8.1f} us"
                   f"   (tail rows {int((m & tail).sum())})")
+    if os.environ.get("VJX_TL_DETAIL") and phase == 3:   # "lo:hi": every row of these levels (index, done us)
+        lo, hi = (int(x) for x in os.environ["VJX_TL_DETAIL"].split(":"))
+        for L in range(lo, hi):
+            m = np.where(lv == L)[0]
+            print(f"   level {L:4d}:", [(int(i), round(ns[i] / 1e3, 1)) for i in m[np.argsort(ns[m])][:12]])
     order = np.argsort(ns)
     print("   last 12 rows (index, level, us):", [(int(i), int(lv[i]), round(ns[i] / 1e3, 1)) for i in order[-12:]])
 e.close()
