@@ -77,6 +77,7 @@ bulk, nd = np.zeros(n, np.int32), C.c_int(0)
 lib.vjx_symbolic_rows2.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_double, C.c_int] + [C.c_void_p] * 6 + [C.c_void_p]
 rc = lib.vjx_symbolic_rows2(n, p(ip), p(ix), p(csr), 1e-3, 159, p(lv_l), p(lv_u), p(l_len), p(u_len), p(waves), p(bulk), C.byref(nd))
 print(f"dense trailing block: {nd.value} rows")
+np.savez(f"/tmp/lu_rows_{model}_{nb}.npz", level_l=lv_l, level_u=lv_u, l_len=l_len, u_len=u_len, waves=waves, bulk=bulk)
 heavy = np.argsort(-bulk)[:12]
 print("heaviest rows: index  k-steps of k_lu_rows  distinct dependency depths among them  (dense-block row?)")
 for i in heavy:

@@ -824,17 +824,22 @@ __device__ __forceinline__ void lu_heavy_role(const LUDev& lu, const double* __r
 // multiply-adds in the same order, so the values are bit-identical - but by three warps of a block: the entries of
 // U(k,:) are spread over 96 threads (a 1,000-entry U row of mul64's trailing part is 11 per thread, requested together,
 // instead of 32 chunks walked by one warp) with one named barrier per k-step.  The next two k-steps' pivot, y and
-// first U value per thread are in flight while the current step is applied; a step whose row is not finished polls
+// first three U values per thread (a whole 288-entry U row) are in flight while the current step is applied; a step whose row is not finished polls
 // pivot and U values in the same round trip, exactly like the warp path.  For rows whose work (entries of their
 // scatter program) is at least VJX_BR_WORK; same block layout / fourth warp / tickets as the heavy-row path above.
+#define VJX_BR_E 3   // entries of U(k,:) per thread that travel with the look-ahead (3 x 96 = 288: a whole U row of mul64's heavy part)
 struct BrStep {
-  int k, ub, ue, pos;
+  int k, ub, ue;
   long long mb;
-  ull inv, y, u;
+  ull inv, y;
+  int pos[VJX_BR_E];
+  ull u[VJX_BR_E];
 };
 
 __device__ __forceinline__ void br_meta(const LUDev& lu, int p, int lend, BrStep& o) {
-  o.k = -1; o.ub = 0; o.ue = 0; o.mb = 0; o.pos = -1; o.inv = 0ULL; o.y = 0ULL; o.u = 0ULL;
+  o.k = -1; o.ub = 0; o.ue = 0; o.mb = 0; o.inv = 0ULL; o.y = 0ULL;
+#pragma unroll
+  for (int e = 0; e < VJX_BR_E; ++e) { o.pos[e] = -1; o.u[e] = 0ULL; }
   if (p < lend) {
     o.k = __ldg(lu.col + p);
     o.ub = __ldg(lu.kub + p);
@@ -846,9 +851,13 @@ __device__ __forceinline__ void br_request(const LUDev& lu, int tid, BrStep& o) 
   if (o.k >= 0) {
     o.inv = ld_poll_u64(lu.inv_diag + o.k);
     if (tid == 0) o.y = ld_poll_u64(lu.y + o.k);
-    if (o.ub + tid < o.ue) {
-      o.pos = __ldg(lu.upd_pos + o.mb + tid);
-      o.u = ld_poll_u64(lu.val + o.ub + tid);
+#pragma unroll
+    for (int e = 0; e < VJX_BR_E; ++e) {
+      const int q = o.ub + tid + e * 32 * VJX_HV_WARPS;
+      if (q < o.ue) {
+        o.pos[e] = __ldg(lu.upd_pos + o.mb + (q - o.ub));
+        o.u[e] = ld_poll_u64(lu.val + q);
+      }
     }
   }
 }
@@ -896,25 +905,31 @@ __device__ __forceinline__ void lu_block_row_role(const LUDev& lu, const double*
           bool ok = true;
           if (c.inv == VJX_SENTINEL) { c.inv = ld_poll_u64(lu.inv_diag + c.k); ok = false; }
           if (tid == 0 && c.y == VJX_SENTINEL) { c.y = ld_poll_u64(lu.y + c.k); ok = false; }
-          if (c.pos >= 0 && c.u == VJX_SENTINEL) c.u = ld_poll_u64(lu.val + c.ub + tid);
+#pragma unroll
+          for (int e = 0; e < VJX_BR_E; ++e)
+            if (c.pos[e] >= 0 && c.u[e] == VJX_SENTINEL) c.u[e] = ld_poll_u64(lu.val + c.ub + tid + e * NT);
           if (__all_sync(0xffffffffu, ok)) break;
           if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
         }
       }
       const double l = w[p - rb] * bits_f64(c.inv);
-      // first entry of this thread
+      // the entries that came with the look-ahead
       if (c.ub + (tid & ~31) < c.ue) {   // warp-uniform: this warp has entries in the first pass
         unsigned spins = 0;
         while (true) {
           bool ok = true;
-          if (c.pos >= 0 && c.u == VJX_SENTINEL) { c.u = ld_poll_u64(lu.val + c.ub + tid); ok = false; }
+#pragma unroll
+          for (int e = 0; e < VJX_BR_E; ++e)
+            if (c.pos[e] >= 0 && c.u[e] == VJX_SENTINEL) { c.u[e] = ld_poll_u64(lu.val + c.ub + tid + e * NT); ok = false; }
           if (__all_sync(0xffffffffu, ok)) break;
           if (++spins > VJX_SPIN_LIMIT) { atomicOr(&st->error, 1); break; }
         }
-        if (c.pos >= 0) w[c.pos] = __fma_rn(-l, bits_f64(c.u), w[c.pos]);
+#pragma unroll
+        for (int e = 0; e < VJX_BR_E; ++e)
+          if (c.pos[e] >= 0) w[c.pos[e]] = __fma_rn(-l, bits_f64(c.u[e]), w[c.pos[e]]);
       }
       // rest of a long U(k,:): 6 entries per thread requested together
-      for (int q0 = c.ub + NT; q0 < c.ue; q0 += 6 * NT) {
+      for (int q0 = c.ub + VJX_BR_E * NT; q0 < c.ue; q0 += 6 * NT) {
         if (q0 + (tid & ~31) >= c.ue) break;   // warp-uniform
         ull u6[6];
         int pos6[6];
