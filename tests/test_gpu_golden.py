@@ -66,3 +66,35 @@ def test_transient_with_limiting_against_reference(bundles):
     assert n == len(ref_t) and st["total_nr_iterations"] == int(ref_st["total_nr_iterations"])
     assert float(np.max(np.abs(V[:n] - ref_V))) < 1e-7
     e.close()
+
+
+def test_result_object_and_raw_csv_files(bundles, tmp_path):
+    """N4 output path end to end: device run -> TransientResult (reference: engine.py:985-1024) -> raw / CSV
+    files -> read back; the named waveforms are the reference golden's columns."""
+    from vajax_b200.io import read_csv, read_rawfile, write_csv, write_rawfile
+
+    g = load("rc")
+    t = tag("rc", False)
+    e = _engine("rc", bundles, False, True)
+    res = e.run_transient_result()
+    ref_t, ref_V = g[t + "_tran_times"], g[t + "_tran_V"]
+    assert res.num_steps == len(ref_t) and set(res.voltages) and set(res.currents)
+    idx = res.stats["node_indices"]
+    for nm, col in idx.items():
+        assert float(np.max(np.abs(res.voltage(nm) - ref_V[:, col]))) < 1e-7
+    write_rawfile(res, tmp_path / "rc.raw", binary=True)
+    back = read_rawfile(tmp_path / "rc.raw")
+    np.testing.assert_array_equal(back["x"], res.times)
+    for nm in idx:
+        np.testing.assert_array_equal(back["voltages"][nm], res.voltage(nm))
+    write_csv(res, tmp_path / "rc.csv")
+    c = read_csv(tmp_path / "rc.csv")
+    for nm in idx:
+        np.testing.assert_allclose(c["voltages"][nm], res.voltage(nm), rtol=1e-9, atol=1e-300)
+    # with a device-side save list only the saved column exists, under its name
+    keep = sorted(idx)[:1]
+    e.set_save_list(keep)
+    res1 = e.run_transient_result()
+    assert list(res1.voltages) == keep
+    np.testing.assert_array_equal(res1.voltage(keep[0]), res.voltage(keep[0]))
+    e.close()

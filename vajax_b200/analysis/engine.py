@@ -1057,6 +1057,14 @@ class B200Engine:
         }
         return times, V_out, stats
 
+    def run_transient_result(self, **kw):
+        """``run_transient`` with the reference's return type (CircuitEngine.run_transient,
+        vajax/analysis/engine.py:985-1024: ``extract_results`` -> ``TransientResult``); what
+        ``vajax_b200.io.write_rawfile`` / ``write_csv`` consume."""
+        from ..io.result import TransientResult
+        times, V_out, stats = self.run_transient(**kw)
+        return TransientResult.from_run(times, V_out, stats)
+
     def step_records(self, count: Optional[int] = None) -> np.ndarray:
         """Per-attempt records (step, t_next, dt, nr_iters, accept, lte_reject, nr_failed, lte_norm)."""
         sc = np.zeros(12)
