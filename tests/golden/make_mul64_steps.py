@@ -18,13 +18,25 @@ from oracle.engine import OracleEngine  # noqa: E402
 from vajax_b200.benchmarks.circuits import mul64_circuit  # noqa: E402
 from vajax_b200.models.fixtures import get_bundle  # noqa: E402
 
-ROWS = 3   # row 0 = initial condition, then two accepted steps
 MODEL = sys.argv[1] if len(sys.argv) > 1 else "psp103"      # psp103 (light surrogate) or psp103w (PSP103-weight)
-OUT = "mul64_first_steps.npz" if MODEL == "psp103" else f"mul64_first_steps_{MODEL}.npz"
+# rows: row 0 = initial condition, then the accepted steps.  3 = the interpreter's golden (two steps); 16 = the
+# reference's 15-step timing window (README.md:80), generated with the oracle's accelerations for long runs
+# (compiled host model functions + cached ordering: oracle/host_compiled.py, tests/test_host_compiled.py)
+ROWS = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+ACCEL = ROWS > 3
+OUT = ("mul64_first_steps.npz" if MODEL == "psp103" else f"mul64_first_steps_{MODEL}.npz") if not ACCEL \
+    else f"mul64_steps{ROWS - 1}_{MODEL}.npz"
 bundles = {k: get_bundle(k) for k in ("resistor", "capacitor", "diode", "psp103", "psp103w")}
 o = OracleEngine(mul64_circuit(64, mos_model=MODEL), bundles)
 rec = []
-t, V, st = o.run_transient(max_steps=ROWS, record=rec)
+if ACCEL:
+    from oracle import host_compiled  # noqa: E402
+
+    o.reuse_ordering = True
+    with host_compiled.installed():
+        t, V, st = o.run_transient(max_steps=ROWS, record=rec)
+else:
+    t, V, st = o.run_transient(max_steps=ROWS, record=rec)
 n = st["n_steps"]
 cols = np.arange(0, V.shape[1], 64)
 np.savez_compressed(

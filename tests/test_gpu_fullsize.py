@@ -273,3 +273,42 @@ def test_mul64_first_steps_match_the_oracle_golden(bundles, model):
     assert np.allclose(np.max(np.abs(V[:n]), axis=1), g["row_absmax"], rtol=0, atol=1e-7)
     assert np.allclose(np.sum(V[:n], axis=1), g["row_sum"], rtol=1e-9, atol=1e-4)
     e.close()
+
+
+@pytest.mark.timeout(900)
+def test_c6288_long_window_matches_the_accelerated_oracle(c6288, bundles):
+    """The window bench.py times (150 accepted steps at BASELINE.json's c6288 size, rejected attempts included)
+    against the CPU oracle: identical attempt records (step, NR iterations, accept / reject), t to 1e-8 and dt to
+    1e-7 relative, waveforms to 1e-6 RMS.  The oracle runs with its two accelerations for timing legs - model functions compiled
+    for the host (oracle/host_compiled.py, held to the interpreter by tests/test_host_compiled.py) and the cached
+    ordering of the sparse solve - because the interpreter needs ~1.2 s per step here; the interpreter itself
+    anchors the first steps (test above) and the small circuits."""
+    from oracle import host_compiled
+    from oracle.engine import OracleEngine
+
+    K = 150
+    o = OracleEngine(circuits.multiplier_circuit(16, mos_model=c6288.mos_model), bundles)
+    o.reuse_ordering = True
+    rec = []
+    with host_compiled.installed():
+        to, Vo, so = o.run_transient(max_steps=K, record=rec)
+    tg, Vg, sg = c6288.run_transient(max_steps=K)
+    gr = c6288.step_records()
+    first_bad = next((i for i, (a, b) in enumerate(zip(gr, rec))
+                      if not (int(a[0]) == b["step"] and int(a[3]) == b["nr_iters"] and bool(a[4]) == b["accept"])), None)
+    assert first_bad is None, (first_bad, list(gr[first_bad]), rec[first_bad])
+    assert sg["error_flags"] == 0 and sg["n_steps"] == so["n_steps"] == K and len(gr) == len(rec)
+    assert sg["total_nr_iterations"] == so["total_nr_iterations"] and sg["rejected_steps"] == so["rejected_steps"]
+    # dt is dt_prev * (lte_ratio / norm)^(1/(order+1)) with norm built from V_new - V_pred, a difference of nearly equal
+    # numbers: the 1e-9 agreement of two converged NR solves is amplified by |V| / |V_new - V_pred| and carried from step
+    # to step, so over 150 steps the bar is 1e-7 on dt and 1e-8 on t (the first-steps test above holds 1e-9)
+    e_t = max(abs(a[1] - b["t_next"]) / abs(b["t_next"]) for a, b in zip(gr, rec))
+    e_dt = max(abs(a[2] - b["dt"]) / b["dt"] for a, b in zip(gr, rec))
+    span = max(np.max(Vo[:K]) - np.min(Vo[:K]), 1e-12)
+    rms = np.sqrt(np.mean((Vg[:K] - Vo[:K]) ** 2)) / span
+    dv = np.max(np.abs(Vg[:K] - Vo[:K]))
+    print(f"c6288/{c6288.mos_model}: {K} steps, {len(rec)} attempts, {so['rejected_steps']} rejected, "
+          f"{so['total_nr_iterations']} NR iterations; max rel dt {e_dt:.2e}, t {e_t:.2e}; rms {rms:.2e}, max |dV| {dv:.2e}")
+    assert e_t < 1e-8 and e_dt < 1e-7, (e_t, e_dt)     # measured on the B200: 5.5e-10 / 6.3e-9
+    assert rms < 1e-6, rms                             # north_star bar; measured 6.3e-11
+    assert dv < 1e-7, dv                               # measured 2.6e-9
