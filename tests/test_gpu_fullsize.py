@@ -312,3 +312,37 @@ def test_c6288_long_window_matches_the_accelerated_oracle(c6288, bundles):
     assert e_t < 1e-8 and e_dt < 1e-7, (e_t, e_dt)     # measured on the B200: 5.5e-10 / 6.3e-9
     assert rms < 1e-6, rms                             # north_star bar; measured 6.3e-11
     assert dv < 1e-7, dv                               # measured 2.6e-9
+
+
+@pytest.mark.timeout(900)
+def test_mul64_15_step_window_matches_the_oracle_golden(bundles):
+    """The window the reference times on mul64 (15 steps, README.md:80) with the PSP103-weight model against the
+    CPU oracle: tests/golden/mul64_steps15_psp103w.npz (make_mul64_steps.py psp103w 16; the oracle with compiled host
+    model functions and cached ordering, 5.5 min in the build container).  Identical attempt records including the
+    rejected third attempt, t / dt / waveform bars as in the c6288 window test, row checksums over all 133,463
+    external nodes."""
+    import os
+
+    from vajax_b200.analysis.engine import B200Engine
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "mul64_steps15_psp103w.npz")
+    g = np.load(path)
+    n = int(g["n_steps"])
+    e = B200Engine(circuits.mul64_circuit(64, mos_model="psp103w"), bundles, use_device_graph=True).prepare()
+    t, V, st = e.run_transient(max_steps=n)
+    assert st["error_flags"] == 0 and st["n_steps"] == n and V.shape[1] == int(g["n_external"])
+    rec = e.step_records()
+    assert [(int(a[0]), int(a[3]), bool(a[4])) for a in rec] == [(int(b[0]), int(b[3]), bool(b[4])) for b in g["records"]]
+    assert st["total_nr_iterations"] == int(g["total_nr"]) and st["rejected_steps"] == int(g["rejected"]) == 1
+    e_t = max(abs(a[1] - b[1]) / abs(b[1]) for a, b in zip(rec, g["records"]))
+    e_dt = max(abs(a[2] - b[2]) / b[2] for a, b in zip(rec, g["records"]))
+    Vc = V[:n][:, g["cols"]]
+    span = max(np.max(g["V_cols"]) - np.min(g["V_cols"]), 1e-12)
+    rms = np.sqrt(np.mean((Vc - g["V_cols"]) ** 2)) / span
+    dv = np.max(np.abs(Vc - g["V_cols"]))
+    print(f"mul64/psp103w: {n - 1} steps, {len(rec)} attempts; max rel dt {e_dt:.2e}, t {e_t:.2e}; rms {rms:.2e}, max |dV| {dv:.2e}")
+    assert e_t < 1e-8 and e_dt < 1e-7, (e_t, e_dt)
+    assert rms < 1e-6 and dv < 1e-7, (rms, dv)
+    assert np.allclose(np.max(np.abs(V[:n]), axis=1), g["row_absmax"], rtol=0, atol=1e-7)
+    assert np.allclose(np.sum(V[:n], axis=1), g["row_sum"], rtol=1e-9, atol=1e-4)
+    e.close()
