@@ -346,3 +346,47 @@ def test_mul64_15_step_window_matches_the_oracle_golden(bundles):
     assert np.allclose(np.max(np.abs(V[:n]), axis=1), g["row_absmax"], rtol=0, atol=1e-7)
     assert np.allclose(np.sum(V[:n], axis=1), g["row_sum"], rtol=1e-9, atol=1e-4)
     e.close()
+
+
+@pytest.mark.timeout(900)
+def test_c6288_corner_sweep_matches_the_oracle_per_corner(bundles):
+    """BASELINE.json configs[4] (PVT sweep of whole-circuit replicas) at c6288 size: four corners that differ in process,
+    temperature and supply, run 4-in-flight on one GPU (run_corners(concurrent=4)), against the CPU oracle run
+    corner by corner through the SAME driver (run_corners with the oracle as engine factory): identical attempt
+    counts and NR iteration counts per corner, waveforms to 1e-6 RMS - the parity target of the sweep is 'a fresh
+    engine per corner' (SURVEY 8e caveat D10)."""
+    from oracle import host_compiled
+    from oracle.engine import OracleEngine
+    from vajax_b200.analysis import corners as cz
+
+    circ = circuits.multiplier_circuit(16, mos_model="psp103w")
+    allc = cz.sweep_corners(64)
+    cs = [allc[0], allc[21], allc[42], allc[63]]     # TT/27C/1.0, FF/-40C/0.9, SS/0C/1.05, FS/125C/1.1
+    assert len({c.name for c in cs}) == 4
+    K = 40
+    g = cz.run_corners(circ, bundles, cs, use_device_graph=True, concurrent=4, max_steps=K)
+
+    def oracle_factory(c, b, device=0, **kw):
+        o = OracleEngine(c, b)
+        o.reuse_ordering = True
+        return o
+
+    with host_compiled.installed():
+        o = cz.run_corners(circ, bundles, cs, engine_factory=oracle_factory, max_steps=K)
+    assert g.all_converged and len(g.results) == len(o.results) == 4
+    seen = set()
+    for rg, ro in zip(g.results, o.results):
+        assert rg.corner.name == ro.corner.name
+        n = int(ro.stats["n_steps"])
+        assert int(rg.stats["n_steps"]) == n == K
+        assert int(rg.stats["total_nr_iterations"]) == int(ro.stats["total_nr_iterations"]), rg.corner.name
+        assert int(rg.stats["rejected_steps"]) == int(ro.stats["rejected_steps"]), rg.corner.name
+        assert np.max(np.abs(rg.times - ro.times)) <= 1e-8 * ro.times[-1]
+        span = max(np.max(ro.voltages) - np.min(ro.voltages), 1e-12)
+        rms = np.sqrt(np.mean((rg.voltages - ro.voltages) ** 2)) / span
+        dv = np.max(np.abs(rg.voltages - ro.voltages))
+        print(f"{rg.corner.name}: {n} steps, {ro.stats['total_nr_iterations']} NR iterations, {ro.stats['rejected_steps']} rejected; "
+              f"rms {rms:.2e}, max |dV| {dv:.2e}, vmax {np.max(ro.voltages):.3f}")
+        assert rms < 1e-6 and dv < 1e-7, (rg.corner.name, rms, dv)
+        seen.add((int(ro.stats["total_nr_iterations"]), round(float(np.max(ro.voltages)), 3)))
+    assert len(seen) > 1      # the corners really are different circuits
