@@ -390,3 +390,51 @@ def test_c6288_corner_sweep_matches_the_oracle_per_corner(bundles):
         assert rms < 1e-6 and dv < 1e-7, (rg.corner.name, rms, dv)
         seen.add((int(ro.stats["total_nr_iterations"]), round(float(np.max(ro.voltages)), 3)))
     assert len(seen) > 1      # the corners really are different circuits
+
+
+def _strict_build_system_parity(e, o, seed, label):
+    """Stamped system of the CUDA path against the interpreter oracle, per-entry metric (golden_util): J 1e-12."""
+    from golden_util import BS_NAMES, assert_vector_parity
+
+    rng = np.random.default_rng(seed)
+    X = np.zeros(e.n_total + e.n_vs)
+    X[1:e.n_total] = rng.uniform(0, 1.2, e.n_unknowns)
+    X[e.noi_indices] = 0.0
+    X[e.n_total:] = rng.normal(0, 1e-4, e.n_vs)
+    vs, isv = e.eval_sources(5e-11)
+    nu = e.n_unknowns
+    Qp, dq, q2 = rng.normal(0, 1e-15, nu), rng.normal(0, 1e-4, nu), rng.normal(0, 1e-15, nu)
+    worst = {}
+    for (c0, c1, d1, c2, it) in ((0.0, 0.0, 0.0, 0.0, 0), (2e12, -2e12, -1.0, 0.0, 1), (1.5e11, -2e11, 0.0, 0.5e11, 3)):
+        got = e.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
+        want = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
+        for nm, a, b in zip(BS_NAMES, got, want):
+            worst[nm] = max(worst.get(nm, 0.0), assert_vector_parity(nm, a, b, (label, c0, it)))
+    print(label, "worst per-entry errors", {k: f"{v:.1e}" for k, v in worst.items()})
+
+
+def test_c6288_build_system_strict_parity_with_the_interpreter_oracle(c6288, bundles):
+    """north_star's 'stamped Jacobians within 1e-12 relative' at the metric's own size: 127,670 CSR slots of 10,048
+    MOSFETs against the NumPy MIR interpreter (the checker proper, no acceleration), three coefficient sets."""
+    from oracle.engine import OracleEngine
+
+    o = OracleEngine(circuits.multiplier_circuit(16, mos_model=c6288.mos_model), bundles)
+    o.setup()
+    assert np.array_equal(o.csr_indptr, c6288.csr_indptr) and np.array_equal(o.csr_indices, c6288.csr_indices)
+    _strict_build_system_parity(c6288, o, 7, f"c6288/{c6288.mos_model}")
+
+
+@pytest.mark.timeout(1200)
+def test_mul64_build_system_strict_parity_with_the_interpreter_oracle(bundles):
+    """The same at BASELINE.json's largest configuration: 3,260,938 CSR slots, 266,408 PSP103-weight MOSFETs."""
+    from oracle.engine import OracleEngine
+    from vajax_b200.analysis.engine import B200Engine
+
+    circ = circuits.mul64_circuit(64, mos_model="psp103w")
+    e = B200Engine(circ, bundles, use_device_graph=False).prepare()
+    o = OracleEngine(circ, bundles)
+    o.setup()
+    assert e.nse == len(o.csr_indices) == 3260938
+    assert np.array_equal(o.csr_indptr, e.csr_indptr) and np.array_equal(o.csr_indices, e.csr_indices)
+    _strict_build_system_parity(e, o, 11, "mul64/psp103w")
+    e.close()
