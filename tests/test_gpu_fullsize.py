@@ -392,15 +392,31 @@ def test_c6288_corner_sweep_matches_the_oracle_per_corner(bundles):
     assert len(seen) > 1      # the corners really are different circuits
 
 
+def _slot_abs_sums(o, parts, c0):
+    """Sum of |contribution| per CSR slot (the scale any summation order's rounding error is relative to)."""
+    s = np.zeros(o.nse)
+    for mt, m in o.models.items():
+        v = np.abs(parts[mt]["jac_resist"] + c0 * parts[mt]["jac_react"])
+        pos = m["csr_pos"]
+        ok = (pos >= 0) & ~np.isnan(v)
+        np.add.at(s, pos[ok], v[ok])
+    return s
+
+
 def _strict_build_system_parity(e, o, seed, label, steps=6):
     """Stamped system of the CUDA path against the interpreter oracle, per-entry metric (golden_util).
 
-    (1) At an operating point the transient visits (the state after ``steps`` accepted steps): the strict bars, J 1e-12.
-    (2) At a random, unphysical bias point (every node uniform in [0, 1.2] V): the PSP103-weight model amplifies the
-        last-bit differences between elementary-function libraries to ~1e-12 there for ANY pair of implementations -
-        the oracle itself moves by that much when its exp / log / pow come from glibc (oracle/host_compiled.py) instead
-        of NumPy.  That self-difference is measured on the spot and the bar is max(1e-12, 10 x it); the share of
-        Jacobian entries inside 1e-12 is printed."""
+    (1) At an operating point the transient visits (the state after ``steps`` accepted steps), three coefficient sets.
+    (2) At a random, unphysical bias point (every node uniform in [0, 1.2] V).
+
+    Bars: f, Q, Ivs, mrc 1e-10 per entry.  J per entry: |got - want| <= 1e-12 max(|want|, 1e-12) + 64 eps S_k, where
+    S_k is the sum of |contribution| into slot k: the second term is the rounding error ANY summation order of that
+    slot's contributions may differ by (a rail's diagonal at mul64 size adds up 133 k terms; the CUDA path reduces
+    long segments in chunks, the oracle left to right) and vanishes (1.4e-14 relative) for slots without cancellation.
+    At (2) the PSP103-weight model also amplifies last-bit differences between elementary-function libraries to
+    ~1e-12: the oracle itself moves by that much when its exp / log / pow come from glibc (oracle/host_compiled.py)
+    instead of NumPy, so that self-difference is measured on the spot and the relative part of the bar is
+    max(1e-12, 10 x it).  The share of Jacobian entries inside plain 1e-12 is printed."""
     from golden_util import ABS_FLOOR, BAR, BS_NAMES, entry_err
     from oracle import host_compiled
 
@@ -410,47 +426,41 @@ def _strict_build_system_parity(e, o, seed, label, steps=6):
     Xp, Qp, dq = e.tran_state()
     vs, isv = e.eval_sources(5e-11)
     q2 = rng.normal(0, 1e-15, nu)
-    worst, floor = {}, {}
-    for (c0, c1, d1, c2, it) in ((0.0, 0.0, 0.0, 0.0, 0), (2e12, -2e12, -1.0, 0.0, 1), (1.5e11, -2e11, 0.0, 0.5e11, 3)):
-        got = e.build_system(Xp, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
-        want = o.build_system(Xp, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
-        with host_compiled.installed():
-            alt = o.build_system(Xp, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
-        for nm, a, b, c in zip(BS_NAMES, got, want, alt):
-            a, b, c = np.asarray(a), np.asarray(b), np.asarray(c)
-            if b.size == 0:
-                continue
-            assert np.array_equal(np.isnan(a), np.isnan(b))
-            m = ~np.isnan(b)
-            err, noise = entry_err(a[m], b[m], ABS_FLOOR[nm]), entry_err(c[m], b[m], ABS_FLOOR[nm])
-            worst[nm] = max(worst.get(nm, 0.0), err)
-            floor[nm] = max(floor.get(nm, 0.0), noise)
-            assert err < max(BAR.get(nm, 1e-10), 10 * noise), (label, "operating point", nm, c0, it, err, noise)
-    print(label, "operating point, worst per-entry errors", {k: f"{v:.1e} (libm-vs-numpy {floor[k]:.1e})" for k, v in worst.items()})
-
-    X = np.zeros(e.n_total + e.n_vs)
-    X[1:e.n_total] = rng.uniform(0, 1.2, nu)
-    X[e.noi_indices] = 0.0
-    X[e.n_total:] = rng.normal(0, 1e-4, e.n_vs)
-    c0, c1, d1, c2, it = 2e12, -2e12, -1.0, 0.0, 1
-    got = e.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
-    want = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
-    with host_compiled.installed():
-        alt = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
-    rep = {}
-    for nm, a, b, c in zip(BS_NAMES, got, want, alt):
-        a, b, c = np.asarray(a), np.asarray(b), np.asarray(c)
-        if b.size == 0:
-            continue
-        assert np.array_equal(np.isnan(a), np.isnan(b))
-        m = ~np.isnan(b)
-        err, noise = entry_err(a[m], b[m], ABS_FLOOR[nm]), entry_err(c[m], b[m], ABS_FLOOR[nm])
-        rep[nm] = f"{err:.1e} (libm-vs-numpy {noise:.1e})"
-        assert err < max(1e-12, 10 * noise), (label, "random point", nm, err, noise)
-        if nm == "J":
-            d = np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), ABS_FLOOR[nm])
-            rep["J within 1e-12"] = f"{100.0 * np.mean(d < 1e-12):.4f} %"
-    print(label, "random bias point", rep)
+    Xr = np.zeros(e.n_total + e.n_vs)
+    Xr[1:e.n_total] = rng.uniform(0, 1.2, nu)
+    Xr[e.noi_indices] = 0.0
+    Xr[e.n_total:] = rng.normal(0, 1e-4, e.n_vs)
+    eps = np.finfo(np.float64).eps
+    for where, X, cases in (("operating point", Xp, ((0.0, 0.0, 0.0, 0.0, 0), (2e12, -2e12, -1.0, 0.0, 1), (1.5e11, -2e11, 0.0, 0.5e11, 3))),
+                            ("random bias point", Xr, ((2e12, -2e12, -1.0, 0.0, 1),))):
+        rep = {}
+        for (c0, c1, d1, c2, it) in cases:
+            got = e.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
+            want = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it, return_parts=True)
+            with host_compiled.installed():
+                alt = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
+            S = _slot_abs_sums(o, want[6], c0)
+            for nm, a, b, c in zip(BS_NAMES, got, want, alt):
+                a, b, c = np.asarray(a), np.asarray(b), np.asarray(c)
+                if b.size == 0:
+                    continue
+                assert np.array_equal(np.isnan(a), np.isnan(b)), (label, where, nm)
+                m = ~np.isnan(b)
+                noise = entry_err(c[m], b[m], ABS_FLOOR[nm])
+                rel = max(BAR.get(nm, 1e-10), 10 * noise)
+                scale = np.maximum(np.abs(b[m]), ABS_FLOOR[nm])
+                d = np.abs(a[m] - b[m])
+                slack = 64 * eps * S[m] if nm == "J" else 0.0
+                bad = d > rel * scale + slack
+                k = int(np.argmax(d / scale))
+                r = rep.setdefault(nm, {"err": 0.0, "noise": 0.0})
+                r["err"], r["noise"] = max(r["err"], float(np.max(d / scale))), max(r["noise"], noise)
+                if nm == "J":
+                    r["within_1e-12"] = min(r.get("within_1e-12", 100.0), 100.0 * float(np.mean(d <= 1e-12 * scale)))
+                    r["worst_slot_cond"] = float(S[m][k] / scale[k])
+                assert not bad.any(), (label, where, nm, c0, it, f"entry {int(np.argmax(bad))}: got {a[m][np.argmax(bad)]!r} want "
+                                       f"{b[m][np.argmax(bad)]!r}", f"noise {noise:.1e}")
+        print(label, where, {k: {kk: (f"{vv:.2e}" if kk != "within_1e-12" else f"{vv:.5f} %") for kk, vv in v.items()} for k, v in rep.items()})
 
 
 def test_c6288_build_system_strict_parity_with_the_interpreter_oracle(c6288, bundles):
