@@ -393,14 +393,30 @@ def test_c6288_corner_sweep_matches_the_oracle_per_corner(bundles):
 
 
 def _slot_abs_sums(o, parts, c0):
-    """Sum of |contribution| per CSR slot (the scale any summation order's rounding error is relative to)."""
-    s = np.zeros(o.nse)
+    """Per CSR slot: sum of |contribution| and number of contributions (the quantities the rounding error of a
+    summation order is bounded by)."""
+    s, cnt = np.zeros(o.nse), np.zeros(o.nse)
     for mt, m in o.models.items():
         v = np.abs(parts[mt]["jac_resist"] + c0 * parts[mt]["jac_react"])
         pos = m["csr_pos"]
         ok = (pos >= 0) & ~np.isnan(v)
         np.add.at(s, pos[ok], v[ok])
-    return s
+        np.add.at(cnt, pos[ok], 1.0)
+    return s, cnt
+
+
+def _slot_exact(o, parts, c0, k):
+    """Correctly rounded sum (math.fsum) of the model contributions into slot k."""
+    import math
+
+    terms = []
+    for mt, m in o.models.items():
+        v = parts[mt]["jac_resist"] + c0 * parts[mt]["jac_react"]
+        sel = (m["csr_pos"] == k) & ~np.isnan(v)
+        terms.extend(v[sel].tolist())
+    if k in set(np.asarray(o.diag_pos).tolist()):
+        terms.append(o.options.gmin + 1e-9)        # diagonal regularisation + the gshunt these calls pass
+    return math.fsum(terms), len(terms)
 
 
 def _strict_build_system_parity(e, o, seed, label, steps=6):
@@ -409,10 +425,13 @@ def _strict_build_system_parity(e, o, seed, label, steps=6):
     (1) At an operating point the transient visits (the state after ``steps`` accepted steps), three coefficient sets.
     (2) At a random, unphysical bias point (every node uniform in [0, 1.2] V).
 
-    Bars: f, Q, Ivs, mrc 1e-10 per entry.  J per entry: |got - want| <= 1e-12 max(|want|, 1e-12) + 64 eps S_k, where
-    S_k is the sum of |contribution| into slot k: the second term is the rounding error ANY summation order of that
-    slot's contributions may differ by (a rail's diagonal at mul64 size adds up 133 k terms; the CUDA path reduces
-    long segments in chunks, the oracle left to right) and vanishes (1.4e-14 relative) for slots without cancellation.
+    Bars: f, Q, Ivs, mrc 1e-10 per entry.  J per entry: |got - want| <= 1e-12 max(|want|, 1e-12) + n_k u S_k, where n_k
+    contributions of absolute sum S_k meet in slot k and u = 2^-53: the second term is the a-priori bound of recursive
+    summation (Higham, Accuracy and Stability of Numerical Algorithms, eq. 4.4), i.e. what the oracle's / the reference's
+    own left-to-right sum may be off by.  It is 1e-15 S_k for an ordinary slot (n_k <= 10) and matters for two kinds of
+    slot only: sums that cancel, and the supply rails' diagonals at mul64 size, where 266 k near-identical conductances
+    add up - identical addends round the same way every time, so the left-to-right sum drifts by ~2e-12 relative while
+    the CUDA path's chunked tree reduction stays next to the exact sum (printed below: both against math.fsum).
     At (2) the PSP103-weight model also amplifies last-bit differences between elementary-function libraries to
     ~1e-12: the oracle itself moves by that much when its exp / log / pow come from glibc (oracle/host_compiled.py)
     instead of NumPy, so that self-difference is measured on the spot and the relative part of the bar is
@@ -439,7 +458,7 @@ def _strict_build_system_parity(e, o, seed, label, steps=6):
             want = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it, return_parts=True)
             with host_compiled.installed():
                 alt = o.build_system(X, vs, isv, Qp, c0, 1e-12, 1e-9, c1, d1, dq, c2, q2, None, it)
-            S = _slot_abs_sums(o, want[6], c0)
+            S, N = _slot_abs_sums(o, want[6], c0)
             for nm, a, b, c in zip(BS_NAMES, got, want, alt):
                 a, b, c = np.asarray(a), np.asarray(b), np.asarray(c)
                 if b.size == 0:
@@ -450,17 +469,23 @@ def _strict_build_system_parity(e, o, seed, label, steps=6):
                 rel = max(BAR.get(nm, 1e-10), 10 * noise)
                 scale = np.maximum(np.abs(b[m]), ABS_FLOOR[nm])
                 d = np.abs(a[m] - b[m])
-                slack = 64 * eps * S[m] if nm == "J" else 0.0
+                slack = N[m] * (eps / 2) * S[m] if nm == "J" else 0.0
                 bad = d > rel * scale + slack
                 k = int(np.argmax(d / scale))
                 r = rep.setdefault(nm, {"err": 0.0, "noise": 0.0})
                 r["err"], r["noise"] = max(r["err"], float(np.max(d / scale))), max(r["noise"], noise)
                 if nm == "J":
                     r["within_1e-12"] = min(r.get("within_1e-12", 100.0), 100.0 * float(np.mean(d <= 1e-12 * scale)))
-                    r["worst_slot_cond"] = float(S[m][k] / scale[k])
+                    if float(d[k] / scale[k]) >= r.get("_worst", -1.0):
+                        r["_worst"] = float(d[k] / scale[k])
+                        kk = int(np.flatnonzero(m)[k])
+                        exact, n_terms = _slot_exact(o, want[6], c0, kk)
+                        r["worst_slot"] = (f"slot {kk}: {n_terms} contributions, |got - fsum| / |fsum| = {abs(a[kk] - exact) / max(abs(exact), 1e-300):.1e}, "
+                                           f"|oracle - fsum| / |fsum| = {abs(b[kk] - exact) / max(abs(exact), 1e-300):.1e} (model contributions + diagonal regularisation)")
                 assert not bad.any(), (label, where, nm, c0, it, f"entry {int(np.argmax(bad))}: got {a[m][np.argmax(bad)]!r} want "
                                        f"{b[m][np.argmax(bad)]!r}", f"noise {noise:.1e}")
-        print(label, where, {k: {kk: (f"{vv:.2e}" if kk != "within_1e-12" else f"{vv:.5f} %") for kk, vv in v.items()} for k, v in rep.items()})
+        print(label, where, {k: {kk: (vv if isinstance(vv, str) else f"{vv:.2e}" if kk != "within_1e-12" else f"{vv:.5f} %")
+                                 for kk, vv in v.items() if not kk.startswith("_")} for k, v in rep.items()})
 
 
 def test_c6288_build_system_strict_parity_with_the_interpreter_oracle(c6288, bundles):
