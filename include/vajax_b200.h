@@ -138,6 +138,13 @@ int vjx_lu_stats(vjx_handle* h, double* out10);
  * the persistent factorisation / back-solve kernels of this handle take 1/div of the GPU's CTA slots so that several
  * handles in flight on one GPU share the SMs.  Results do not depend on it.  Call before the first solve. */
 int vjx_lu_set_grid_div(vjx_handle* h, int div);
+/* A12, the reference's DENSE linear-solve path (make_dense_full_mna_solver.linear_solve,
+ * vajax/analysis/solver_factories.py:784-788: solve(J + 1e-14 * I, -f); the reference's default below ~1000 nodes):
+ * reg is added to every diagonal entry - node rows and branch rows - inside each NR solve, after the NOI rows were
+ * rewritten, exactly where the reference adds it; what vjx_build_system returns stays the unregularised J.  The
+ * factorisation itself remains this library's sparse LU.  Needs the branch rows' diagonal entries in the CSR pattern
+ * given to vjx_create (VJX_ERR_INVALID otherwise); 0 = the sparse paths' semantics (default).  Call before the first solve. */
+int vjx_set_dense_regularization(vjx_handle* h, double reg);
 
 /* ---- Seam S3: nr_solve (vajax/analysis/solver_factories.py:604-725) ---------------------- */
 int vjx_nr_solve(vjx_handle* h, const double* X_init_dev, const double* vsrc_dev, const double* isrc_dev,

@@ -98,3 +98,27 @@ def test_result_object_and_raw_csv_files(bundles, tmp_path):
     assert list(res1.voltages) == keep
     np.testing.assert_array_equal(res1.voltage(keep[0]), res.voltage(keep[0]))
     e.close()
+
+
+@pytest.mark.parametrize("name", ["rc", "clipper", "ring", "mul3", "ringw"])
+def test_dense_path_transient_against_reference(name, bundles):
+    """A12: the reference's dense linear-solve path (solve(J + 1e-14 I, -f), solver_factories.py:728-800 - its default
+    for circuits this small) through B200Engine(linear_solver="dense"): the reference's DENSE-path goldens, same
+    accepted-step sequence.  The ring is the case where the two paths part: 67 accepted steps dense, 64 sparse."""
+    from vajax_b200.analysis.engine import B200Engine
+
+    g = load(name)
+    t = tag(name, False, sparse=False)
+    e = B200Engine(CIRCUITS[name](), bundles, use_device_graph=True, linear_solver="dense").prepare()
+    times, V, st = e.run_transient()
+    ref_t, ref_V, ref_st = g[t + "_tran_times"], g[t + "_tran_V"], tran_stats(g, t)
+    n = st["n_steps"]
+    assert st["error_flags"] == 0
+    assert n == len(ref_t), (n, len(ref_t))
+    assert st["rejected_steps"] == int(ref_st["rejected_steps"])
+    assert st["total_nr_iterations"] == int(ref_st["total_nr_iterations"])
+    assert scaled_err(times[:n], ref_t, rel_floor=1e-30, abs_floor=1e-30) < 1e-9
+    assert float(np.max(np.abs(V[:n] - ref_V))) < 1e-7 * max(1.0, float(np.max(np.abs(ref_V))))
+    if name == "ring":
+        assert n == 67 and len(g[tag(name, False) + "_tran_times"]) == 64
+    e.close()

@@ -102,3 +102,29 @@ def test_transient_step_sequence_and_waveform(name, limiting, oracle_cache):
     span = max(float(np.max(ref_V) - np.min(ref_V)), 1e-12)
     assert np.sqrt(np.mean((V[:n] - ref_V) ** 2)) / span < 1e-9
     assert float(np.max(np.abs(V[:n] - ref_V))) < 1e-8 * max(1.0, float(np.max(np.abs(ref_V))))
+
+
+@pytest.mark.parametrize("name", ["rc", "clipper", "ring", "mul3", "ringw"])
+def test_dense_path_transient(name, bundles):
+    """A12: the reference's dense linear-solve path (make_dense_full_mna_solver, solver_factories.py:728-800:
+    ``solve(J + 1e-14 I, -f)``), the default for small circuits.  The oracle with ``linear_solver = "dense"``
+    reproduces the reference's dense-path transients; on the ring they differ from the sparse path's (67 accepted
+    steps against 64), and the 1e-14 regulariser alone accounts for it."""
+    from oracle.engine import OracleEngine
+
+    g = load(name)
+    t = tag(name, False, sparse=False)
+    if t + "_tran_times" not in g.files:
+        pytest.skip("no dense-path golden for this circuit")
+    o = OracleEngine(CIRCUITS[name](), bundles)
+    o.linear_solver = "dense"
+    times, V, st = o.run_transient()
+    ref_t, ref_V, ref_st = g[t + "_tran_times"], g[t + "_tran_V"], tran_stats(g, t)
+    n = st["n_steps"]
+    assert n == len(ref_t)
+    assert st["rejected_steps"] == int(ref_st["rejected_steps"])
+    assert st["total_nr_iterations"] == int(ref_st["total_nr_iterations"])
+    assert scaled_err(times[:n], ref_t, rel_floor=1e-30, abs_floor=1e-30) < 1e-9
+    assert float(np.max(np.abs(V[:n] - ref_V))) < 1e-8 * max(1.0, float(np.max(np.abs(ref_V))))
+    if name == "ring":
+        assert n == 67 and len(g[tag(name, False) + "_tran_times"]) == 64

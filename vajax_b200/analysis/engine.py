@@ -136,13 +136,20 @@ class B200Engine:
     def __init__(self, circuit: dict, bundles: Dict[str, dict], use_device_limiting: bool = False,
                  device: int = 0, use_device_graph: bool = False, pivot_tol: float = 1e-3, stream=None,
                  eval_slices: Optional[int] = None, eval_min_blocks: Optional[int] = None,
-                 lu_grid_div: Optional[int] = None):
+                 lu_grid_div: Optional[int] = None, linear_solver: str = "sparse"):
         """``stream``: None = the default CUDA stream; "own" = a private non-blocking stream, so that several
         engines (corners of a sweep) can run their device-resident loops concurrently on one GPU; or a
         ``torch.cuda.Stream``.  ``eval_slices`` / ``eval_min_blocks``: output slices and resident CTAs per SM of the
         model kernels (None = by instance count, cuda_emitter.default_slices / default_min_blocks).  A single
         c6288-sized transient wants the shortest chain (3 slices); a sweep with several corners in flight wants the
         smallest footprint per launch (1 slice, 4 CTAs per SM) so that the corners' model kernels overlap."""
+        # "sparse": the semantics of the reference's sparse solver paths (UMFPACK / cuDSS: plain J).  "dense": those of its
+        # dense path (A12, solver_factories.py:728-800, the reference's default for small circuits): J + 1e-14 I inside
+        # every NR solve - still factorised by the sparse GPU LU; the ring takes 67 accepted steps instead of 64 with it,
+        # as in the reference.
+        if linear_solver not in ("sparse", "dense"):
+            raise ValueError(f"linear_solver must be 'sparse' or 'dense', got {linear_solver!r}")
+        self.linear_solver = linear_solver
         self.eval_slices = eval_slices
         self.eval_min_blocks = eval_min_blocks
         self.lu_grid_div = lu_grid_div   # sweep tuning: persistent LU kernels take 1/div of the CTA slots (vjx_lu_set_grid_div)
@@ -561,7 +568,8 @@ class B200Engine:
             p1, n1 = self.vs_p.astype(np.int64) - 1, self.vs_n.astype(np.int64) - 1
             lin += [np.where(vp, p1 * n_aug + nu + br, 0), np.where(vn_, n1 * n_aug + nu + br, 0),
                     np.where(vp, (nu + br) * n_aug + p1, 0), np.where(vn_, (nu + br) * n_aug + n1, 0)]
-        di = np.arange(nu, dtype=np.int64)
+        # the dense path regularises every diagonal, so the branch rows get a (structurally new) diagonal slot
+        di = np.arange(n_aug if self.linear_solver == "dense" else nu, dtype=np.int64)
         lin.append(di * n_aug + di)
         self.unique_linear = np.unique(np.concatenate(lin))
         self.nse = len(self.unique_linear)
@@ -620,6 +628,8 @@ class B200Engine:
         vlib.check(lib.vjx_create(C.byref(cd), self.device, C.byref(self.handle)))
         if self.lu_grid_div:
             vlib.check(lib.vjx_lu_set_grid_div(self.handle, int(self.lu_grid_div)))
+        if self.linear_solver == "dense":
+            vlib.check(lib.vjx_set_dense_regularization(self.handle, 1e-14))
         self.timings["create"] = time.perf_counter() - t1
         self.timings["prepare"] = time.perf_counter() - t0
         self.cfg = cfg

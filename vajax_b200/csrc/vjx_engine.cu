@@ -241,7 +241,7 @@ __global__ void k_isrc(int n2, const int* __restrict__ dest, const double* __res
   q[3] = 0.0;
 }
 
-enum { SLOT_DIAG = 1, SLOT_NOI_ZERO = 2, SLOT_NOI_ONE = 4 };
+enum { SLOT_DIAG = 1, SLOT_NOI_ZERO = 2, SLOT_NOI_ONE = 4, SLOT_BRANCH_DIAG = 8 };
 
 // Segments longer than this are reduced by a whole CTA (supply-rail diagonals collect one
 // contribution per attached transistor: 10^4 at c6288 size, 10^5 at mul64 size).  Shorter ones are summed
@@ -276,12 +276,16 @@ __device__ __forceinline__ double block_max_256(double v, double* sh) {
 // (model order, instance, entry; vajax/analysis/mna_builder.py:953-958), then the diagonal
 // regularisation (:969) and the vsource incidence constants (:972-989).  With enforce_noi the
 // NOI rows/columns are rewritten as in solver_factories.py:1268-1276.
-__device__ __forceinline__ double finish_slot(double acc, unsigned char f, float c, double reg, int enforce_noi) {
+// dreg != 0 is the reference's DENSE linear-solve path (A12, make_dense_full_mna_solver.linear_solve,
+// solver_factories.py:784-788): J + dreg * I on every diagonal, node rows and branch rows alike, added where the
+// reference adds it - inside the NR solve, after the NOI rows were rewritten - and not in what build_system returns.
+__device__ __forceinline__ double finish_slot(double acc, unsigned char f, float c, double reg, int enforce_noi, double dreg) {
   if (f & SLOT_DIAG) acc += reg;
   if (c != 0.0f) acc += (double)c;
   if (enforce_noi) {
     if (f & SLOT_NOI_ZERO) acc = 0.0;
     if (f & SLOT_NOI_ONE) acc = 1.0;
+    if (dreg != 0.0 && (f & (SLOT_DIAG | SLOT_BRANCH_DIAG))) acc += dreg;
   }
   return acc;
 }
@@ -321,7 +325,7 @@ __device__ __forceinline__ bool long_seg_arrive(const LongSeg& L, int k, int* sh
 __global__ void __launch_bounds__(256) k_stamp_jacobian(int nse, const int* __restrict__ seg,
                                  const double* __restrict__ jsorted, const unsigned char* __restrict__ flags,
                                  const float* __restrict__ cst, const double* __restrict__ ctl, int enforce_noi,
-                                 LongSeg L, double* __restrict__ csr) {
+                                 LongSeg L, double* __restrict__ csr, double dreg) {
   __shared__ double sh[8];
   __shared__ int sh_flag;
   const double reg = ctl[VJX_CTL_DIAGREG] + ctl[VJX_CTL_GSHUNT];
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(256) k_stamp_jacobian(int nse, const int* __re
       for (int q = L.first[k] + threadIdx.x; q < L.first[k + 1]; q += 32) t += __ldcg(L.partial + q);
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
       const int s = L.seg_id[k];
-      if (threadIdx.x == 0) csr[s] = finish_slot(t, flags[s], cst[s], reg, enforce_noi);
+      if (threadIdx.x == 0) csr[s] = finish_slot(t, flags[s], cst[s], reg, enforce_noi, dreg);
     }
     return;
   }
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(256) k_stamp_jacobian(int nse, const int* __re
     if (e - b > VJX_LONG_SEG) continue;
     double acc = 0.0;
     for (int p = b; p < e; ++p) acc += jsorted[p];
-    csr[s] = finish_slot(acc, flags[s], cst[s], reg, enforce_noi);
+    csr[s] = finish_slot(acc, flags[s], cst[s], reg, enforce_noi, dreg);
   }
 }
 
@@ -2555,6 +2559,7 @@ struct vjx_handle {
   // LU
   bool lu_ready = false;
   int lu_grid_div = 0;   // > 1: persistent LU kernels take 1 / lu_grid_div of the SM slots (vjx_lu_set_grid_div)
+  double dense_reg = 0.0;   // != 0: the reference's dense linear-solve path, J + dense_reg * I (vjx_set_dense_regularization)
   VjxSymbolic sym;
   DevBuf<int> lu_ptr, lu_col, lu_diag, lu_src, lu_init, lu_kub, lu_order_u, lu_perm_r, lu_perm_c;
   long long ffi_id = 0;           // id handed out by vjx_handle_id (0 = none)
@@ -2856,6 +2861,10 @@ extern "C" int vjx_create(const vjx_circuit_desc* d, int device, vjx_handle** ou
     if (s < 0) return fail(VJX_ERR_INVALID, "diagonal entry missing from the CSR pattern");
     flags[s] |= SLOT_DIAG;
   }
+  for (int i = nu; i < h->n_aug; ++i) {   // present only when the caller put them into the pattern (dense-path mode)
+    int s = csr_find(h->h_indptr, h->h_indices, i, i);
+    if (s >= 0) flags[s] |= SLOT_BRANCH_DIAG;
+  }
   for (int v = 0; v < h->n_vs; ++v) {
     int p = d->vs_node_p[v], n = d->vs_node_n[v];
     if (p < 0 || p >= h->n_total || n < 0 || n >= h->n_total) return fail(VJX_ERR_INVALID, "vsource node out of range");
@@ -3143,7 +3152,8 @@ static int launch_eval(vjx_handle* h, const BuildPtrs& b, cudaStream_t s) {
 
 static void launch_stamp(vjx_handle* h, double* csr, int enforce_noi, cudaStream_t s) {
   k_stamp_jacobian<<<grid_for(h, h->nse) + h->long_slots.n_chunks, 256, 0, s>>>(
-      h->nse, h->jseg.p, h->jsorted.p, h->slot_flags.p, h->slot_const.p, h->ctl.p, enforce_noi, h->long_slots.dev(), csr);
+      h->nse, h->jseg.p, h->jsorted.p, h->slot_flags.p, h->slot_const.p, h->ctl.p, enforce_noi, h->long_slots.dev(), csr,
+      h->dense_reg);
   h->launches++;
 }
 
@@ -4072,6 +4082,19 @@ extern "C" int vjx_lu_set_grid_div(vjx_handle* h, int div) {
   if (!h || div < 1) return fail(VJX_ERR_INVALID, "bad grid divisor");
   if (h->lu_ready) return fail(VJX_ERR_INVALID, "vjx_lu_set_grid_div: the LU of this handle is already analysed");
   h->lu_grid_div = div;
+  return VJX_OK;
+}
+
+// A12: the reference's dense linear-solve path adds reg * I (1e-14) to the Jacobian inside every NR solve
+// (solver_factories.py:784-788).  Needs the branch rows' diagonal entries in the CSR pattern handed to vjx_create.
+// Call before the first solve of the handle (captured graphs hold the value).
+extern "C" int vjx_set_dense_regularization(vjx_handle* h, double reg) {
+  if (!h || !(reg >= 0.0)) return fail(VJX_ERR_INVALID, "bad dense regularisation");
+  if (reg != 0.0)
+    for (int i = h->n_unknowns; i < h->n_aug; ++i)
+      if (csr_find(h->h_indptr, h->h_indices, i, i) < 0)
+        return fail(VJX_ERR_INVALID, "vjx_set_dense_regularization: a branch row has no diagonal entry in the CSR pattern");
+  h->dense_reg = reg;
   return VJX_OK;
 }
 

@@ -98,7 +98,7 @@ class VjxInitArgs(C.Structure):
 EXPORTS = [
     "vjx_last_error", "vjx_version", "vjx_device_count", "vjx_create", "vjx_destroy", "vjx_clear_cache",
     "vjx_update_model_data", "vjx_update_sources", "vjx_build_system", "vjx_lu_solve", "vjx_lu_analyze",
-    "vjx_lu_stats", "vjx_lu_set_grid_div", "vjx_nr_solve", "vjx_nr_solve_async", "vjx_tran_begin", "vjx_tran_run", "vjx_tran_scalars", "vjx_tran_read",
+    "vjx_lu_stats", "vjx_lu_set_grid_div", "vjx_set_dense_regularization", "vjx_nr_solve", "vjx_nr_solve_async", "vjx_tran_begin", "vjx_tran_run", "vjx_tran_scalars", "vjx_tran_read",
     "vjx_tran_set_step_limit", "vjx_tran_set_save_list", "vjx_tran_run_ms", "vjx_tran_records", "vjx_tran_state", "vjx_time_phase", "vjx_lu_timeline", "vjx_launch_count",
     "vjx_sizes", "vjx_handle_id", "vjx_handle_from_id",
 ]
@@ -136,6 +136,7 @@ def load() -> C.CDLL:
     lib.vjx_lu_analyze.argtypes = [p, p, p]
     lib.vjx_lu_stats.argtypes = [p, p]
     lib.vjx_lu_set_grid_div.argtypes = [p, i]
+    lib.vjx_set_dense_regularization.argtypes = [p, d]
     lib.vjx_nr_solve.argtypes = [p, p, p, p, p, d, d, d, d, d, p, d, p, p, p, i, p, C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.POINTER(C.c_double), p, p, p, p, p, p]
     lib.vjx_nr_solve_async.argtypes = [p, p, p, p, p, d, d, d, d, d, p, d, p, p, p, i, p, p, p, p, p, p, p, p]
