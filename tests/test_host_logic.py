@@ -311,3 +311,50 @@ def test_reference_adapter_reproduces_the_circuit_description():
     lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 8 and all(ln["arrays_equal"] >= 5 for ln in lines), lines
     assert {ln["circuit"] for ln in lines} == {"rc", "clipper", "ring", "mul3"}
+
+
+def test_init_keys_shared_per_parameter_set():
+    """B200Engine._init_keys (set-up of a sweep corner): one tuple per distinct instance parameter set, equal to the
+    per-device formula (instance value, else model default, else 0)."""
+    import random
+
+    from vajax_b200.analysis.engine import B200Engine
+
+    rnd = random.Random(3)
+    names = [f"p{i}" for i in range(40)]
+    defaults = {f"p{i}": float(i) for i in range(0, 40, 2)}
+    sets = [{"p1": 1e-6, "p3": 2e-7}, {"p1": 1e-6, "p3": 2e-7, "p4": 5.0}, {"p2": 3, "type": -1.0}, {}]
+    devs = [{"name": f"m{i}", "params": dict(rnd.choice(sets))} for i in range(500)]
+    devs[7]["params"]["p5"] = [1.0]          # unhashable value: handled per device, float() raises as before
+    devs[7]["params"].pop("p5")
+    want = [tuple(float(d["params"][n]) if n in d["params"] else float(defaults.get(n, 0.0)) for n in names) for d in devs]
+    got = B200Engine._init_keys(devs, names, defaults)
+    assert got == want
+    assert len({id(k) for k in got}) <= len(sets)      # shared objects, one per distinct set
+    mixed = [{"params": {"a": 1.0, 3: 2.0}}]          # unorderable keys: falls back to the per-device path
+    assert B200Engine._init_keys(mixed, ["a"], {}) == [(1.0,)]
+
+
+def test_apply_corner_leaves_the_input_untouched_and_equals_a_deep_copy():
+    import copy
+
+    from vajax_b200.analysis import corners as cz
+    from vajax_b200.benchmarks import circuits
+
+    circ = circuits.multiplier_circuit(3, mos_model="psp103w")
+    src = circuits.source_mix_circuit(stop=6e-8)          # pwl sources: list-valued parameters
+    for c0 in (circ, src):
+        before = copy.deepcopy(c0)
+        for corner in cz.sweep_corners(64)[:5] + cz.monte_carlo_corners(2):
+            got = cz.apply_corner(c0, corner)
+            want = dict(c0)
+            want["devices"] = copy.deepcopy(c0["devices"])
+            cz.apply_process_corner(want["devices"], corner.process)
+            cz.apply_voltage_corner(want["devices"], corner.voltage)
+            assert got["devices"] == want["devices"]
+            assert c0["devices"] == before["devices"]                      # input untouched
+            for a, b in zip(got["devices"], c0["devices"]):               # nothing mutable is shared
+                assert a is not b and a["params"] is not b["params"] and a["nodes"] is not b["nodes"]
+                for k, v in a["params"].items():
+                    if isinstance(v, (list, dict)):
+                        assert v is not b["params"][k]

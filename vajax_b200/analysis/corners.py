@@ -170,10 +170,20 @@ def apply_voltage_corner(devices: List[Dict[str, Any]], corner: Optional[Voltage
             p["dc"] = float(p["dc"]) * corner.vdd_scale
 
 
+def _copy_device(d: Dict[str, Any]) -> Dict[str, Any]:
+    out = {k: (list(v) if isinstance(v, list) else dict(v) if isinstance(v, dict) else v) for k, v in d.items()}
+    prm = out.get("params")
+    if isinstance(prm, dict):
+        out["params"] = {k: (copy.deepcopy(v) if isinstance(v, (list, dict)) else v) for k, v in prm.items()}
+    return out
+
+
 def apply_corner(circuit: dict, corner: CornerConfig) -> dict:
     """A fresh circuit dict with the corner applied (the input is left untouched)."""
     c = dict(circuit)
-    c["devices"] = copy.deepcopy(circuit["devices"])
+    # per device: a new dict, a new params dict (the only thing the corner edits) and new node / value lists; a generic
+    # deepcopy of 10 k device dicts cost 0.45 s per corner, half of a c6288 corner's set-up after the first one
+    c["devices"] = [_copy_device(d) for d in circuit["devices"]]
     apply_process_corner(c["devices"], corner.process)
     apply_voltage_corner(c["devices"], corner.voltage)
     c["temperature_k"] = float(corner.temperature)

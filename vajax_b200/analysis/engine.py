@@ -258,8 +258,7 @@ class B200Engine:
             if len(names) == 0 or len(pairs) == 0:
                 out[mt] = (None, {None: list(pairs)})
                 continue
-            keys = [tuple(float(d["params"][n]) if n in d["params"] else float(defaults.get(n, 0.0)) for n in names)
-                    for d in devs]
+            keys = self._init_keys(devs, names, defaults)
             uniq = list(dict.fromkeys(keys))
             cols = [np.array([u[i] for u in uniq]) for i in range(len(names))]
             _, col = self._run_init(mt, cols, len(uniq))
@@ -269,6 +268,29 @@ class B200Engine:
                 table[u] = [pairs[i] for i in range(len(pairs)) if i < col.shape[1] and col[k, i] > 0.5]
             out[mt] = (keys, table)
         return out
+
+    @staticmethod
+    def _init_keys(devs: List[dict], names: List[str], defaults: Dict[str, Any]) -> List[tuple]:
+        """Per device, the tuple of init-parameter values (instance value, else model default, else 0) that keys its
+        collapse decision.  A PSP103-weight model has ~750 init parameters and a netlist only a handful of distinct
+        instance parameter sets, so the tuple is built once per distinct set (10,048 x 754 Python-level lookups per
+        corner were 70 % of a sweep corner's set-up time, scripts/prepare_timing.py)."""
+        cache: Dict[tuple, tuple] = {}
+        keys = []
+        for d in devs:
+            prm = d["params"]
+            try:
+                sig = tuple(sorted(prm.items()))
+                hash(sig)
+            except TypeError:          # unhashable / unorderable values: no sharing for this device
+                sig = None
+            k = cache.get(sig) if sig is not None else None
+            if k is None:
+                k = tuple(float(prm[n]) if n in prm else float(defaults.get(n, 0.0)) for n in names)
+                if sig is not None:
+                    cache[sig] = k
+            keys.append(k)
+        return keys
 
     @staticmethod
     def _collapse_roots(pairs, n_nodes):
