@@ -358,3 +358,31 @@ def test_apply_corner_leaves_the_input_untouched_and_equals_a_deep_copy():
                 for k, v in a["params"].items():
                     if isinstance(v, (list, dict)):
                         assert v is not b["params"][k]
+
+
+def test_emitted_source_cache_is_exact(bundles, monkeypatch):
+    """engine._emit_eval_cached returns what emit_eval_source returns, per key: arguments, layout and the VJX_EVAL_*
+    switches all take part in the key; the cached meta is handed out as a copy."""
+    from vajax_b200.analysis import engine as eng
+    from vajax_b200.codegen import cuda_emitter as em
+
+    b = bundles["psp103"]
+    kinds = b["param_kinds"]
+    shared = [i for i, k in enumerate(kinds) if k not in ("voltage", "prev_state", "new_state", "enable_lim", "enable_integration")]
+    varying = [i for i, k in enumerate(kinds) if k == "voltage"]
+    nc = len(b["init_mir_data"]["cache_mapping"])
+    lay1 = em.compute_eval_layout(b, shared, varying, list(range(nc)), [], {})
+    lay2 = em.compute_eval_layout(b, shared[1:], varying + shared[:1], list(range(nc)), [], {})
+    monkeypatch.delenv("VJX_EVAL_BLOCK", raising=False)
+    for lay in (lay1, lay2):
+        for ns, mb in ((1, 0), (3, 0), (1, 5)):
+            want = em.emit_eval_source(b, lay, False, n_slices=ns, min_blocks=mb)
+            for _ in range(2):
+                got = eng._emit_eval_cached(b, lay, False, ns, mb)
+                assert got[0] == want[0] and got[1] == want[1]
+            got[1]["n_slices"] = -1                              # a caller's edit must not leak into the cache
+            assert eng._emit_eval_cached(b, lay, False, ns, mb)[1] == want[1]
+    a = eng._emit_eval_cached(b, lay1, False, 1, 0)[0]
+    monkeypatch.setenv("VJX_EVAL_BLOCK", "64")
+    c = eng._emit_eval_cached(b, lay1, False, 1, 0)[0]
+    assert a != c and c == em.emit_eval_source(b, lay1, False, n_slices=1, min_blocks=0)[0]
